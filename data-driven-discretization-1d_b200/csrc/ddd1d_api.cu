@@ -1,0 +1,592 @@
+// C ABI of libddd1d (see include/ddd1d.h): handle management, packing of the
+// reference's TF-layout weights / NumPy tables into the on-chip constant blob,
+// launch planning and the kernel launches.  No torch types, no C++ exceptions
+// across the boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ddd1d.h"
+#include "ddd1d_device.cuh"
+
+using namespace ddd1d;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct HostLayer {
+  bool set = false;
+  int k = 0, cin = 0, cout = 0;
+  std::vector<float> kernel, bias;
+};
+
+}  // namespace
+
+struct ddd1d_handle {
+  ddd1d_config cfg;
+  Params P;
+  std::string error;
+  bool dirty = true;
+  bool have_stencils = false, have_projection = false;
+  std::vector<double> stencils;      // [D][7]
+  std::vector<double> nullspace;     // [C][7]
+  std::vector<int> input_sizes;      // [D]
+  HostLayer layers[kMaxLayers];
+  float* d_blob = nullptr;
+  float* d_fparams = nullptr;
+  float* d_fbasis = nullptr;
+  int forcing_batch = 0, forcing_P = 0, forcing_M = 0;
+  int threads = 0, blocks_per_sm = 0, num_sms = 0;
+  long long launches = 0;
+  // staging for the *_host entry points
+  void* d_stage_in = nullptr;
+  void* d_stage_out = nullptr;
+  int* d_stage_bad = nullptr;
+  size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_bad_bytes = 0;
+};
+
+namespace {
+
+int fail(ddd1d_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->error = buf;
+  g_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(h, DDD1D_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),      \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+int expected_derivatives(int equation, int variant) {
+  // equations.py DERIVATIVE_NAMES of the nine classes
+  static const int table[3][3] = {{2, 2, 3}, {2, 2, 3}, {3, 3, 4}};
+  return table[equation][variant];
+}
+
+int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+double plan_cost(int cout, int N, int nwarps, int cg, int pbt) {
+  int ncg = (cout + cg - 1) / cg;
+  int npb = (N + 127) / 128;
+  if (pbt == 2 && npb < 2) return 1e30;
+  int ntasks = ncg * ((npb + pbt - 1) / pbt);
+  int rounds = (ntasks + nwarps - 1) / nwarps;
+  // FFMAs per input channel + ~4 issue slots per shared-memory load
+  double per_ci = 20.0 * pbt * cg + 4.0 * (2.0 * pbt + 1.25 * cg);
+  return rounds * per_ci;
+}
+
+// Build P (plans, blob, shared-memory carve-up) from the host-side description.
+int finalize(ddd1d_handle* h) {
+  if (!h->dirty) return DDD1D_OK;
+  const ddd1d_config& c = h->cfg;
+  Params& P = h->P;
+  const int N = c.num_points;
+  const int D = c.num_derivatives;
+  if (!h->have_stencils && !(c.mode == DDD1D_MODE_LEARNED && c.projection != DDD1D_PROJ_NULLSPACE))
+    return fail(h, DDD1D_ESTATE, "ddd1d_set_stencils has not been called");
+
+  std::vector<float> blob;
+  P.nlayers = 0;
+  P.fast_conv = 0;
+  P.pitch = 0;
+  int chan_max = 0;
+  if (c.mode == DDD1D_MODE_LEARNED) {
+    const int K = c.kernel_size;
+    P.nlayers = c.num_layers;
+    P.K = K;
+    P.kleft = K / 2;                 // ceil((K-1)/2), layers.py:77
+    P.fast_conv = (K == 5 && (N % 4) == 0 && N >= 4) ? 1 : 0;
+    if (getenv("DDD1D_FORCE_GENERIC_CONV")) P.fast_conv = 0;
+    P.pitch = align_up(N + K - 1, 4);
+    h->threads = P.fast_conv ? std::min(512, 128 * ((N + 255) / 256)) : 256;
+    const int nwarps = h->threads / 32;
+    int cin = 1;
+    for (int l = 0; l < c.num_layers; ++l) {
+      const HostLayer& hl = h->layers[l];
+      const int want_out = (l == c.num_layers - 1) ? c.net_outputs : c.filter_size;
+      if (!hl.set) return fail(h, DDD1D_ESTATE, "ddd1d_set_layer(%d) has not been called", l);
+      if (hl.k != K || hl.cin != cin || hl.cout != want_out)
+        return fail(h, DDD1D_EINVAL, "layer %d has shape [%d,%d,%d], expected [%d,%d,%d]", l, hl.k,
+                    hl.cin, hl.cout, K, cin, want_out);
+      LayerPlan& L = P.layer[l];
+      L.cin = cin;
+      L.cout = hl.cout;
+      L.cout_pad = align_up(hl.cout, 8);
+      L.act = (l == c.num_layers - 1) ? DDD1D_ACT_NONE : c.activation;
+      L.w_off = (int)blob.size();
+      blob.resize(blob.size() + (size_t)cin * K * L.cout_pad, 0.f);
+      // TF kernel [k][ci][co] -> W[(ci*K + k)*cout_pad + co]
+      for (int k = 0; k < K; ++k)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int co = 0; co < hl.cout; ++co)
+            blob[L.w_off + ((size_t)ci * K + k) * L.cout_pad + co] =
+                hl.kernel[((size_t)k * cin + ci) * hl.cout + co];
+      L.b_off = (int)blob.size();
+      blob.resize(blob.size() + L.cout_pad, 0.f);
+      for (int co = 0; co < hl.cout; ++co) blob[L.b_off + co] = hl.bias[co];
+      // tile plan
+      double best = 1e30;
+      L.cg = 8; L.pbt = 1;
+      const int cgs[2] = {8, 4}, pbts[2] = {2, 1};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          double cost = plan_cost(L.cout, N, nwarps, cgs[a], pbts[b]);
+          if (cost < best) { best = cost; L.cg = cgs[a]; L.pbt = pbts[b]; }
+        }
+      chan_max = std::max(chan_max, std::max(cin, L.cout_pad));
+      cin = hl.cout;
+    }
+    P.C = c.net_outputs;
+    P.projection = c.projection;
+    P.S = c.stencil_size;
+    P.wshift = 3 - (c.stencil_size / 2);   // 3 - ceil((S-1)/2)
+    if (c.projection == DDD1D_PROJ_NULLSPACE) {
+      if (!h->have_projection) return fail(h, DDD1D_ESTATE, "ddd1d_set_projection has not been called");
+      int total = 0;
+      P.cstart[0] = 0;
+      for (int d = 0; d < D; ++d) {
+        total += h->input_sizes[d];
+        P.cstart[d + 1] = total;
+      }
+      for (int d = D; d < kMaxD; ++d) P.cstart[d + 1] = total;
+      if (total != c.net_outputs)
+        return fail(h, DDD1D_EINVAL, "sum(input_sizes)=%d but net_outputs=%d", total, c.net_outputs);
+      P.ns_off = (int)blob.size();
+      blob.resize(blob.size() + (size_t)c.net_outputs * kWinPad, 0.f);
+      for (int ch = 0; ch < c.net_outputs; ++ch)
+        for (int j = 0; j < kWin; ++j)
+          blob[P.ns_off + ch * kWinPad + j] = (float)h->nullspace[(size_t)ch * kWin + j];
+    } else {
+      if (c.net_outputs != D * c.stencil_size)
+        return fail(h, DDD1D_EINVAL, "raw projection needs net_outputs == D*S (%d != %d*%d)",
+                    c.net_outputs, D, c.stencil_size);
+      P.ns_off = 0;
+      for (int d = 0; d <= kMaxD; ++d) P.cstart[d] = 0;
+    }
+  } else {
+    h->threads = std::min(512, std::max(64, align_up(N, 32)));
+    P.K = 1; P.kleft = 0; P.C = 0; P.projection = 0; P.S = 0; P.wshift = 0; P.ns_off = 0;
+    for (int d = 0; d <= kMaxD; ++d) P.cstart[d] = 0;
+  }
+  // stencil / bias window table [kMaxD][8]
+  P.st_off = (int)blob.size();
+  blob.resize(blob.size() + kMaxD * kWinPad, 0.f);
+  if (h->have_stencils)
+    for (int d = 0; d < D; ++d)
+      for (int j = 0; j < kWin; ++j) blob[P.st_off + d * kWinPad + j] = (float)h->stencils[d * kWin + j];
+  blob.resize(align_up((int)blob.size(), 4), 0.f);
+
+  P.eq = c.equation * 3 + c.variant;
+  P.mode = c.mode;
+  P.N = N;
+  P.D = D;
+  P.weno_real = c.weno_real;
+  P.sigma = (float)c.standard_deviation;
+  P.eta = (float)c.eta;
+  P.inv_dx = (float)(1.0 / c.dx);
+  P.blob_floats = (int)blob.size();
+
+  // shared-memory carve-up
+  int off = 0;
+  P.off_bar = off; off += 16;
+  P.off_blob = off; off += P.blob_floats * 4;
+  P.off_ust = off; off += align_up((N + 2 * kHalo) * 4, 16);
+  P.off_ydbl = off; off += align_up(N * 8, 16);
+  P.off_k = off; off += align_up(kMaxStages * N * 4, 16);
+  P.off_flux = off; off += align_up((N + 1) * 4, 16);
+  P.off_fs = off; off += 2 * kMaxModes * 4;
+  P.off_act0 = off;
+  P.off_act1 = off;
+  if (c.mode == DDD1D_MODE_LEARNED) {
+    int bytes = align_up(chan_max * P.pitch * 4, 16);
+    P.off_act0 = off; off += bytes;
+    P.off_act1 = off; off += bytes;
+  }
+  P.smem_bytes = off;
+  if (P.smem_bytes > 227 * 1024)
+    return fail(h, DDD1D_EUNSUPPORTED,
+                "row of %d points with this net needs %d bytes of shared memory (limit 232448)", N,
+                P.smem_bytes);
+  P.use_bulk_copy = getenv("DDD1D_NO_BULK_COPY") ? 0 : 1;
+
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  if (h->d_blob) CUDA_TRY(h, cudaFree(h->d_blob));
+  CUDA_TRY(h, cudaMalloc(&h->d_blob, blob.size() * sizeof(float)));
+  CUDA_TRY(h, cudaMemcpy(h->d_blob, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  P.blob = h->d_blob;
+  P.fparams = h->d_fparams;
+  P.fbasis = h->d_fbasis;
+  P.P = h->forcing_batch > 0 ? h->forcing_P : 0;
+  P.M = h->forcing_M;
+  P.fcap = h->forcing_batch;
+
+  // launch shape
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
+  h->num_sms = prop.multiProcessorCount;
+  const void* fn = c.mode == DDD1D_MODE_LEARNED  ? (const void*)row_kernel<MODE_LEARNED>
+                   : c.mode == DDD1D_MODE_WENO   ? (const void*)row_kernel<MODE_WENO>
+                                                 : (const void*)row_kernel<MODE_STENCIL>;
+  CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+  int occ = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, h->threads, P.smem_bytes));
+  if (occ < 1) return fail(h, DDD1D_EUNSUPPORTED, "kernel does not fit on an SM (%d threads, %d B smem)",
+                           h->threads, P.smem_bytes);
+  h->blocks_per_sm = occ;
+  h->dirty = false;
+  return DDD1D_OK;
+}
+
+int launch(ddd1d_handle* h, Work& W, void* stream) {
+  int rc = finalize(h);
+  if (rc) return rc;
+  if (W.batch <= 0) return DDD1D_OK;
+  const ddd1d_config& c = h->cfg;
+  const Params& P = h->P;
+  if (c.equation == DDD1D_BURGERS && P.P > 0 && (W.op == OP_RHS || W.op == OP_INTEGRATE) &&
+      (W.sample_offset < 0 || W.sample_offset + W.batch > P.fcap))
+    return fail(h, DDD1D_EINVAL, "samples [%d, %d) exceed the %d forcing rows set", W.sample_offset,
+                W.sample_offset + W.batch, P.fcap);
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  const int grid = std::min(W.batch, h->num_sms * h->blocks_per_sm);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c.mode == DDD1D_MODE_LEARNED)
+    row_kernel<MODE_LEARNED><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+  else if (c.mode == DDD1D_MODE_WENO)
+    row_kernel<MODE_WENO><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+  else
+    row_kernel<MODE_STENCIL><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches += 1;
+  return DDD1D_OK;
+}
+
+Work blank_work() {
+  Work W;
+  memset(&W, 0, sizeof(W));
+  W.save_every = 1;
+  return W;
+}
+
+int ensure_stage(ddd1d_handle* h, void** buf, size_t* have, size_t need) {
+  if (*have >= need) return DDD1D_OK;
+  if (*buf) CUDA_TRY(h, cudaFree(*buf));
+  *buf = nullptr;
+  *have = 0;
+  CUDA_TRY(h, cudaMalloc(buf, need));
+  *have = need;
+  return DDD1D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddd1d_version(void) { return DDD1D_VERSION; }
+
+const char* ddd1d_last_error(const ddd1d_handle* handle) {
+  return handle ? handle->error.c_str() : g_error.c_str();
+}
+
+int ddd1d_create(const ddd1d_config* config, ddd1d_handle** out) {
+  if (!config || !out) return fail(nullptr, DDD1D_EINVAL, "null argument");
+  *out = nullptr;
+  if (config->struct_bytes != (int)sizeof(ddd1d_config))
+    return fail(nullptr, DDD1D_EINVAL, "ddd1d_config is %d bytes, library expects %d",
+                config->struct_bytes, (int)sizeof(ddd1d_config));
+  const ddd1d_config& c = *config;
+  if (c.equation < 0 || c.equation > 2 || c.variant < 0 || c.variant > 2)
+    return fail(nullptr, DDD1D_EINVAL, "unknown equation/variant %d/%d", c.equation, c.variant);
+  if (c.mode < 0 || c.mode > 2) return fail(nullptr, DDD1D_EINVAL, "unknown mode %d", c.mode);
+  if (c.num_points < 1) return fail(nullptr, DDD1D_EINVAL, "num_points must be positive");
+  if (c.num_derivatives != expected_derivatives(c.equation, c.variant))
+    return fail(nullptr, DDD1D_EINVAL, "equation %d/%d has %d derivative channels, got %d", c.equation,
+                c.variant, expected_derivatives(c.equation, c.variant), c.num_derivatives);
+  if (!(c.dx > 0)) return fail(nullptr, DDD1D_EINVAL, "dx must be positive");
+  if (c.mode == DDD1D_MODE_WENO && c.variant != DDD1D_GODUNOV)
+    return fail(nullptr, DDD1D_EINVAL, "WENO mode needs a Godunov-flux equation (integrate.py:320-321)");
+  if (c.mode == DDD1D_MODE_WENO && c.weno_real != DDD1D_REAL_F32)
+    return fail(nullptr, DDD1D_EUNSUPPORTED, "float64 WENO inside the row kernel is not built yet; "
+                "use ddd1d_weno_reconstruct for float64 reconstructions");
+  if (c.mode == DDD1D_MODE_LEARNED) {
+    if (c.num_layers < 1 || c.num_layers > kMaxLayers)
+      return fail(nullptr, c.num_layers == 0 ? DDD1D_EUNSUPPORTED : DDD1D_EINVAL,
+                  "num_layers=%d outside 1..%d", c.num_layers, kMaxLayers);
+    if (c.kernel_size < 1 || c.kernel_size > 15)
+      return fail(nullptr, DDD1D_EUNSUPPORTED, "kernel_size=%d outside 1..15", c.kernel_size);
+    if (c.filter_size < 1 || c.net_outputs < 1) return fail(nullptr, DDD1D_EINVAL, "bad net widths");
+    if (c.activation < 0 || c.activation > DDD1D_ACT_ELU)
+      return fail(nullptr, DDD1D_EINVAL, "unknown activation %d", c.activation);
+    if (c.projection < 0 || c.projection > DDD1D_PROJ_RAW_UNBIASED)
+      return fail(nullptr, DDD1D_EINVAL, "unknown projection %d", c.projection);
+    if (c.stencil_size < 1 || c.stencil_size > kWin)
+      return fail(nullptr, DDD1D_EUNSUPPORTED,
+                  "coefficient grid of %d points exceeds the %d-point window", c.stencil_size, kWin);
+    if (!(c.standard_deviation > 0)) return fail(nullptr, DDD1D_EINVAL, "standard_deviation must be positive");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || c.device < 0 || c.device >= ndev)
+    return fail(nullptr, DDD1D_ECUDA, "CUDA device %d unavailable (%s, %d devices)", c.device,
+                cudaGetErrorString(e), ndev);
+  ddd1d_handle* h = new ddd1d_handle();
+  h->cfg = c;
+  memset(&h->P, 0, sizeof(h->P));
+  *out = h;
+  return DDD1D_OK;
+}
+
+int ddd1d_destroy(ddd1d_handle* h) {
+  if (!h) return DDD1D_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->d_blob);
+  cudaFree(h->d_fparams);
+  cudaFree(h->d_fbasis);
+  cudaFree(h->d_stage_in);
+  cudaFree(h->d_stage_out);
+  cudaFree(h->d_stage_bad);
+  delete h;
+  return DDD1D_OK;
+}
+
+int ddd1d_set_stencils(ddd1d_handle* h, const double* w) {
+  if (!h || !w) return fail(h, DDD1D_EINVAL, "null argument");
+  h->stencils.assign(w, w + (size_t)h->cfg.num_derivatives * kWin);
+  h->have_stencils = true;
+  h->dirty = true;
+  return DDD1D_OK;
+}
+
+int ddd1d_set_layer(ddd1d_handle* h, int layer, const float* kernel, const float* bias, int kernel_size,
+                    int cin, int cout) {
+  if (!h || !kernel || !bias) return fail(h, DDD1D_EINVAL, "null argument");
+  if (h->cfg.mode != DDD1D_MODE_LEARNED) return fail(h, DDD1D_EINVAL, "handle has no conv net");
+  if (layer < 0 || layer >= h->cfg.num_layers)
+    return fail(h, DDD1D_EINVAL, "layer %d outside 0..%d", layer, h->cfg.num_layers - 1);
+  if (kernel_size < 1 || cin < 1 || cout < 1) return fail(h, DDD1D_EINVAL, "bad layer shape");
+  HostLayer& L = h->layers[layer];
+  L.set = true;
+  L.k = kernel_size; L.cin = cin; L.cout = cout;
+  L.kernel.assign(kernel, kernel + (size_t)kernel_size * cin * cout);
+  L.bias.assign(bias, bias + cout);
+  h->dirty = true;
+  return DDD1D_OK;
+}
+
+int ddd1d_set_projection(ddd1d_handle* h, const double* ns, const int* input_sizes) {
+  if (!h || !ns || !input_sizes) return fail(h, DDD1D_EINVAL, "null argument");
+  if (h->cfg.mode != DDD1D_MODE_LEARNED) return fail(h, DDD1D_EINVAL, "handle has no conv net");
+  int total = 0;
+  for (int d = 0; d < h->cfg.num_derivatives; ++d) {
+    if (input_sizes[d] < 0) return fail(h, DDD1D_EINVAL, "negative input size");
+    total += input_sizes[d];
+  }
+  if (total != h->cfg.net_outputs)
+    return fail(h, DDD1D_EINVAL, "sum(input_sizes)=%d but net_outputs=%d", total, h->cfg.net_outputs);
+  h->nullspace.assign(ns, ns + (size_t)total * kWin);
+  h->input_sizes.assign(input_sizes, input_sizes + h->cfg.num_derivatives);
+  h->have_projection = true;
+  h->dirty = true;
+  return DDD1D_OK;
+}
+
+int ddd1d_set_forcing(ddd1d_handle* h, const double* a, const double* omega, const double* k,
+                      const double* phi, int batch, int nparams, int resample_factor, int mean_resample,
+                      double period) {
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (h->d_fparams) { CUDA_TRY(h, cudaFree(h->d_fparams)); h->d_fparams = nullptr; }
+  if (h->d_fbasis) { CUDA_TRY(h, cudaFree(h->d_fbasis)); h->d_fbasis = nullptr; }
+  h->forcing_batch = 0; h->forcing_P = 0; h->forcing_M = 0;
+  h->dirty = true;
+  if (batch == 0) return DDD1D_OK;
+  if (!a || !omega || !k || !phi || batch < 0 || nparams < 1 || resample_factor < 1 || !(period > 0))
+    return fail(h, DDD1D_EINVAL, "bad forcing arguments");
+  const int N = h->cfg.num_points, P = nparams;
+  int M = 0;
+  for (size_t i = 0; i < (size_t)batch * P; ++i) {
+    double kk = k[i];
+    if (kk != std::floor(kk)) return fail(h, DDD1D_EINVAL, "forcing wavenumbers must be integers");
+    M = std::max(M, (int)std::fabs(kk));
+  }
+  if (M > kMaxModes) return fail(h, DDD1D_EUNSUPPORTED, "|k| up to %d supported, got %d", kMaxModes, M);
+  if (M == 0) M = 1;
+  std::vector<float> fp((size_t)batch * 4 * P);
+  for (int b = 0; b < batch; ++b)
+    for (int q = 0; q < P; ++q) {
+      size_t s = (size_t)b * P + q, base = (size_t)b * 4 * P;
+      fp[base + q] = (float)a[s];
+      fp[base + P + q] = (float)omega[s];
+      fp[base + 2 * P + q] = (float)phi[s];
+      fp[base + 3 * P + q] = (float)k[s];
+    }
+  // basis on the reference grid, resampled like Grid.resample (equations.py:65-68)
+  std::vector<float> basis((size_t)2 * M * N);
+  const int Nref = N * resample_factor;
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int m = 1; m <= M; ++m)
+    for (int x = 0; x < N; ++x) {
+      double cs = 0.0, sn = 0.0;
+      const int count = mean_resample ? resample_factor : 1;
+      for (int r = 0; r < count; ++r) {
+        double xr = period / Nref * (double)(x * resample_factor + r);
+        double th = two_pi * m * xr / period;
+        cs += std::cos(th);
+        sn += std::sin(th);
+      }
+      basis[(size_t)(m - 1) * N + x] = (float)(cs / count);
+      basis[(size_t)(M + m - 1) * N + x] = (float)(sn / count);
+    }
+  CUDA_TRY(h, cudaMalloc(&h->d_fparams, fp.size() * sizeof(float)));
+  CUDA_TRY(h, cudaMemcpy(h->d_fparams, fp.data(), fp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMalloc(&h->d_fbasis, basis.size() * sizeof(float)));
+  CUDA_TRY(h, cudaMemcpy(h->d_fbasis, basis.data(), basis.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->forcing_batch = batch; h->forcing_P = P; h->forcing_M = M;
+  return DDD1D_OK;
+}
+
+int ddd1d_rhs(ddd1d_handle* h, double t, const float* u, float* dudt, int batch, int sample_offset,
+              void* stream) {
+  if (!h || !u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
+  Work W = blank_work();
+  W.op = OP_RHS; W.batch = batch; W.sample_offset = sample_offset; W.u = u; W.out = dudt; W.t0 = t;
+  return launch(h, W, stream);
+}
+
+int ddd1d_rhs_f64(ddd1d_handle* h, double t, const double* u, double* dudt, int batch, int sample_offset,
+                  void* stream) {
+  if (!h || !u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
+  Work W = blank_work();
+  W.op = OP_RHS; W.batch = batch; W.sample_offset = sample_offset; W.u64 = u; W.out64 = dudt; W.t0 = t;
+  return launch(h, W, stream);
+}
+
+int ddd1d_coefficients(ddd1d_handle* h, const float* u, float* coefficients, int batch, void* stream) {
+  if (!h || !u || !coefficients) return fail(h, DDD1D_EINVAL, "null argument");
+  if (h->cfg.mode != DDD1D_MODE_LEARNED) return fail(h, DDD1D_EINVAL, "handle has no conv net");
+  Work W = blank_work();
+  W.op = OP_COEF; W.batch = batch; W.u = u; W.out = coefficients;
+  return launch(h, W, stream);
+}
+
+int ddd1d_space_derivatives(ddd1d_handle* h, const float* u, float* derivatives, int batch, void* stream) {
+  if (!h || !u || !derivatives) return fail(h, DDD1D_EINVAL, "null argument");
+  Work W = blank_work();
+  W.op = OP_DERIV; W.batch = batch; W.u = u; W.out = derivatives;
+  return launch(h, W, stream);
+}
+
+int ddd1d_integrate(ddd1d_handle* h, double t0, double dt, int num_steps, int save_every, int scheme,
+                    const float* u0, float* snapshots, int* first_bad_step, int batch, int sample_offset,
+                    void* stream) {
+  if (!h || !u0 || !snapshots) return fail(h, DDD1D_EINVAL, "null argument");
+  if (num_steps < 0 || save_every < 1) return fail(h, DDD1D_EINVAL, "bad step counts");
+  if (scheme < 0 || scheme > DDD1D_RK4) return fail(h, DDD1D_EINVAL, "unknown scheme %d", scheme);
+  Work W = blank_work();
+  W.op = OP_INTEGRATE; W.batch = batch; W.sample_offset = sample_offset; W.u = u0; W.snaps = snapshots;
+  W.first_bad = first_bad_step; W.t0 = t0; W.dt = dt; W.nsteps = num_steps; W.save_every = save_every;
+  W.scheme = scheme;
+  return launch(h, W, stream);
+}
+
+int ddd1d_rhs_host(ddd1d_handle* h, double t, const double* u, double* dudt, int batch, int sample_offset) {
+  if (!h || !u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
+  int rc = finalize(h);
+  if (rc) return rc;
+  const size_t bytes = (size_t)batch * h->cfg.num_points * sizeof(double);
+  if ((rc = ensure_stage(h, &h->d_stage_in, &h->stage_in_bytes, bytes))) return rc;
+  if ((rc = ensure_stage(h, &h->d_stage_out, &h->stage_out_bytes, bytes))) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage_in, u, bytes, cudaMemcpyHostToDevice, 0));
+  rc = ddd1d_rhs_f64(h, t, (const double*)h->d_stage_in, (double*)h->d_stage_out, batch, sample_offset,
+                     nullptr);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(dudt, h->d_stage_out, bytes, cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(h, cudaStreamSynchronize(0));
+  return DDD1D_OK;
+}
+
+int ddd1d_integrate_host(ddd1d_handle* h, double t0, double dt, int num_steps, int save_every, int scheme,
+                         const float* u0, float* snapshots, int* first_bad_step, int batch,
+                         int sample_offset) {
+  if (!h || !u0 || !snapshots) return fail(h, DDD1D_EINVAL, "null argument");
+  if (save_every < 1) return fail(h, DDD1D_EINVAL, "bad step counts");
+  int rc = finalize(h);
+  if (rc) return rc;
+  const size_t row = (size_t)batch * h->cfg.num_points * sizeof(float);
+  const size_t nsave = (size_t)(num_steps / save_every);
+  if ((rc = ensure_stage(h, &h->d_stage_in, &h->stage_in_bytes, row))) return rc;
+  if ((rc = ensure_stage(h, &h->d_stage_out, &h->stage_out_bytes, std::max<size_t>(row * nsave, 16)))) return rc;
+  void* bad = nullptr;
+  if (first_bad_step) {
+    if ((rc = ensure_stage(h, (void**)&h->d_stage_bad, &h->stage_bad_bytes, (size_t)batch * sizeof(int)))) return rc;
+    bad = h->d_stage_bad;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_stage_in, u0, row, cudaMemcpyHostToDevice, 0));
+  rc = ddd1d_integrate(h, t0, dt, num_steps, save_every, scheme, (const float*)h->d_stage_in,
+                       (float*)h->d_stage_out, (int*)bad, batch, sample_offset, nullptr);
+  if (rc) return rc;
+  if (nsave) CUDA_TRY(h, cudaMemcpyAsync(snapshots, h->d_stage_out, row * nsave, cudaMemcpyDeviceToHost, 0));
+  if (first_bad_step)
+    CUDA_TRY(h, cudaMemcpyAsync(first_bad_step, bad, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, 0));
+  CUDA_TRY(h, cudaStreamSynchronize(0));
+  return DDD1D_OK;
+}
+
+int ddd1d_weno_reconstruct(int device, int real, const void* u, void* left, void* right, int batch,
+                           int num_points, void* stream) {
+  if (!u || !left || !right || batch < 0 || num_points < 1)
+    return fail(nullptr, DDD1D_EINVAL, "bad argument");
+  if (batch == 0) return DDD1D_OK;
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = std::min(512, std::max(64, align_up(num_points, 32)));
+  const int grid = std::min(batch, 148 * 8);
+  if (real == DDD1D_REAL_F64) {
+    size_t smem = (size_t)(num_points + 7) * sizeof(double);
+    if (smem > 48 * 1024)
+      CUDA_TRY(nullptr, cudaFuncSetAttribute(weno_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    weno_kernel<double><<<grid, threads, smem, st>>>((const double*)u, (double*)left, (double*)right, batch, num_points);
+  } else if (real == DDD1D_REAL_F32) {
+    size_t smem = (size_t)(num_points + 7) * sizeof(float);
+    if (smem > 48 * 1024)
+      CUDA_TRY(nullptr, cudaFuncSetAttribute(weno_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    weno_kernel<float><<<grid, threads, smem, st>>>((const float*)u, (float*)left, (float*)right, batch, num_points);
+  } else {
+    return fail(nullptr, DDD1D_EINVAL, "unknown real type %d", real);
+  }
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+
+long long ddd1d_launch_count(const ddd1d_handle* h) { return h ? h->launches : 0; }
+
+int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* block, int* shared_bytes) {
+  ddd1d_handle* h = const_cast<ddd1d_handle*>(handle);
+  if (!h) return fail(nullptr, DDD1D_EINVAL, "null handle");
+  int rc = finalize(h);
+  if (rc) return rc;
+  if (grid) *grid = std::min(batch, h->num_sms * h->blocks_per_sm);
+  if (block) *block = h->threads;
+  if (shared_bytes) *shared_bytes = h->P.smem_bytes;
+  return DDD1D_OK;
+}
+
+}  // extern "C"

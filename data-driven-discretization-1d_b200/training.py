@@ -1,0 +1,53 @@
+"""Hyper-parameter defaults for the coefficient model -- the part of
+pde_superresolution/training.py the integration path depends on
+(create_hparams, training.py:40-165).  Training itself is out of scope."""
+import copy
+import json
+
+
+class HParams(object):
+  """Plain attribute bag standing in for tf.contrib.training.HParams."""
+
+  def __init__(self, **kwargs):
+    self.__dict__.update(kwargs)
+
+  def override_from_dict(self, values):
+    for name, value in values.items():
+      if name not in self.__dict__:
+        raise ValueError('Unknown hyperparameter: {}'.format(name))
+      setattr(self, name, value)
+    return self
+
+  def values(self):
+    return copy.deepcopy(self.__dict__)
+
+  def to_json(self):
+    return json.dumps(self.values(), sort_keys=True)
+
+  def __repr__(self):
+    return 'HParams({})'.format(', '.join('%s=%r' % kv for kv in sorted(self.__dict__.items())))
+
+
+_DEFAULTS = dict(
+    # dataset (training.py:126-131)
+    conservative=True, numerical_flux=False, equation_kwargs='{}', resample_factor=4,
+    # network (training.py:132-141)
+    model_target='coefficients', num_layers=3, filter_size=32, kernel_size=5, nonlinearity='relu',
+    polynomial_accuracy_order=1, polynomial_accuracy_scale=1.0, ensure_unbiased_coefficients=False,
+    coefficient_grid_min_size=6,
+    # optimisation / noise / loss (training.py:142-163): carried for checkpoint
+    # compatibility, unused by the integrator
+    base_batch_size=128, learning_rates=[1e-3, 1e-4], learning_stops=[20000, 40000],
+    frac_training=0.8, eval_interval=250, noise_probability=0.0, noise_amplitude=0.0,
+    noise_type='white', ground_truth_order=-1, num_time_steps=0, error_floor_quantile=0.1,
+    error_scale=[float('nan')], error_floor=[float('nan')], error_max=0.0,
+    absolute_error_weight=1.0, relative_error_weight=0.0, space_derivatives_weight=0.0,
+    time_derivative_weight=1.0, integrated_solution_weight=0.0,
+)
+
+
+def create_hparams(equation, **kwargs):
+  """Defaults of training.create_hparams (training.py:125-165) with overrides."""
+  hparams = HParams(equation=equation, **copy.deepcopy(_DEFAULTS))
+  hparams.override_from_dict(kwargs)
+  return hparams

@@ -1,0 +1,416 @@
+"""Parity of the CUDA path (through the C ABI, via ddd1d_b200.runtime.RowSolver ->
+ctypes -> libddd1d.so) against (a) fixtures minted from the reference's own code
+and (b) the NumPy oracle on the same seeded inputs.
+
+Tolerances (float32 arithmetic; the reference's TF graph is float32 too):
+  RHS_TOL   1e-5  relative L-inf of dy/dt, coefficients and derivatives per call
+            (BASELINE.md section 4);
+  TRAJ_TOL  1e-4  relative L-inf of a fixed-step trajectory vs the oracle's
+            fixed-step trajectory (float64 state on both sides).
+"""
+import numpy as np
+import pytest
+
+from oracle import pde_oracle as O
+from tests.helpers import KINDS, VARIANTS, net_from_json, rel_err, weights_from
+from tests import gpu_helpers as G
+
+pytestmark = pytest.mark.gpu
+
+RHS_TOL = 1e-5
+TRAJ_TOL = 1e-4
+
+
+def cpu(t):
+  return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------
+# per-call parity: coefficients, derivatives, dy/dt
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('variant', VARIANTS)
+@pytest.mark.parametrize('n', (32, 64))
+def test_learned_against_reference_fixture(golden, kind, variant, n):
+  from ddd1d_b200 import model, integrate
+  g = golden('learned')
+  key = 'default/%s/%s/%d' % (kind, variant, n)
+  hp = G.product_hparams(kind, variant, n)
+  w = weights_from(g, key)
+  u = g[key + '/u']
+  assert rel_err(cpu(model.predict_coefficients(u, hp, w)), g[key + '/coefficients']) < RHS_TOL
+  assert rel_err(cpu(model.predict_space_derivatives(u, hp, w)), g[key + '/space_derivatives']) < RHS_TOL
+  assert rel_err(cpu(model.predict_time_derivative(u, hp, w)), g[key + '/time_derivative']) < RHS_TOL
+  # the Differentiator surface SciPy calls (adds forcing for Burgers)
+  eq = G.product_equation(kind, variant, n, seed=7)
+  d = integrate.SavedModelDifferentiator(w, eq, hp)
+  got = d(float(g[key + '/t']), u[0].astype(np.float64))
+  assert got.dtype == np.float64
+  assert rel_err(got, g[key + '/differentiator']) < RHS_TOL
+
+
+def test_learned_hparam_variants_against_reference_fixture(golden):
+  from ddd1d_b200 import model
+  g = golden('learned')
+  names = sorted({k.split('/')[0] for k in g.files} - {'default'})
+  for name in names:
+    for variant in ('plain', 'conservative'):
+      key = '%s/burgers/%s/32' % (name, variant)
+      if key + '/u' not in g.files:
+        continue
+      overrides = dict(__import__('json').loads(str(g[key + '/hparams'])))
+      hp = G.product_hparams('burgers', variant, 32, **overrides)
+      w = weights_from(g, key)
+      u = g[key + '/u']
+      assert rel_err(cpu(model.predict_coefficients(u, hp, w)), g[key + '/coefficients']) < RHS_TOL, key
+      assert rel_err(cpu(model.predict_time_derivative(u, hp, w)), g[key + '/time_derivative']) < RHS_TOL, key
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_baseline_against_reference_fixture(golden, kind, variant):
+  from ddd1d_b200 import model, integrate
+  g = golden('baseline')
+  key = '%s/%s/32' % (kind, variant)
+  eq = G.product_equation(kind, variant, 32, seed=11)
+  u = g[key + '/u']
+  for acc in (1, 3):
+    sd = model.baseline_space_derivatives(u, eq, acc)
+    assert rel_err(cpu(sd), g['%s/acc%d/space_derivatives' % (key, acc)]) < RHS_TOL
+    d = integrate.PolynomialDifferentiator(eq, acc)
+    assert rel_err(d(1.25, u[0].astype(np.float64)), g['%s/acc%d/differentiator' % (key, acc)]) < RHS_TOL
+    named = d.calculate_space_derivatives(u[0])
+    assert sorted(named) == sorted(eq.DERIVATIVE_NAMES)
+
+
+def test_weno_against_reference_fixture(golden):
+  from ddd1d_b200 import weno, model, integrate, equations
+  g = golden('pointwise')
+  u = g['weno/u']
+  left, right = weno.reconstruct_left(u), weno.reconstruct_right(u)       # float64 kernel
+  np.testing.assert_allclose(left, g['weno/left'], rtol=1e-12, atol=1e-12)
+  np.testing.assert_allclose(right, g['weno/right'], rtol=1e-12, atol=1e-12)
+  l32, r32 = weno.reconstruct_both(u.astype(np.float32))                  # float32 kernel
+  np.testing.assert_allclose(l32, g['weno/left_f32'], rtol=0, atol=3e-5)
+  np.testing.assert_allclose(r32, g['weno/right_f32'], rtol=0, atol=3e-5)
+  # the "exact" dispatch of baseline_space_derivatives (WENO in float32, model.py:81-97)
+  gb = golden('baseline')
+  eq = equations.GodunovBurgersEquation(32, random_seed=11)
+  sd = model.baseline_space_derivatives(gb['burgers/godunov/32/exact/u'], eq, None)
+  assert rel_err(cpu(sd), gb['burgers/godunov/32/exact/space_derivatives']) < 2e-5
+  # WENODifferentiator (integrate.py:124-140); the reference runs the reconstruction in
+  # float64, this build in float32 -> looser tolerance, stated
+  gt = golden('trajectories')
+  eqw = equations.GodunovBurgersEquation(64, random_seed=1)
+  d = integrate.WENODifferentiator(eqw)
+  assert rel_err(d(0.4, gt['weno_burgers/rhs_u']), gt['weno_burgers/rhs']) < 2e-5
+
+
+# ---------------------------------------------------------------------------------
+# trajectories
+# ---------------------------------------------------------------------------------
+def _fixed_step_case(kind, variant, n, batch, steps, dt, mode, seed=0, scheme='rk3', tol=TRAJ_TOL):
+  from ddd1d_b200 import integrate
+  eqs = [G.product_equation(kind, variant, n, seed=s) for s in range(batch)]
+  oeqs = [G.oracle_equation(kind, variant, n, seed=s) for s in range(batch)]
+  u0 = G.smooth_rows(batch, n, seed=seed)
+  if mode == 'learned':
+    net = O.NetSpec()
+    w = O.glorot_weights(oeqs[0], net, seed=seed + 1, last_layer_scale=0.01)
+    solver = integrate.BatchIntegrator.learned(eqs, G.product_hparams(kind, variant, n), w)
+    rhs = O.batched_rhs(oeqs, net, w, mode='learned')
+  elif mode == 'fd':
+    solver = integrate.BatchIntegrator.baseline(eqs, 1)
+    rhs = O.batched_rhs(oeqs, mode='fd', accuracy_order=1)
+  else:
+    solver = integrate.BatchIntegrator.weno(eqs)
+    rhs = O.batched_rhs(oeqs, mode='weno', weno_dtype=np.float32)
+  save_every = max(1, steps // 2)
+  got, bad = solver.integrate(u0, 0.1, dt, steps, save_every, scheme, return_first_bad=True)
+  want = O.fixed_step_integrate(rhs, u0, 0.1, dt, steps, save_every, scheme=scheme)
+  assert got.shape == want.shape
+  assert (cpu(bad) == -1).all()
+  err = rel_err(cpu(got), want)
+  assert err < tol, (kind, variant, mode, err)
+  return err
+
+
+@pytest.mark.parametrize('kind,dt', (('burgers', 1e-3), ('kdv', 2.5e-5), ('ks', 1e-5)))
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_fixed_step_learned(kind, dt, variant):
+  _fixed_step_case(kind, variant, 64, 5, 40, dt, 'learned')
+
+
+@pytest.mark.parametrize('kind,dt', (('burgers', 1e-3), ('kdv', 2.5e-5), ('ks', 1e-5)))
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_fixed_step_baseline(kind, dt, variant):
+  _fixed_step_case(kind, variant, 64, 5, 60, dt, 'fd')
+
+
+@pytest.mark.parametrize('kind,dt', (('burgers', 1e-3), ('kdv', 2.5e-5), ('ks', 1e-5)))
+def test_fixed_step_weno(kind, dt):
+  _fixed_step_case(kind, 'godunov', 64, 5, 60, dt, 'weno', tol=2e-4)
+
+
+@pytest.mark.parametrize('scheme', ('midpoint', 'euler', 'rk4'))
+def test_other_schemes(scheme):
+  _fixed_step_case('burgers', 'plain', 32, 3, 30, 1e-3, 'learned', scheme=scheme)
+
+
+def test_scipy_driven_c1_matches_reference_fixture(golden):
+  """BASELINE config 1: Burgers FD accuracy 1, N=64, T=2 through the reference's
+  own driver loop (SciPy RK23, max_step=0.01) with the GPU Differentiator."""
+  from ddd1d_b200 import integrate, equations
+  g = golden('trajectories')
+  for tag, seed in (('c1', 0), ('c1_seed2', 2)):
+    eq = equations.BurgersEquation(64, random_seed=seed)
+    ds = integrate.integrate_baseline(eq, times=g['c1/times'])
+    y = np.asarray(ds['y'].data)
+    assert int(np.asarray(ds['num_evals'].data if hasattr(ds['num_evals'], 'data') else ds['num_evals'])) == int(g[tag + '/nfev'])
+    np.testing.assert_allclose(y, g[tag + '/y'], rtol=0, atol=5e-5)
+    assert abs(y.mean(axis=1)).max() < 1e-3          # integrate_test.py:182-185
+
+
+def test_scipy_driven_learned_matches_reference_fixture(golden):
+  from ddd1d_b200 import integrate, equations
+  g = golden('trajectories')
+  eq = equations.BurgersEquation(32, random_seed=4)
+  w = weights_from(g, 'learned_burgers')
+  d = integrate.SavedModelDifferentiator(w, eq, G.product_hparams('burgers', 'plain', 32))
+  y, nfev = integrate.odeint(eq.initial_value(), d, g['learned_burgers/times'])
+  assert nfev == int(g['learned_burgers/nfev'])
+  np.testing.assert_allclose(y, g['learned_burgers/y'], rtol=0, atol=5e-5)
+  eq = equations.KdVEquation(32, random_seed=2)
+  w = weights_from(g, 'learned_kdv')
+  d = integrate.SavedModelDifferentiator(w, eq, G.product_hparams('kdv', 'plain', 32))
+  y, nfev = integrate.odeint(eq.initial_value(), d, g['learned_kdv/times'])
+  assert nfev == int(g['learned_kdv/nfev'])
+  np.testing.assert_allclose(y, g['learned_kdv/y'], rtol=0, atol=1e-4)
+
+
+def test_fixed_step_c1_twin_matches_scipy_fixture(golden):
+  """The fused fixed-step kernel (dt=0.01, 200 steps) lands on the reference's adaptive
+  result for C1 within SciPy's own tolerance (rtol=1e-3): the controller sits at max_step."""
+  from ddd1d_b200 import integrate, equations
+  g = golden('trajectories')
+  eqs = [equations.BurgersEquation(64, random_seed=s) for s in (0, 2)]
+  ds = integrate.BatchIntegrator.baseline(eqs, 1).integrate_times(times=g['c1/times'], dt=0.01)
+  y = np.asarray(ds['y'].data)
+  assert y.shape == (2, 5, 64)
+  np.testing.assert_allclose(y[0], g['c1/y'], rtol=0, atol=5e-4)
+  np.testing.assert_allclose(y[1], g['c1_seed2/y'], rtol=0, atol=5e-4)
+
+
+# ---------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties + oracle on a row subset
+# ---------------------------------------------------------------------------------
+def _c2_solver(batch, n=256):
+  from ddd1d_b200 import integrate
+  eqs = [G.product_equation('burgers', 'plain', n, seed=s) for s in range(batch)]
+  oeq = G.oracle_equation('burgers', 'plain', n)
+  w = O.glorot_weights(oeq, O.NetSpec(), seed=0, last_layer_scale=0.01)
+  return integrate.BatchIntegrator.learned(eqs, G.product_hparams('burgers', 'plain', n), w), w
+
+
+def test_c2_full_batch_properties():
+  """BASELINE config 2 shape (Burgers learned, N=256, batch=4096), short run."""
+  import torch
+  batch, n, steps = 4096, 256, 6
+  solver, w = _c2_solver(batch, n)
+  u0 = G.smooth_rows(batch, n, seed=5)
+  full = solver.integrate(u0, 0.0, 1e-3, steps, steps)[0]
+  assert torch.isfinite(full).all()
+  # (1) a row's trajectory does not depend on the rest of the batch or on the CTA it lands on
+  pick = [0, 1, 147, 148, 149, 2047, 4095]
+  for i in pick:
+    alone = solver.integrate(u0[i:i + 1], 0.0, 1e-3, steps, steps, sample_offset=i)[0, 0]
+    assert torch.equal(alone, full[i]), i
+  # (2) oracle on the same subset
+  oeqs = [G.oracle_equation('burgers', 'plain', n, seed=i) for i in pick]
+  rhs = O.batched_rhs(oeqs, O.NetSpec(), w, mode='learned')
+  want = O.fixed_step_integrate(rhs, u0[pick], 0.0, 1e-3, steps, steps)[0]
+  assert rel_err(cpu(full[pick]), want) < TRAJ_TOL
+  # (3) determinism
+  again = solver.integrate(u0, 0.0, 1e-3, steps, steps)[0]
+  assert torch.equal(again, full)
+
+
+def test_coefficients_satisfy_accuracy_constraints_at_full_size():
+  """polynomials_test.py:94-104 lifted to the network output: A @ coef == b at every
+  grid point of a [4096, 256] batch."""
+  from ddd1d_b200 import model, polynomials, runtime
+  n, batch = 256, 4096
+  hp = G.product_hparams('burgers', 'plain', n)
+  eq = G.product_equation('burgers', 'plain', n)
+  oeq = G.oracle_equation('burgers', 'plain', n)
+  w = O.glorot_weights(oeq, O.NetSpec(), seed=3, last_layer_scale=0.1)
+  coefs = model.predict_coefficients(G.smooth_rows(batch, n, seed=9), hp, w)
+  assert tuple(coefs.shape) == (batch, n, 2, 7)
+  grid = runtime.coefficient_grid(eq, hp)
+  import torch
+  for d, order in enumerate(eq.DERIVATIVE_ORDERS):
+    a, b = polynomials.constraints(grid, polynomials.Method.FINITE_DIFFERENCES, order, 1)
+    a_t = torch.as_tensor(a, device=coefs.device, dtype=torch.float64)
+    resid = coefs[:, :, d, :].double() @ a_t.T - torch.as_tensor(b, device=coefs.device)
+    scale = (coefs[:, :, d, :].double().abs() @ a_t.abs().T).max()
+    assert float(resid.abs().max() / scale) < 1e-5
+
+
+def test_translation_equivariance_and_conservation():
+  """Unforced equations commute with periodic shifts; conservative forms keep sum(u)."""
+  import torch
+  from ddd1d_b200 import integrate
+  n, batch = 128, 64
+  for kind, dt in (('kdv', 2.5e-5), ('ks', 1e-5)):
+    for variant in VARIANTS:
+      eqs = [G.product_equation(kind, variant, n)]
+      oeq = G.oracle_equation(kind, variant, n)
+      w = O.glorot_weights(oeq, O.NetSpec(), seed=1, last_layer_scale=0.01)
+      solver = integrate.BatchIntegrator.learned(eqs, G.product_hparams(kind, variant, n), w)
+      u0 = torch.as_tensor(G.smooth_rows(batch, n, seed=2)).cuda()
+      y = solver.integrate(u0, 0.0, dt, 10, 10)[0]
+      y_shift = solver.integrate(torch.roll(u0, 17, dims=1), 0.0, dt, 10, 10)[0]
+      assert torch.equal(torch.roll(y, 17, dims=1), y_shift), (kind, variant)
+      if variant != 'plain':
+        drift = (y.double().sum(dim=1) - u0.double().sum(dim=1)).abs().max()
+        assert float(drift) < 5e-4 * n, (kind, variant, float(drift))
+
+
+@pytest.mark.parametrize('kind,n,dt', (('kdv', 128, 2.5e-5), ('ks', 512, 1e-5)))
+def test_c3_c4_shapes_against_oracle(kind, n, dt):
+  """BASELINE configs 3 and 4 (KdV N=128, KS N=512): per-GPU shard shape, oracle on a subset."""
+  import torch
+  from ddd1d_b200 import integrate
+  batch, steps = 4096, 4
+  eqs = [G.product_equation(kind, 'plain', n)]
+  oeq = G.oracle_equation(kind, 'plain', n)
+  w = O.glorot_weights(oeq, O.NetSpec(), seed=2, last_layer_scale=0.01)
+  solver = integrate.BatchIntegrator.learned(eqs, G.product_hparams(kind, 'plain', n), w)
+  rs = np.random.RandomState(0)
+  u0 = np.stack([O.EquationSpec(kind, num_points=n, random_seed=int(s)).initial_value()
+                 for s in rs.randint(0, 1000, size=8)]).astype(np.float32)
+  u0 = np.tile(u0, (batch // 8, 1))
+  got = solver.integrate(u0, 0.0, dt, steps, steps)[0]
+  assert torch.isfinite(got).all()
+  rhs = O.batched_rhs([oeq], O.NetSpec(), w, mode='learned')
+  want = O.fixed_step_integrate(rhs, u0[:8], 0.0, dt, steps, steps)[0]
+  assert rel_err(cpu(got[:8]), want) < TRAJ_TOL
+  assert torch.equal(got[:8], got[batch - 8:])
+
+
+def test_c5_weno_shape_against_oracle():
+  """BASELINE config 5 row shape (WENO5 Godunov Burgers, N=2048), reduced batch."""
+  import torch
+  from ddd1d_b200 import integrate
+  n, batch, steps, dt = 2048, 512, 6, 1e-4
+  eqs = [G.product_equation('burgers', 'godunov', n, seed=s) for s in range(batch)]
+  solver = integrate.BatchIntegrator.weno(eqs)
+  u0 = G.smooth_rows(batch, n, seed=4)
+  got = solver.integrate(u0, 0.0, dt, steps, steps)[0]
+  assert torch.isfinite(got).all()
+  pick = [0, 255, 511]
+  oeqs = [G.oracle_equation('burgers', 'godunov', n, seed=i) for i in pick]
+  rhs = O.batched_rhs(oeqs, mode='weno', weno_dtype=np.float32)
+  want = O.fixed_step_integrate(rhs, u0[pick], 0.0, dt, steps, steps)[0]
+  assert rel_err(cpu(got[pick]), want) < 2e-4
+
+
+# ---------------------------------------------------------------------------------
+# edge cases and error behaviour
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', (8, 30, 50, 200))
+def test_odd_sizes_use_generic_path(n):
+  """N not a multiple of 4 (and tiny N) exercise the generic conv path; N=200 is the
+  reference's own test size (integrate_test.py:129-198)."""
+  from ddd1d_b200 import model
+  for kind, variant in (('burgers', 'plain'), ('ks', 'godunov')):
+    hp = G.product_hparams(kind, variant, n)
+    oeq = G.oracle_equation(kind, variant, n)
+    w = O.glorot_weights(oeq, O.NetSpec(), seed=n, last_layer_scale=0.1, bias_scale=0.1)
+    u = G.smooth_rows(3, n, seed=n)
+    assert rel_err(cpu(model.predict_coefficients(u, hp, w)), O.predict_coefficients(u, oeq, O.NetSpec(), w)) < RHS_TOL
+    assert rel_err(cpu(model.predict_time_derivative(u, hp, w)),
+                   O.predict_time_derivative(u, oeq, O.NetSpec(), w)) < RHS_TOL
+
+
+def test_fast_and_generic_conv_paths_agree(monkeypatch):
+  from ddd1d_b200 import model
+  n = 64
+  hp = G.product_hparams('kdv', 'conservative', n)
+  oeq = G.oracle_equation('kdv', 'conservative', n)
+  w = O.glorot_weights(oeq, O.NetSpec(), seed=5, last_layer_scale=0.1, bias_scale=0.1)
+  u = G.smooth_rows(4, n, seed=1)
+  fast = cpu(model.predict_time_derivative(u, hp, w))
+  model._SOLVERS.clear()
+  monkeypatch.setenv('DDD1D_FORCE_GENERIC_CONV', '1')
+  monkeypatch.setenv('DDD1D_NO_BULK_COPY', '1')
+  slow = cpu(model.predict_time_derivative(u, hp, w))
+  model._SOLVERS.clear()
+  assert rel_err(fast, slow) < 2e-6
+
+
+def test_empty_single_and_oversubscribed_batches():
+  import torch
+  from ddd1d_b200 import integrate, equations
+  eq = equations.KdVEquation(64)
+  solver = integrate.BatchIntegrator.baseline([eq], 1)
+  empty = solver.integrate(np.zeros((0, 64), np.float32), 0.0, 1e-5, 4, 2)
+  assert tuple(empty.shape) == (2, 0, 64)
+  one = solver.integrate(eq.initial_value()[None], 0.0, 1e-5, 4, 2)
+  many = solver.integrate(np.tile(eq.initial_value()[None], (5000, 1)), 0.0, 1e-5, 4, 2)
+  assert torch.equal(many[:, 0], one[:, 0]) and torch.equal(many[:, 4999], one[:, 0])
+  # num_steps not a multiple of save_every: floor(num_steps / save_every) snapshots
+  assert tuple(solver.integrate(eq.initial_value()[None], 0.0, 1e-5, 5, 2).shape) == (2, 1, 64)
+
+
+def test_divergence_is_data_not_an_error():
+  """Unstable step: rows go non-finite, first_bad_step says when, integrate_times NaN-pads
+  (integrate.py:161-167)."""
+  from ddd1d_b200 import integrate, equations
+  eqs = [equations.KSEquation(64, random_seed=s) for s in range(3)]
+  solver = integrate.BatchIntegrator.baseline(eqs, 1)
+  u0 = solver.initial_values()
+  snaps, bad = solver.integrate(u0, 0.0, 1e-2, 200, 50, return_first_bad=True)   # dt far too large
+  bad = cpu(bad)
+  assert (bad >= 0).all() and (bad < 200).all()
+  assert not np.isfinite(cpu(snaps[-1])).any()
+  ds = solver.integrate_times(u0, times=np.linspace(0, 2, 5), dt=1e-2)
+  y = np.asarray(ds['y'].data)
+  assert np.isfinite(y[:, 0]).all() and np.isnan(y[:, -1]).all()
+  stable = integrate.BatchIntegrator.baseline(eqs, 1).integrate(u0, 0.0, 1e-5, 20, 20, return_first_bad=True)
+  assert (cpu(stable[1]) == -1).all()
+
+
+def test_argument_errors_mirror_the_reference():
+  from ddd1d_b200 import model, integrate, equations, runtime
+  hp = G.product_hparams('burgers', 'plain', 32)
+  oeq = G.oracle_equation('burgers', 'plain', 32)
+  w = O.glorot_weights(oeq, O.NetSpec(), seed=0)
+  with pytest.raises(ValueError):                      # model.py:53-56
+    model.predict_coefficients(np.zeros((2, 48), np.float32), hp, w)
+  with pytest.raises(ValueError):                      # wrong weight shapes
+    model.predict_coefficients(np.zeros((2, 32), np.float32), hp, w[:-1])
+  with pytest.raises(ValueError):                      # integrate.py:320-321
+    integrate.integrate_weno(equations.BurgersEquation(32))
+  with pytest.raises(ValueError):                      # more rows than forcing samples
+    integrate.BatchIntegrator.baseline([equations.BurgersEquation(32)], 1).integrate(
+        np.zeros((2, 32), np.float32), 0.0, 1e-3, 1)
+  with pytest.raises(NotImplementedError):             # coefficient_grid_min_size=9 -> 9-point stencil
+    runtime.learned_solver(equations.BurgersEquation(32),
+                           G.product_hparams('burgers', 'plain', 32, coefficient_grid_min_size=9),
+                           O.glorot_weights(oeq, O.NetSpec(coefficient_grid_min_size=9), seed=0))
+
+
+def test_host_buffer_entry_points():
+  """ddd1d_integrate_host / ddd1d_rhs_host: NumPy in, NumPy out (copies inside the library)."""
+  from ddd1d_b200 import integrate, equations
+  eqs = [equations.BurgersEquation(64, random_seed=s) for s in range(4)]
+  solver = integrate.BatchIntegrator.baseline(eqs, 1).solver
+  u0 = G.smooth_rows(4, 64, seed=3)
+  snaps, bad = solver.integrate_host(u0, 0.0, 1e-3, 10, 5)
+  dev = solver.integrate(u0, 0.0, 1e-3, 10, 5)
+  np.testing.assert_array_equal(snaps, cpu(dev))
+  assert (bad == -1).all()
+  r = solver.rhs_host(0.3, u0.astype(np.float64))
+  np.testing.assert_array_equal(r, cpu(solver.rhs(0.3, u0)).astype(np.float64))
+  assert solver.launch_count() >= 3
