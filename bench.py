@@ -103,6 +103,30 @@ class ClockSampler(object):
             'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def usable_cores():
+  """Host threads this process may really use: min(cpu_count, affinity mask, cgroup quota)."""
+  n = os.cpu_count() or 1
+  try:
+    n = min(n, len(os.sched_getaffinity(0)))
+  except (AttributeError, OSError):
+    pass
+  for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+    try:
+      with open(path) as f:
+        fields = f.read().split()
+      if path.endswith('cpu.max'):
+        if fields[0] != 'max':
+          n = min(n, max(1, int(int(fields[0]) / int(fields[1]))))
+      else:
+        quota = int(fields[0])
+        if quota > 0:
+          with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as g:
+            n = min(n, max(1, quota // int(g.read().split()[0])))
+    except (OSError, ValueError, IndexError):
+      continue
+  return n
+
+
 def build_case(workload, batch, seed_offset=0):
   import ddd1d_b200 as ddd
   from oracle import pde_oracle as O     # weights only: deterministic Glorot init shared with the tests
@@ -177,16 +201,15 @@ def _cpu_one_sample(args):
   return int(sol.nfev)
 
 
-def cpu_reference_rate(workload, rk_steps, samples, processes):
+def cpu_reference_rate(workload, rk_steps, samples, processes, pool=None):
   """grid-point-steps/sec of the CPU path: `samples` independent samples, one
-  solve_ivp each (the reference's execution model), `processes` worker processes."""
+  solve_ivp each (the reference's execution model), on `processes` worker processes.
+  The pool (if any) is created by the caller so its start-up is not timed."""
   kind, variant, n, _, dt, mode = WORKLOADS[workload]
   jobs = [(workload, s, rk_steps) for s in range(samples)]
   t0 = time.perf_counter()
-  if processes > 1:
-    import multiprocessing as mp
-    with mp.get_context('spawn').Pool(processes) as pool:
-      nfev = pool.map(_cpu_one_sample, jobs)
+  if pool is not None:
+    nfev = pool.map(_cpu_one_sample, jobs, chunksize=1)
   else:
     nfev = [_cpu_one_sample(j) for j in jobs]
   elapsed = time.perf_counter() - t0
@@ -197,27 +220,31 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  cores = os.cpu_count() or 1
+  import multiprocessing as mp
+  cores = usable_cores()
   kind, variant, n, batch, dt, mode = WORKLOADS[args.workload]
-  samples = max(cores, 8) * 2
-  rk = min(args.rk_steps, 20)
-  # pool start-up is excluded by timing whole steps after a warm-up step
+  samples = max(4 * cores, 16)
+  rk = args.rk_steps
   rates = []
-  for i in range(args.warmup + args.steps):
-    rate, elapsed, _ = cpu_reference_rate(args.workload, rk, samples, cores)
-    if i >= args.warmup:
-      rates.append((rate, elapsed))
+  with mp.get_context('spawn').Pool(cores) as pool:
+    pool.map(_cpu_one_sample, [(args.workload, s, 2) for s in range(cores)])   # import + warm the workers
+    for i in range(args.warmup + args.steps):
+      rate, elapsed, _ = cpu_reference_rate(args.workload, rk, samples, cores, pool)
+      if i >= args.warmup:
+        rates.append((rate, elapsed))
   value = float(np.mean([r for r, _ in rates]))
   ms = float(np.mean([e for _, e in rates]) * 1e3)
-  sample = ('%d samples x %d RK3 steps of %s %s N=%d per step, one scipy solve_ivp(RK23, max_step=dt) per '
-            'sample over a %d-process pool (oracle port of integrate.odeint; tensorflow<2 is not installable '
-            'offline so the literal TF graph cannot run)' % (samples, rk, kind, mode, n, cores))
+  sample = ('%d samples x %d RK3 steps of %s %s N=%d per bench step (a bounded sample of the %d-row batch), one '
+            'scipy solve_ivp(RK23, max_step=dt) per sample over a %d-process pool, BLAS 1 thread per worker '
+            '(oracle port of integrate.odeint: tensorflow<2 is not installable offline so the literal TF graph '
+            'cannot run)' % (samples, rk, kind, mode, n, batch, cores))
+  cfg = workload_config(args, batch)
+  cfg['cpu_samples_per_step'] = samples
   line = {
       'impl': 'reference', 'metric': 'grid-point-steps/sec', 'value': value, 'unit': 'grid-point-steps/s',
       'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-      'data': 'synthetic',
-      'config': workload_config(args, batch),
+      'data': 'synthetic', 'config': cfg,
       'cpu_baseline': {'value': value, 'unit': 'grid-point-steps/s', 'cores': cores, 'kind': 'port',
                        'sample': sample},
       'e2e': {'value': value, 'unit': 'grid-point-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -352,8 +379,9 @@ def run_ours(args):
       'launch': shape, 'wall_s': wall,
   }
   if not args.no_cpu:
-    samples = 4
-    rk_cpu = min(rk, 20)
+    samples = 8
+    rk_cpu = rk
+    _cpu_one_sample((args.workload, 0, 2))     # imports, first-call costs
     rate, elapsed, nfev = cpu_reference_rate(args.workload, rk_cpu, samples, 1)
     line['cpu_baseline'] = {
         'value': rate, 'unit': 'grid-point-steps/s', 'cores': 1, 'kind': 'port',

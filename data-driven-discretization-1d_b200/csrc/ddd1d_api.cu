@@ -465,7 +465,9 @@ int ddd1d_set_forcing(ddd1d_handle* h, const double* a, const double* omega, con
 
 int ddd1d_rhs(ddd1d_handle* h, double t, const float* u, float* dudt, int batch, int sample_offset,
               void* stream) {
-  if (!h || !u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
+  if (batch == 0) return DDD1D_OK;
+  if (!u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
   Work W = blank_work();
   W.op = OP_RHS; W.batch = batch; W.sample_offset = sample_offset; W.u = u; W.out = dudt; W.t0 = t;
   return launch(h, W, stream);
@@ -473,14 +475,18 @@ int ddd1d_rhs(ddd1d_handle* h, double t, const float* u, float* dudt, int batch,
 
 int ddd1d_rhs_f64(ddd1d_handle* h, double t, const double* u, double* dudt, int batch, int sample_offset,
                   void* stream) {
-  if (!h || !u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
+  if (batch == 0) return DDD1D_OK;
+  if (!u || !dudt) return fail(h, DDD1D_EINVAL, "null argument");
   Work W = blank_work();
   W.op = OP_RHS; W.batch = batch; W.sample_offset = sample_offset; W.u64 = u; W.out64 = dudt; W.t0 = t;
   return launch(h, W, stream);
 }
 
 int ddd1d_coefficients(ddd1d_handle* h, const float* u, float* coefficients, int batch, void* stream) {
-  if (!h || !u || !coefficients) return fail(h, DDD1D_EINVAL, "null argument");
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
+  if (batch == 0) return DDD1D_OK;
+  if (!u || !coefficients) return fail(h, DDD1D_EINVAL, "null argument");
   if (h->cfg.mode != DDD1D_MODE_LEARNED) return fail(h, DDD1D_EINVAL, "handle has no conv net");
   Work W = blank_work();
   W.op = OP_COEF; W.batch = batch; W.u = u; W.out = coefficients;
@@ -488,7 +494,9 @@ int ddd1d_coefficients(ddd1d_handle* h, const float* u, float* coefficients, int
 }
 
 int ddd1d_space_derivatives(ddd1d_handle* h, const float* u, float* derivatives, int batch, void* stream) {
-  if (!h || !u || !derivatives) return fail(h, DDD1D_EINVAL, "null argument");
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
+  if (batch == 0) return DDD1D_OK;
+  if (!u || !derivatives) return fail(h, DDD1D_EINVAL, "null argument");
   Work W = blank_work();
   W.op = OP_DERIV; W.batch = batch; W.u = u; W.out = derivatives;
   return launch(h, W, stream);
@@ -497,8 +505,10 @@ int ddd1d_space_derivatives(ddd1d_handle* h, const float* u, float* derivatives,
 int ddd1d_integrate(ddd1d_handle* h, double t0, double dt, int num_steps, int save_every, int scheme,
                     const float* u0, float* snapshots, int* first_bad_step, int batch, int sample_offset,
                     void* stream) {
-  if (!h || !u0 || !snapshots) return fail(h, DDD1D_EINVAL, "null argument");
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
   if (num_steps < 0 || save_every < 1) return fail(h, DDD1D_EINVAL, "bad step counts");
+  if (batch == 0) return DDD1D_OK;
+  if (!u0 || (!snapshots && num_steps / save_every > 0)) return fail(h, DDD1D_EINVAL, "null argument");
   if (scheme < 0 || scheme > DDD1D_RK4) return fail(h, DDD1D_EINVAL, "unknown scheme %d", scheme);
   Work W = blank_work();
   W.op = OP_INTEGRATE; W.batch = batch; W.sample_offset = sample_offset; W.u = u0; W.snaps = snapshots;

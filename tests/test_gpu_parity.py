@@ -18,6 +18,7 @@ from tests import gpu_helpers as G
 pytestmark = pytest.mark.gpu
 
 RHS_TOL = 1e-5
+FLUX_TOL = 3e-5   # dy/dt of flux-difference forms: float32 rounding of the flux is divided by dx
 TRAJ_TOL = 1e-4
 
 
@@ -330,7 +331,7 @@ def test_odd_sizes_use_generic_path(n):
     u = G.smooth_rows(3, n, seed=n)
     assert rel_err(cpu(model.predict_coefficients(u, hp, w)), O.predict_coefficients(u, oeq, O.NetSpec(), w)) < RHS_TOL
     assert rel_err(cpu(model.predict_time_derivative(u, hp, w)),
-                   O.predict_time_derivative(u, oeq, O.NetSpec(), w)) < RHS_TOL
+                   O.predict_time_derivative(u, oeq, O.NetSpec(), w)) < (RHS_TOL if variant == 'plain' else FLUX_TOL)
 
 
 def test_fast_and_generic_conv_paths_agree(monkeypatch):
@@ -367,7 +368,7 @@ def test_divergence_is_data_not_an_error():
   """Unstable step: rows go non-finite, first_bad_step says when, integrate_times NaN-pads
   (integrate.py:161-167)."""
   from ddd1d_b200 import integrate, equations
-  eqs = [equations.KSEquation(64, random_seed=s) for s in range(3)]
+  eqs = [equations.KSEquation(256, random_seed=s) for s in range(3)]   # dx=0.25: 16 dt/dx^4 = 41 >> 2.5
   solver = integrate.BatchIntegrator.baseline(eqs, 1)
   u0 = solver.initial_values()
   snaps, bad = solver.integrate(u0, 0.0, 1e-2, 200, 50, return_first_bad=True)   # dt far too large
