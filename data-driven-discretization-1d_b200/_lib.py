@@ -16,6 +16,7 @@ ACTIVATIONS = {None: 0, 'none': 0, 'relu': 1, 'relu6': 2, 'tanh': 3, 'softplus':
 PROJ_NULLSPACE, PROJ_RAW, PROJ_RAW_UNBIASED = 0, 1, 2
 SCHEMES = {'rk3': 0, 'RK23': 0, 'bogacki_shampine': 0, 'midpoint': 1, 'euler': 2, 'rk4': 3}
 REAL_F32, REAL_F64 = 0, 1
+ENGINES = {'auto': 0, 'ffma': 1, 'tensor': 2}
 WINDOW = 7
 
 
@@ -27,7 +28,7 @@ class Config(ctypes.Structure):
       ('dx', ctypes.c_double), ('eta', ctypes.c_double), ('standard_deviation', ctypes.c_double),
       ('num_layers', ctypes.c_int), ('filter_size', ctypes.c_int), ('kernel_size', ctypes.c_int),
       ('activation', ctypes.c_int), ('net_outputs', ctypes.c_int), ('stencil_size', ctypes.c_int),
-      ('projection', ctypes.c_int), ('reserved', ctypes.c_int),
+      ('projection', ctypes.c_int), ('engine', ctypes.c_int),
   ]
 
 
@@ -68,6 +69,12 @@ _SIGNATURES = {
     'ddd1d_launch_count': (ctypes.c_longlong, [_P]),
     'ddd1d_launch_shape': (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                           ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    'ddd1d_engine': (ctypes.c_int, [_P]),
+}
+
+# test-only entry points (include/ddd1d_debug.h)
+_DEBUG_SIGNATURES = {
+    'ddd1d_debug_tc_probe': (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P, ctypes.c_int, _P]),
 }
 
 
@@ -85,7 +92,7 @@ def load():
           '%s not found: run `python __graft_entry__.py` (nvcc, sm_100a) first; '
           'there is no CPU fallback' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (restype, argtypes) in _SIGNATURES.items():
+    for name, (restype, argtypes) in list(_SIGNATURES.items()) + list(_DEBUG_SIGNATURES.items()):
       fn = getattr(lib, name)
       fn.restype = restype
       fn.argtypes = argtypes

@@ -14,9 +14,15 @@
 #include <vector>
 
 #include "../../include/ddd1d.h"
+#include "../../include/ddd1d_debug.h"
 #include "ddd1d_device.cuh"
+#include "ddd1d_tc.cuh"
 
 using namespace ddd1d;
+
+#ifndef DDD1D_AUTO_PREFERS_TENSOR
+#define DDD1D_AUTO_PREFERS_TENSOR 0
+#endif
 
 namespace {
 
@@ -46,6 +52,12 @@ struct ddd1d_handle {
   int forcing_batch = 0, forcing_P = 0, forcing_M = 0;
   int threads = 0, blocks_per_sm = 0, num_sms = 0;
   long long launches = 0;
+  // tensor-core engine
+  Params Ptc;
+  bool tc_ok = false;
+  std::string tc_why;
+  float* d_blob_tc = nullptr;
+  int tc_threads = 0;
   // staging for the *_host entry points
   void* d_stage_in = nullptr;
   void* d_stage_out = nullptr;
@@ -91,6 +103,176 @@ double plan_cost(int cout, int N, int nwarps, int cg, int pbt) {
   // FFMAs per input channel + ~4 issue slots per shared-memory load
   double per_ci = 20.0 * pbt * cg + 4.0 * (2.0 * pbt + 1.25 * cg);
   return rounds * per_ci;
+}
+
+
+float tf32_hi(float v) {
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  b &= 0xffffe000u;
+  float r;
+  memcpy(&r, &b, 4);
+  return r;
+}
+
+int engine_request(const ddd1d_handle* h) {
+  int e = h->cfg.engine;
+  const char* env = getenv("DDD1D_ENGINE");
+  if (e == DDD1D_ENGINE_AUTO && env) {
+    if (!strcmp(env, "ffma")) e = DDD1D_ENGINE_FFMA;
+    if (!strcmp(env, "tensor")) e = DDD1D_ENGINE_TENSOR;
+  }
+  return e;
+}
+
+// Build the tensor-core engine's blob and shared-memory plan (ddd1d_tc.cuh) when the net has the
+// shape that kernel is written for.  Not being eligible is not an error unless the caller forced
+// DDD1D_ENGINE_TENSOR.
+int finalize_tc(ddd1d_handle* h) {
+  const ddd1d_config& c = h->cfg;
+  h->tc_ok = false;
+  h->tc_why.clear();
+  const int N = c.num_points, D = c.num_derivatives;
+  const int want = engine_request(h);
+  if (c.mode != DDD1D_MODE_LEARNED) h->tc_why = "not a learned-coefficient handle";
+  else if (c.kernel_size != 5 || c.filter_size != tc::kF) h->tc_why = "needs kernel_size 5 and filter_size 32";
+  else if (c.num_layers < 2 || c.num_layers > 3) h->tc_why = "needs 2 or 3 conv layers";
+  else if (N != 128 && N != 256 && N != 512) h->tc_why = "needs num_points in {128, 256, 512}";
+  if (!h->tc_why.empty() || want == DDD1D_ENGINE_FFMA) {
+    if (want == DDD1D_ENGINE_TENSOR)
+      return fail(h, DDD1D_EUNSUPPORTED, "tensor engine unavailable: %s", h->tc_why.c_str());
+    return DDD1D_OK;
+  }
+  Params P = h->P;   // equation / forcing / projection scalars are shared
+  const int L = c.num_layers;
+  const int NL = (D * kWin <= 16) ? 16 : 32;
+  const int K = 5, F = tc::kF;
+  // linear map net channel -> window coefficient (projection folded into the last layer)
+  const int Q = D * kWin;
+  std::vector<double> pm((size_t)c.net_outputs * Q, 0.0), pbias(Q, 0.0);
+  if (c.projection == DDD1D_PROJ_NULLSPACE) {
+    int ch = 0;
+    for (int d = 0; d < D; ++d)
+      for (int i = 0; i < h->input_sizes[d]; ++i, ++ch)
+        for (int j = 0; j < kWin; ++j) pm[(size_t)ch * Q + d * kWin + j] = h->nullspace[(size_t)ch * kWin + j];
+    for (int d = 0; d < D; ++d)
+      for (int j = 0; j < kWin; ++j) pbias[d * kWin + j] = h->stencils[d * kWin + j];
+  } else {
+    const int S = c.stencil_size, ws = 3 - S / 2;
+    for (int d = 0; d < D; ++d)
+      for (int i = 0; i < S; ++i)
+        for (int i2 = 0; i2 < S; ++i2) {
+          double v = (i == i2) ? 1.0 : 0.0;
+          if (c.projection == DDD1D_PROJ_RAW_UNBIASED) v -= 1.0 / S;
+          pm[(size_t)(d * S + i2) * Q + d * kWin + i + ws] = v;
+        }
+  }
+  std::vector<float> blob;
+  auto reserve = [&](size_t n) { size_t off = blob.size(); blob.resize(off + n, 0.f); return (int)off; };
+  // first layer [5][32] + bias
+  const HostLayer& l0 = h->layers[0];
+  P.tc_w1_off = reserve(K * F);
+  for (int k = 0; k < K; ++k)
+    for (int co = 0; co < F; ++co) blob[P.tc_w1_off + k * F + co] = (L == 1) ? 0.f : l0.kernel[(size_t)k * F + co];
+  P.tc_b1_off = reserve(F);
+  for (int co = 0; co < F; ++co) blob[P.tc_b1_off + co] = l0.bias[co];
+  // hidden tensor-core layers
+  const int nhid = L - 2;
+  P.tc_bh_off = reserve((size_t)std::max(nhid, 1) * F);
+  P.tc_bl_off = reserve(32);
+  P.tc_bhid_stride = 2 * K * tc::kChunks * F * 4;
+  P.tc_bhid_lo = K * tc::kChunks * F * 4;
+  P.tc_bhid_off = reserve((size_t)std::max(nhid, 0) * P.tc_bhid_stride);
+  for (int l = 0; l < nhid; ++l) {
+    const HostLayer& hl = h->layers[1 + l];
+    for (int co = 0; co < F; ++co) blob[P.tc_bh_off + l * F + co] = hl.bias[co];
+    float* hi = blob.data() + P.tc_bhid_off + (size_t)l * P.tc_bhid_stride;
+    float* lo = hi + P.tc_bhid_lo;
+    for (int k = 0; k < K; ++k)
+      for (int ci = 0; ci < F; ++ci)
+        for (int co = 0; co < F; ++co) {
+          const float w = hl.kernel[((size_t)k * F + ci) * F + co];
+          const size_t idx = ((size_t)(k * tc::kChunks + ci / 4) * F + co) * 4 + (ci % 4);
+          hi[idx] = tf32_hi(w);
+          lo[idx] = w - hi[idx];
+        }
+  }
+  // last layer with the projection folded in: W'[k][ci][q] = sum_c W[k][ci][c] pm[c][q]
+  const HostLayer& ll = h->layers[L - 1];
+  P.tc_blast_lo = K * tc::kChunks * NL * 4;
+  P.tc_blast_off = reserve((size_t)2 * P.tc_blast_lo);
+  {
+    float* hi = blob.data() + P.tc_blast_off;
+    float* lo = hi + P.tc_blast_lo;
+    for (int k = 0; k < K; ++k)
+      for (int ci = 0; ci < F; ++ci)
+        for (int q = 0; q < Q; ++q) {
+          double acc = 0.0;
+          for (int ch = 0; ch < c.net_outputs; ++ch)
+            acc += (double)ll.kernel[((size_t)k * F + ci) * c.net_outputs + ch] * pm[(size_t)ch * Q + q];
+          const float w = (float)acc;
+          const size_t idx = ((size_t)(k * tc::kChunks + ci / 4) * NL + q) * 4 + (ci % 4);
+          hi[idx] = tf32_hi(w);
+          lo[idx] = w - hi[idx];
+        }
+    for (int q = 0; q < Q; ++q) {
+      double acc = pbias[q];
+      for (int ch = 0; ch < c.net_outputs; ++ch) acc += (double)ll.bias[ch] * pm[(size_t)ch * Q + q];
+      blob[P.tc_bl_off + q] = (float)acc;
+    }
+  }
+  blob.resize(align_up((int)blob.size(), 32), 0.f);
+  P.blob_floats = (int)blob.size();
+  P.tc_nlast = NL;
+  P.tc_teams = 512 / N;
+  // shared-memory plan
+  const int plane = (N + 4) * 16;
+  int t = 0;
+  P.tc_t_act_hi = t; t += tc::kChunks * plane;
+  P.tc_t_act_lo = t; t += tc::kChunks * plane;
+  P.tc_t_ust = t; t += align_up((N + 2 * kHalo) * 4, 16);
+  P.tc_t_k = t; t += kMaxStages * N * 4;
+  P.tc_t_flux = t; t += N * 4;
+  P.tc_t_fs = t; t += align_up((4 * kMaxModes + 4) * 4, 16);
+  P.tc_team_stride = align_up(t, 128);
+  P.off_bar = 0;
+  P.tc_off_slot = 112;
+  P.tc_off_tab = 128;                       // Tableau (200 B)
+  P.off_blob = 384;
+  P.tc_off_team0 = align_up(P.off_blob + P.blob_floats * 4, 128);
+  P.smem_bytes = P.tc_off_team0 + P.tc_teams * P.tc_team_stride;
+  if (P.smem_bytes > 227 * 1024) {
+    h->tc_why = "shared memory plan does not fit";
+    if (want == DDD1D_ENGINE_TENSOR)
+      return fail(h, DDD1D_EUNSUPPORTED, "tensor engine needs %d bytes of shared memory", P.smem_bytes);
+    return DDD1D_OK;
+  }
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  if (h->d_blob_tc) CUDA_TRY(h, cudaFree(h->d_blob_tc));
+  CUDA_TRY(h, cudaMalloc(&h->d_blob_tc, blob.size() * sizeof(float)));
+  CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  P.blob = h->d_blob_tc;
+  CUDA_TRY(h, cudaFuncSetAttribute(tc::tc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+  h->tc_threads = P.tc_teams * N + 32;
+  int occ = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_row_kernel, h->tc_threads, P.smem_bytes));
+  if (occ < 1) {
+    h->tc_why = "tensor kernel does not fit on an SM";
+    if (want == DDD1D_ENGINE_TENSOR) return fail(h, DDD1D_EUNSUPPORTED, "%s", h->tc_why.c_str());
+    return DDD1D_OK;
+  }
+  h->Ptc = P;
+  // AUTO currently resolves to the FFMA kernel unless DDD1D_ENGINE / cfg.engine asks for "tensor"
+  h->tc_ok = true;
+  return DDD1D_OK;
+}
+
+bool use_tc(const ddd1d_handle* h) {
+  if (!h->tc_ok) return false;
+  const int want = engine_request(h);
+  if (want == DDD1D_ENGINE_TENSOR) return true;
+  if (want == DDD1D_ENGINE_FFMA) return false;
+  return DDD1D_AUTO_PREFERS_TENSOR != 0;
 }
 
 // Build P (plans, blob, shared-memory carve-up) from the host-side description.
@@ -251,6 +433,8 @@ int finalize(ddd1d_handle* h) {
   if (occ < 1) return fail(h, DDD1D_EUNSUPPORTED, "kernel does not fit on an SM (%d threads, %d B smem)",
                            h->threads, P.smem_bytes);
   h->blocks_per_sm = occ;
+  int rc_tc = finalize_tc(h);
+  if (rc_tc) return rc_tc;
   h->dirty = false;
   return DDD1D_OK;
 }
@@ -266,8 +450,17 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     return fail(h, DDD1D_EINVAL, "samples [%d, %d) exceed the %d forcing rows set", W.sample_offset,
                 W.sample_offset + W.batch, P.fcap);
   CUDA_TRY(h, cudaSetDevice(c.device));
-  const int grid = std::min(W.batch, h->num_sms * h->blocks_per_sm);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_tc(h)) {
+    const Params& T = h->Ptc;
+    const int teams_needed = (W.batch + T.tc_teams - 1) / T.tc_teams;
+    const int grid_tc = std::min(teams_needed, h->num_sms);
+    tc::tc_row_kernel<<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return DDD1D_OK;
+  }
+  const int grid = std::min(W.batch, h->num_sms * h->blocks_per_sm);
   if (c.mode == DDD1D_MODE_LEARNED)
     row_kernel<MODE_LEARNED><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
   else if (c.mode == DDD1D_MODE_WENO)
@@ -358,6 +551,7 @@ int ddd1d_destroy(ddd1d_handle* h) {
   if (!h) return DDD1D_OK;
   cudaSetDevice(h->cfg.device);
   cudaFree(h->d_blob);
+  cudaFree(h->d_blob_tc);
   cudaFree(h->d_fparams);
   cudaFree(h->d_fbasis);
   cudaFree(h->d_stage_in);
@@ -588,11 +782,36 @@ int ddd1d_weno_reconstruct(int device, int real, const void* u, void* left, void
 
 long long ddd1d_launch_count(const ddd1d_handle* h) { return h ? h->launches : 0; }
 
+int ddd1d_engine(const ddd1d_handle* handle) {
+  ddd1d_handle* h = const_cast<ddd1d_handle*>(handle);
+  if (!h) return fail(nullptr, DDD1D_EINVAL, "null handle");
+  int rc = finalize(h);
+  if (rc) return rc;
+  return use_tc(h) ? DDD1D_ENGINE_TENSOR : DDD1D_ENGINE_FFMA;
+}
+
+int ddd1d_debug_tc_probe(int device, const float* x, const float* w_hi, const float* w_lo, float* out, int nout,
+                         void* stream) {
+  if (!x || !w_hi || !w_lo || !out || (nout != 16 && nout != 32)) return fail(nullptr, DDD1D_EINVAL, "bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  const int smem = 128 + 2 * tc::kChunks * 132 * 16 + 2 * tc::kTaps * tc::kChunks * nout * 16;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_probe_kernel<<<1, 160, smem, static_cast<cudaStream_t>(stream)>>>(x, w_hi, w_lo, out, nout);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+
 int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* block, int* shared_bytes) {
   ddd1d_handle* h = const_cast<ddd1d_handle*>(handle);
   if (!h) return fail(nullptr, DDD1D_EINVAL, "null handle");
   int rc = finalize(h);
   if (rc) return rc;
+  if (use_tc(h)) {
+    if (grid) *grid = std::min((batch + h->Ptc.tc_teams - 1) / h->Ptc.tc_teams, h->num_sms);
+    if (block) *block = h->tc_threads;
+    if (shared_bytes) *shared_bytes = h->Ptc.smem_bytes;
+    return DDD1D_OK;
+  }
   if (grid) *grid = std::min(batch, h->num_sms * h->blocks_per_sm);
   if (block) *block = h->threads;
   if (shared_bytes) *shared_bytes = h->P.smem_bytes;

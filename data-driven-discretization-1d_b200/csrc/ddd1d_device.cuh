@@ -59,6 +59,12 @@ struct Params {
   int off_bar, off_blob, off_ust, off_ydbl, off_k, off_flux, off_fs, off_act0, off_act1;
   int smem_bytes;
   int use_bulk_copy;
+  // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
+  int tc_teams, tc_nlast;
+  int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
+  int tc_t_act_hi, tc_t_act_lo, tc_t_ust, tc_t_k, tc_t_flux, tc_t_fs;      // byte offsets inside a team region
+  int tc_w1_off, tc_b1_off, tc_bh_off, tc_bl_off;                          // float offsets into the blob
+  int tc_bhid_off, tc_bhid_stride, tc_bhid_lo, tc_blast_off, tc_blast_lo;
 };
 
 struct Work {

@@ -1,0 +1,573 @@
+// Tensor-core (tcgen05 / TMEM) version of the learned-coefficient row kernel, sm_100a.
+//
+// The conv stack is 96 % of the FLOPs and is an implicit GEMM per 128-position tile:
+//   hidden layer : D[128 x 32] += sum_{tap k, ci-block} A_k[128 x 8] * B_k[8 x 32]   (K = 5*32)
+//   last layer   : D[128 x NL] += ...                                                 (NL = 16 | 32)
+// A = activations kept in shared memory as K-major "chunk planes" [ci/4][position][4 floats]
+// (no swizzle), so the tap shift k is just +16 B on the descriptor start address and the periodic
+// halo is two extra positions per plane.  B = filters pre-packed on the host in the same canonical
+// layout.  FP32 fidelity on a TF32 pipe comes from the 3xTF32 split: x = hi + lo with hi = the top
+// 19 bits, and hi*Whi + lo*Whi + hi*Wlo accumulated in FP32 in TMEM (the dropped lo*Wlo term is
+// 2^-22 relative).  The polynomial-accuracy projection is folded into the last layer's filters on
+// the host (W3' = W3 . nullspace, window form), so the last epilogue reads stencil coefficients
+// straight out of TMEM.
+//
+// Warp roles (one CTA per SM, persistent): R "row teams" of N threads (thread <-> grid point; the
+// team's warps are 4-aligned so each warp reads its own TMEM lane quadrant) run the whole
+// Runge-Kutta program of their row; one extra warp issues every tcgen05.mma for all teams and
+// signals completion with tcgen05.commit -> mbarrier.  While one team runs an epilogue on the CUDA
+// cores, the tensor pipe works on another team's tile.
+#pragma once
+#include "ddd1d_device.cuh"
+
+namespace ddd1d {
+namespace tc {
+
+constexpr int kF = 32;             // hidden width this path is built for
+constexpr int kTaps = 5;
+constexpr int kChunks = kF / 4;    // 16-byte chunks along ci
+constexpr long long kSpinCycles = 4000000000ll;   // ~2 s at 1.9 GHz: a protocol bug traps instead of hanging
+
+// ---- descriptors -------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) leading byte offset>>4 (between the two 16-B K chunks of one MMA)
+//   [32,46) stride byte offset>>4 (between 8-row groups) | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Instruction descriptor for kind::tf32, FP32 accumulate, A and B K-major (cute::UMMA::InstrDescriptor):
+//   c_format F32 = 1 @4 | a_format TF32 = 2 @7 | b_format TF32 = 2 @10 | N>>3 @17 | M>>4 @24
+__device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// mbarrier helpers with a spin guard: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  long long start = 0;
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (start == 0) start = now;
+      else if (now - start > kSpinCycles) asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void team_sync(int team, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(threads) : "memory");
+}
+
+// x = hi + lo, hi exactly representable in TF32
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  lo = v - hi;
+}
+
+// ---- shared layouts ----------------------------------------------------------------------------
+// activation planes of one team: plane c (ci = 4c..4c+3), position x at byte (x + 2) * 16
+// filters: hidden  Bh[(tap*8 + chunk) * 512 + co*16 + (ci%4)*4],  last  Bl[(tap*8 + chunk) * NL*16 + ...]
+
+struct TcView {
+  uint64_t* bars;        // [0] blob copy, [1+t] request (count N), [1+R+t] done (count 1)
+  uint32_t* tmem_slot;
+  float* blob;
+  unsigned char* team_base;
+};
+
+// Issue all MMAs of one layer for one team (one thread).
+__device__ __noinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes,
+                                            uint32_t b_hi, uint32_t b_lo, uint32_t b_plane_bytes, int tiles,
+                                            uint32_t tmem_col0, uint32_t idesc) {
+  for (int m = 0; m < tiles; ++m) {
+    const uint32_t d = tmem_col0 + (uint32_t)m * 32u;
+    uint32_t accumulate = 0;
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+#pragma unroll
+      for (int kb = 0; kb < kChunks / 2; ++kb) {
+        const uint32_t a_off = (uint32_t)(2 * kb) * plane_bytes + (uint32_t)(128 * m + k) * 16u;
+        const uint32_t b_off = (uint32_t)(k * kChunks + 2 * kb) * b_plane_bytes;
+        const uint64_t ah = smem_desc(act_hi + a_off, plane_bytes, 128);
+        const uint64_t al = smem_desc(act_lo + a_off, plane_bytes, 128);
+        const uint64_t bh = smem_desc(b_hi + b_off, b_plane_bytes, 128);
+        const uint64_t bl = smem_desc(b_lo + b_off, b_plane_bytes, 128);
+        mma_tf32(d, ah, bh, idesc, accumulate);
+        mma_tf32(d, al, bh, idesc, 1);
+        mma_tf32(d, ah, bl, idesc, 1);
+        accumulate = 1;
+      }
+    }
+  }
+}
+
+// store 4 consecutive channels of one position into a plane (+ its wrapped halo copy)
+__device__ __forceinline__ void store_chunk(unsigned char* plane, int x, int N, float4 v) {
+  *reinterpret_cast<float4*>(plane + (size_t)(x + 2) * 16) = v;
+  if (x < 2) *reinterpret_cast<float4*>(plane + (size_t)(x + 2 + N) * 16) = v;
+  if (x >= N - 2) *reinterpret_cast<float4*>(plane + (size_t)(x + 2 - N) * 16) = v;
+}
+
+__device__ __forceinline__ void store_split(unsigned char* hi_plane, unsigned char* lo_plane, int x, int N,
+                                            float a, float b, float c, float d) {
+  float4 h, l;
+  split_tf32(a, h.x, l.x);
+  split_tf32(b, h.y, l.y);
+  split_tf32(c, h.z, l.z);
+  split_tf32(d, h.w, l.w);
+  store_chunk(hi_plane, x, N, h);
+  store_chunk(lo_plane, x, N, l);
+}
+
+
+// Last-layer epilogue for one grid point: window coefficients = TMEM accumulators + folded bias,
+// then the stencil dot products (model.py:536-548).  NLV = TMEM columns of the last layer.
+template <int NLV>
+__device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, uint32_t taddr,
+                                              const float* __restrict__ blast, const float (&u7)[kWin],
+                                              int row, int x, float (&dv)[kMaxD]) {
+  float cfv[NLV];
+  if (NLV == 16) tmem_ld16(taddr, reinterpret_cast<float(&)[16]>(cfv));
+  else tmem_ld32(taddr, reinterpret_cast<float(&)[32]>(cfv));
+  fence_before();
+  const int N = P.N;
+#pragma unroll
+  for (int d = 0; d < kMaxD; ++d) {
+    dv[d] = 0.f;
+    if (d * kWin + kWin > NLV || d >= P.D) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWin; ++j) {
+      const float cf = cfv[d * kWin + j] + blast[d * kWin + j];
+      sum = fmaf(cf, u7[j], sum);
+      if (W.op == OP_COEF) {
+        const int i = j - P.wshift;
+        if (i >= 0 && i < P.S) W.out[(((size_t)row * N + x) * P.D + d) * P.S + i] = cf;
+      }
+    }
+    dv[d] = sum;
+    if (W.op == OP_DERIV) W.out[((size_t)row * N + x) * P.D + d] = sum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Work W) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = P.N, R = P.tc_teams, tiles = N / 128;
+  const int team_warps = N / 32;
+  const bool is_mma_warp = warp == R * team_warps;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot);
+  float* blob = reinterpret_cast<float*>(smem_raw + P.off_blob);
+  const uint32_t plane_bytes = (uint32_t)(N + 4) * 16u;
+  const int NL = P.tc_nlast;                         // 16 or 32 columns for the last layer
+  const int hidden_tc_layers = P.nlayers - 2;        // layers between the first and the last
+  const int requests_per_rhs = hidden_tc_layers + 1;
+
+  Tableau* tab_s = reinterpret_cast<Tableau*>(smem_raw + P.tc_off_tab);
+  if (tid == 0) {
+    *tab_s = make_tableau(W.scheme);
+    mbar_init(&bars[0], 1);
+    for (int t = 0; t < R; ++t) {
+      mbar_init(&bars[1 + t], (uint32_t)N);
+      mbar_init(&bars[1 + R + t], 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)P.blob_floats * 4u;
+    mbar_expect_tx(&bars[0], bytes);
+    bulk_copy_g2s(blob, P.blob, bytes, &bars[0]);
+  }
+  if (is_mma_warp) tmem_alloc(tmem_slot, 128);
+  mbar_wait_guarded(&bars[0], 0);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_teams = gridDim.x * R;
+  const int stages_of = tab_s->stages;
+  const int rhs_per_row = (W.op == OP_INTEGRATE) ? W.nsteps * stages_of : 1;
+
+  if (is_mma_warp) {
+    // ---------------- MMA issuer: serve whichever team has posted a request ----------------
+    uint32_t remaining[4], parity[4], layer_idx[4];
+    uint32_t total = 0;
+    for (int t = 0; t < 4; ++t) {
+      remaining[t] = 0; parity[t] = 0; layer_idx[t] = 0;
+      if (t < R) {
+        const int g = blockIdx.x * R + t;
+        const int rows = g < W.batch ? (W.batch - g + total_teams - 1) / total_teams : 0;
+        remaining[t] = (uint32_t)rows * (uint32_t)rhs_per_row * (uint32_t)requests_per_rhs;
+        total += remaining[t];
+      }
+    }
+    const uint32_t idesc_h = instr_desc_tf32(128, 32);
+    const uint32_t idesc_l = instr_desc_tf32(128, NL);
+    const uint32_t blob_s = smem_u32(blob);
+    uint32_t spins = 0;
+    long long spin_start = 0;
+    while (total > 0) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t >= R || remaining[t] == 0) continue;
+        if (!mbar_test(&bars[1 + t], parity[t])) {
+          if ((++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (spin_start == 0) spin_start = now;
+            else if (now - spin_start > kSpinCycles) asm volatile("trap;");
+          }
+          continue;
+        }
+        spins = 0;
+        spin_start = 0;
+        fence_after();
+        if (lane == 0) {
+          unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)t * P.tc_team_stride;
+          const uint32_t act_hi = smem_u32(tb + P.tc_t_act_hi), act_lo = smem_u32(tb + P.tc_t_act_lo);
+          const uint32_t col0 = tmem_base + (uint32_t)(t * tiles) * 32u;
+          const bool last = (int)layer_idx[t] == hidden_tc_layers;
+          if (!last) {
+            const uint32_t off = (uint32_t)(P.tc_bhid_off + (int)layer_idx[t] * P.tc_bhid_stride) * 4u;
+            issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_bhid_lo * 4u,
+                        32 * 16, tiles, col0, idesc_h);
+          } else {
+            const uint32_t off = (uint32_t)P.tc_blast_off * 4u;
+            issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_blast_lo * 4u,
+                        (uint32_t)NL * 16u, tiles, col0, idesc_l);
+          }
+          mma_commit(&bars[1 + R + t]);
+        }
+        __syncwarp();
+        parity[t] ^= 1u;
+        layer_idx[t] = (layer_idx[t] + 1 == (uint32_t)requests_per_rhs) ? 0u : layer_idx[t] + 1;
+        remaining[t] -= 1;
+        total -= 1;
+      }
+    }
+  } else {
+    // ---------------- row team ----------------
+    const int team = warp / team_warps;
+    const int x = tid - team * N;                      // this thread's grid point
+    unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)team * P.tc_team_stride;
+    unsigned char* act_hi = tb + P.tc_t_act_hi;
+    unsigned char* act_lo = tb + P.tc_t_act_lo;
+    float* ust = reinterpret_cast<float*>(tb + P.tc_t_ust);
+    float* kst = reinterpret_cast<float*>(tb + P.tc_t_k);
+    float* flux = reinterpret_cast<float*>(tb + P.tc_t_flux);
+    float* fs = reinterpret_cast<float*>(tb + P.tc_t_fs);
+    uint64_t* req = &bars[1 + team];
+    uint64_t* done = &bars[1 + R + team];
+    uint32_t done_parity = 0;
+    uint32_t fsel = 0;                                   // forcing amplitudes are double buffered per stage
+    const int tile = x >> 7;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 32);
+    const Tableau& tab = *tab_s;
+    const bool cons = eq_conservative(P.eq);
+    const bool forced_eq = eq_forced(P.eq) && P.P > 0;
+    const float* w1 = blob + P.tc_w1_off;               // [5][32]
+    const float* b1 = blob + P.tc_b1_off;
+    const float* blast = blob + P.tc_bl_off;            // folded bias of the last layer [32]
+
+    const int g = blockIdx.x * R + team;
+    for (int row = g; row < W.batch; row += total_teams) {
+      const int sample = W.sample_offset + row;
+      double y = W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
+      int first_bad = -1, save_idx = 0;
+      const int nsteps = (W.op == OP_INTEGRATE) ? W.nsteps : 1;
+      for (int step = 0; step < nsteps; ++step) {
+        const double t0 = W.t0 + (double)step * W.dt;
+        const int nstages = (W.op == OP_INTEGRATE) ? tab.stages : 1;
+        for (int s = 0; s < nstages; ++s) {
+          // ---- stage value, rounded to float32 (integrate.py:57-60,71) ----
+          double accd = 0.0;
+#pragma unroll
+          for (int j = 0; j < kMaxStages; ++j)
+            if (j < s && tab.a[s][j] != 0.0) accd += tab.a[s][j] * (double)kst[j * N + x];
+          const float us = (float)(s == 0 ? y : y + W.dt * accd);
+          ust[x + kHalo] = us;
+          if (x < kHalo) ust[x + kHalo + N] = us;
+          if (x >= N - kHalo) ust[x + kHalo - N] = us;
+          const float tstage = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[s] * W.dt : W.t0);
+          const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
+          fsel ^= 1u;
+          float* fs_cur = fs + fsel * (2 * kMaxModes);
+          if (forced && x < 2 * P.M) {
+            const float* fp = P.fparams + (size_t)sample * 4 * P.P;
+            const int m = (x < P.M ? x : x - P.M) + 1;
+            float a = 0.f;
+            for (int q = 0; q < P.P; ++q) {
+              const float kk = fp[3 * P.P + q];
+              if (fabsf(kk) != (float)m) continue;
+              float sn, cs;
+              sincosf(fmaf(fp[P.P + q], tstage, fp[2 * P.P + q]), &sn, &cs);
+              a += (x < P.M) ? fp[q] * sn : (kk < 0.f ? -fp[q] : fp[q]) * cs;
+            }
+            fs_cur[x] = a;
+          }
+          team_sync(team, N);
+          float u7[kWin];
+#pragma unroll
+          for (int j = 0; j < kWin; ++j) u7[j] = ust[x + j];
+
+          // ---- first layer 1 -> 32 on the CUDA cores, split and written as A planes ----
+          {
+            float un[kTaps];
+#pragma unroll
+            for (int k = 0; k < kTaps; ++k) un[k] = __fdiv_rn(u7[k + 1], P.sigma);   // model.py:450-451
+#pragma unroll
+            for (int c4 = 0; c4 < kChunks; ++c4) {
+              float4 h = *reinterpret_cast<const float4*>(b1 + 4 * c4);
+#pragma unroll
+              for (int k = 0; k < kTaps; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(w1 + k * kF + 4 * c4);
+                h.x = fmaf(un[k], w.x, h.x); h.y = fmaf(un[k], w.y, h.y);
+                h.z = fmaf(un[k], w.z, h.z); h.w = fmaf(un[k], w.w, h.w);
+              }
+              const int act = P.layer[0].act;
+              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N,
+                          activate(h.x, act), activate(h.y, act), activate(h.z, act), activate(h.w, act));
+            }
+          }
+          fence_async_smem();
+          mbar_arrive(req);
+
+          // ---- hidden layers on the tensor pipe; epilogue rewrites the planes in place ----
+          for (int l = 0; l < hidden_tc_layers; ++l) {
+            mbar_wait_guarded(done, done_parity);
+            done_parity ^= 1u;
+            fence_after();
+            float acc[32];
+            tmem_ld32(taddr, acc);
+            fence_before();
+            const float* bias = blob + P.tc_bh_off + l * kF;
+            const int act = P.layer[1 + l].act;
+#pragma unroll
+            for (int c4 = 0; c4 < kChunks; ++c4) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + 4 * c4);
+              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N,
+                          activate(acc[4 * c4] + b.x, act), activate(acc[4 * c4 + 1] + b.y, act),
+                          activate(acc[4 * c4 + 2] + b.z, act), activate(acc[4 * c4 + 3] + b.w, act));
+            }
+            fence_async_smem();
+            mbar_arrive(req);
+          }
+
+          // ---- last layer: stencil coefficients (projection folded in) straight from TMEM ----
+          mbar_wait_guarded(done, done_parity);
+          done_parity ^= 1u;
+          fence_after();
+          float dv[kMaxD];
+          if (NL == 16) last_epilogue<16>(P, W, taddr, blast, u7, row, x, dv);
+          else last_epilogue<32>(P, W, taddr, blast, u7, row, x, dv);
+          if (W.op == OP_COEF || W.op == OP_DERIV) continue;
+          float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
+          if (cons) {
+            flux[x] = r;
+            team_sync(team, N);
+            const float fwd = flux[x + 1 == N ? 0 : x + 1];
+            r = -__fmul_rn(P.inv_dx, __fsub_rn(fwd, r));
+          }
+          if (forced) {
+            float f = 0.f;
+            for (int m = 0; m < P.M; ++m) {
+              f = fmaf(fs_cur[m], __ldg(P.fbasis + (size_t)m * N + x), f);
+              f = fmaf(fs_cur[P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
+            }
+            r = __fadd_rn(r, f);
+          }
+          if (W.op == OP_RHS) {
+            if (W.out64) W.out64[(size_t)row * N + x] = (double)r;
+            else W.out[(size_t)row * N + x] = r;
+          } else {
+            kst[s * N + x] = r;
+          }
+        }
+        if (W.op != OP_INTEGRATE) continue;
+        double accd = 0.0;
+#pragma unroll
+        for (int j = 0; j < kMaxStages; ++j)
+          if (j < tab.stages && tab.b[j] != 0.0) accd += tab.b[j] * (double)kst[j * N + x];
+        y = y + W.dt * accd;
+        if (first_bad < 0 && !isfinite(y)) first_bad = step;
+        if (((step + 1) % W.save_every) == 0) {
+          W.snaps[((size_t)save_idx * W.batch + row) * N + x] = (float)y;
+          ++save_idx;
+        }
+      }
+      if (W.op == OP_INTEGRATE && W.first_bad) {
+        unsigned int* slot = reinterpret_cast<unsigned int*>(fs + 4 * kMaxModes);
+        if (x == 0) *slot = 0xffffffffu;
+        team_sync(team, N);
+        atomicMin(slot, first_bad < 0 ? 0xffffffffu : (unsigned int)first_bad);
+        team_sync(team, N);
+        if (x == 0) W.first_bad[row] = (*slot == 0xffffffffu) ? -1 : (int)*slot;
+        team_sync(team, N);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (is_mma_warp) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Probe: one 128-position tile of a 32 -> NOUT, 5-tap periodic-free conv through the same
+// descriptor / split / TMEM path.  Used by tests to validate layouts in isolation.
+//   x   [132][32] float  (positions -2..129)      w_hi/w_lo  packed B planes [5*8][NOUT][4]
+//   out [128][NOUT] float
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restrict__ xin,
+                                                          const float* __restrict__ w_hi,
+                                                          const float* __restrict__ w_lo, float* __restrict__ out,
+                                                          int nout) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t plane_bytes = 132u * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned char* a_hi = smem_raw + 128;
+  unsigned char* a_lo = a_hi + kChunks * plane_bytes;
+  float* b_hi = reinterpret_cast<float*>(a_lo + kChunks * plane_bytes);
+  float* b_lo = b_hi + kTaps * kChunks * nout * 4;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(slot, 32);
+  for (int i = tid; i < 132 * kChunks; i += blockDim.x) {
+    const int pos = i / kChunks, c4 = i % kChunks;
+    const float4 v = *reinterpret_cast<const float4*>(xin + (size_t)pos * kF + 4 * c4);
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(a_hi + (size_t)c4 * plane_bytes + (size_t)pos * 16) = h;
+    *reinterpret_cast<float4*>(a_lo + (size_t)c4 * plane_bytes + (size_t)pos * 16) = l;
+  }
+  for (int i = tid; i < kTaps * kChunks * nout * 4; i += blockDim.x) {
+    b_hi[i] = w_hi[i];
+    b_lo[i] = w_lo[i];
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  if (tid == 128) {
+    issue_layer(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_hi), smem_u32(b_lo), (uint32_t)nout * 16u,
+                1, tmem_base, instr_desc_tf32(128, nout));
+    mma_commit(bar);
+  }
+  if (warp < 4) {
+    mbar_wait_guarded(bar, 0);
+    fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (nout == 16) {
+      float v[16];
+      tmem_ld16(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[(size_t)tid * 16 + i] = v[i];
+    } else {
+      float v[32];
+      tmem_ld32(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) out[(size_t)tid * 32 + i] = v[i];
+    }
+    fence_before();
+  }
+  __syncthreads();
+  fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, 32);
+}
+
+}  // namespace tc
+}  // namespace ddd1d

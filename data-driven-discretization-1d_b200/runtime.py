@@ -86,7 +86,7 @@ class RowSolver(object):
   """One ddd1d_handle plus the per-sample forcing it was given."""
 
   def __init__(self, equations, mode, hparams=None, weights=None, accuracy_order=1,
-               weno_real='float32', device=None, forcing=True):
+               weno_real='float32', device=None, forcing=True, engine='auto'):
     torch = _torch()
     self._lib = _lib.load()
     self.equations = _as_list(equations)
@@ -110,6 +110,7 @@ class RowSolver(object):
     cfg.dx = eq.grid.solution_dx
     cfg.eta = getattr(eq, 'eta', 0.0)
     cfg.standard_deviation = eq.standard_deviation
+    cfg.engine = _lib.ENGINES[engine]
     layers = None
     if mode == _lib.MODE_LEARNED:
       if hparams.model_target != 'coefficients':
@@ -270,6 +271,13 @@ class RowSolver(object):
         self._handle, float(t0), float(dt), int(num_steps), int(save_every), _lib.SCHEMES[scheme],
         _lib.host_ptr(u0), _lib.host_ptr(snaps), _lib.host_ptr(bad), u0.shape[0], sample_offset))
     return snaps, bad
+
+  def engine(self):
+    """'ffma' or 'tensor': the kernel the next launch will use."""
+    code = self._lib.ddd1d_engine(self._handle)
+    if code < 0:
+      self._check(code)
+    return {1: 'ffma', 2: 'tensor'}[code]
 
   def launch_count(self):
     return int(self._lib.ddd1d_launch_count(self._handle))

@@ -77,6 +77,12 @@ enum {
   DDD1D_RK4 = 3
 };
 
+/* conv-stack engine (learned mode).  AUTO picks the tcgen05 kernel when the net is
+ * the shape it is built for (kernel_size 5, filter_size 32, >= 2 layers, N in
+ * {128, 256, 512}) and the FP32-FFMA kernel otherwise; both satisfy the same
+ * float32 tolerances (the tensor path uses the 3xTF32 split). */
+enum { DDD1D_ENGINE_AUTO = 0, DDD1D_ENGINE_FFMA = 1, DDD1D_ENGINE_TENSOR = 2 };
+
 /* arithmetic of the WENO reconstruction: float32 (TF path, model.py:81-87) or
  * float64 (NumPy path of WENODifferentiator, integrate.py:137-138) */
 enum { DDD1D_REAL_F32 = 0, DDD1D_REAL_F64 = 1 };
@@ -103,7 +109,7 @@ typedef struct ddd1d_config {
   int net_outputs;         /* C = channels of the last conv */
   int stencil_size;        /* S = size of the coefficient grid (6 staggered, 7 centred) */
   int projection;          /* DDD1D_PROJ_* */
-  int reserved;
+  int engine;              /* DDD1D_ENGINE_*: which kernel evaluates the conv stack */
 } ddd1d_config;
 
 /* Build a handle.  Replaces graph construction in SavedModelDifferentiator /
@@ -188,6 +194,8 @@ int ddd1d_weno_reconstruct(int device, int real, const void* u, void* left, void
  * the launch shape the integrator uses (grid, block, dynamic shared bytes). */
 long long ddd1d_launch_count(const ddd1d_handle* handle);
 int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* block, int* shared_bytes);
+/* DDD1D_ENGINE_FFMA or DDD1D_ENGINE_TENSOR: the engine the next launch will use. */
+int ddd1d_engine(const ddd1d_handle* handle);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,18 @@
+/* Test-only entry points of libddd1d (not part of the drop-in surface). */
+#ifndef DDD1D_DEBUG_H_
+#define DDD1D_DEBUG_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* One 128-position tile of a 32 -> nout (16 | 32), 5-tap conv through the tcgen05 path
+ * (same shared-memory descriptors, 3xTF32 split and TMEM read-back as the row kernel).
+ *   x      device float [132][32]   inputs at positions -2..129
+ *   w_hi   device float [5*8][nout][4]   filters packed as B planes, high TF32 part
+ *   w_lo   device float [5*8][nout][4]   low part
+ *   out    device float [128][nout] */
+int ddd1d_debug_tc_probe(int device, const float* x, const float* w_hi, const float* w_lo, float* out,
+                         int nout, void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

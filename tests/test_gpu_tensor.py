@@ -1,0 +1,145 @@
+"""The tcgen05 / TMEM engine of the learned-coefficient kernel (csrc/ddd1d_tc.cuh):
+descriptor probe, parity against the oracle and against the FFMA engine.  Same
+float32 tolerances as the FFMA path (the tensor path is 3xTF32).  Runs after
+test_gpu_parity.py (alphabetical) so that a fault here cannot poison those tests."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import pde_oracle as O
+from tests.helpers import KINDS, VARIANTS, rel_err
+from tests import gpu_helpers as G
+
+pytestmark = pytest.mark.gpu
+
+RHS_TOL = 1e-5
+FLUX_TOL = 3e-5
+TRAJ_TOL = 1e-4
+
+
+def cpu(t):
+  return t.detach().cpu().numpy()
+
+
+def _split(w):
+  hi = (w.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+  return hi, (w - hi).astype(np.float32)
+
+
+@pytest.mark.parametrize('nout', (32, 16))
+def test_descriptor_probe(nout):
+  """One 128-position tile, 32 -> nout channels, 5 taps: validates the shared-memory
+  descriptors (tap shift by start address), the B packing, the 3xTF32 split and the
+  TMEM read-back in isolation."""
+  import torch
+  from ddd1d_b200 import _lib
+  lib = _lib.load()
+  rs = np.random.RandomState(nout)
+  x = rs.randn(132, 32).astype(np.float32)
+  w = (rs.randn(5, 32, nout) / 8).astype(np.float32)
+  packed = np.zeros((5 * 8, nout, 4), np.float32)
+  for k in range(5):
+    for ci in range(32):
+      packed[k * 8 + ci // 4, :, ci % 4] = w[k, ci, :]
+  hi, lo = _split(packed)
+  dx, dhi, dlo = (torch.as_tensor(a).cuda().contiguous() for a in (x, hi, lo))
+  out = torch.zeros((128, nout), dtype=torch.float32, device='cuda')
+  _lib.check(lib.ddd1d_debug_tc_probe(0, dx.data_ptr(), dhi.data_ptr(), dlo.data_ptr(), out.data_ptr(), nout,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+  torch.cuda.synchronize()
+  want = np.zeros((128, nout))
+  for k in range(5):
+    want += x[k:k + 128].astype(np.float64) @ w[k].astype(np.float64)
+  err = rel_err(cpu(out), want)
+  assert err < 2e-6, err
+
+
+def _solvers(kind, variant, n, seed=0):
+  from ddd1d_b200 import runtime
+  eq = G.product_equation(kind, variant, n, seed=3)
+  hp = G.product_hparams(kind, variant, n)
+  oeq = G.oracle_equation(kind, variant, n, seed=3)
+  w = O.glorot_weights(oeq, O.NetSpec(), seed=seed, last_layer_scale=0.1, bias_scale=0.1)
+  tensor = runtime.learned_solver(eq, hp, w, engine='tensor')
+  ffma = runtime.learned_solver(eq, hp, w, engine='ffma')
+  assert tensor.engine() == 'tensor' and ffma.engine() == 'ffma'
+  return tensor, ffma, oeq, w
+
+
+@pytest.mark.parametrize('kind', KINDS)
+@pytest.mark.parametrize('variant', VARIANTS)
+def test_tensor_engine_per_call_parity(kind, variant):
+  n = 128
+  tensor, ffma, oeq, w = _solvers(kind, variant, n)
+  u = G.smooth_rows(5, n, seed=7)
+  net = O.NetSpec()
+  want_c = O.predict_coefficients(u, oeq, net, w)
+  assert rel_err(cpu(tensor.coefficients(u)), want_c) < RHS_TOL
+  want_d = O.apply_coefficients(want_c, u)
+  assert rel_err(cpu(tensor.space_derivatives(u)), want_d) < RHS_TOL
+  tol = RHS_TOL if variant == 'plain' else FLUX_TOL
+  want_t = oeq.finalize_time_derivative(np.float32(0.4), O.predict_time_derivative(u[:1], oeq, net, w),
+                                        dtype=np.float32)
+  assert rel_err(cpu(tensor.rhs(0.4, u[:1])), want_t) < tol
+  assert rel_err(cpu(tensor.rhs(0.4, u[:1])), cpu(ffma.rhs(0.4, u[:1]))) < tol
+  # float64 rows (what SciPy hands over)
+  assert rel_err(cpu(tensor.rhs(0.4, u[:1].astype(np.float64))), want_t) < tol
+
+
+@pytest.mark.parametrize('n,kind,dt', ((256, 'burgers', 1e-3), (128, 'kdv', 2.5e-5), (512, 'ks', 1e-5)))
+def test_tensor_engine_trajectories(n, kind, dt):
+  """BASELINE shapes C2/C3/C4 on the tensor engine: odd batch sizes exercise teams that
+  own different numbers of rows (and none at all)."""
+  import torch
+  from ddd1d_b200 import runtime
+  for batch in (1, 3, 301):
+    eqs = [G.product_equation(kind, 'plain', n, seed=s) for s in range(batch)]
+    oeq0 = G.oracle_equation(kind, 'plain', n)
+    w = O.glorot_weights(oeq0, O.NetSpec(), seed=1, last_layer_scale=0.01)
+    solver = runtime.learned_solver(eqs, G.product_hparams(kind, 'plain', n), w, engine='tensor')
+    u0 = G.smooth_rows(batch, n, seed=batch)
+    steps = 6
+    got, bad = solver.integrate(u0, 0.05, dt, steps, 3, return_first_bad=True)
+    assert tuple(got.shape) == (2, batch, n)
+    assert (cpu(bad) == -1).all()
+    pick = sorted({0, batch // 2, batch - 1})
+    oeqs = [G.oracle_equation(kind, 'plain', n, seed=i) for i in pick]
+    rhs = O.batched_rhs(oeqs, O.NetSpec(), w, mode='learned')
+    want = O.fixed_step_integrate(rhs, u0[pick], 0.05, dt, steps, 3)
+    assert rel_err(cpu(got[:, pick]), want) < TRAJ_TOL
+    again = solver.integrate(u0, 0.05, dt, steps, 3)
+    assert torch.equal(again, got)
+
+
+def test_tensor_engine_other_nets_and_schemes():
+  """2-layer net, raw (accuracy-order 0) projection, tanh; midpoint scheme."""
+  from ddd1d_b200 import runtime
+  n = 128
+  for overrides in (dict(num_layers=2), dict(polynomial_accuracy_order=0), dict(nonlinearity='tanh'),
+                    dict(polynomial_accuracy_order=0, ensure_unbiased_coefficients=True)):
+    eq = G.product_equation('burgers', 'plain', n)
+    hp = G.product_hparams('burgers', 'plain', n, **overrides)
+    net = O.NetSpec(**overrides)
+    oeq = G.oracle_equation('burgers', 'plain', n)
+    w = O.glorot_weights(oeq, net, seed=4, last_layer_scale=0.1, bias_scale=0.1)
+    solver = runtime.learned_solver(eq, hp, w, engine='tensor', forcing=False)
+    u = G.smooth_rows(3, n, seed=1)
+    assert rel_err(cpu(solver.coefficients(u)), O.predict_coefficients(u, oeq, net, w)) < RHS_TOL, overrides
+    assert rel_err(cpu(solver.rhs(0.0, u)), O.predict_time_derivative(u, oeq, net, w)) < RHS_TOL, overrides
+  snaps = solver.integrate(u, 0.0, 1e-3, 4, 2, 'midpoint')
+  rhs = O.batched_rhs([oeq], net, w, mode='learned')
+  # forcing disabled on the GPU side: compare with an unforced oracle RHS
+  unforced = lambda t, y: O.predict_time_derivative(np.asarray(y, np.float32), oeq, net, w)
+  want = O.fixed_step_integrate(unforced, u, 0.0, 1e-3, 4, 2, scheme='midpoint')
+  assert rel_err(cpu(snaps), want) < TRAJ_TOL
+
+
+def test_tensor_engine_rejects_unsupported_shapes():
+  from ddd1d_b200 import runtime
+  eq = G.product_equation('burgers', 'plain', 64)
+  hp = G.product_hparams('burgers', 'plain', 64)
+  w = O.glorot_weights(G.oracle_equation('burgers', 'plain', 64), O.NetSpec(), seed=0)
+  with pytest.raises(NotImplementedError):
+    runtime.learned_solver(eq, hp, w, engine='tensor').engine()
+  assert runtime.learned_solver(eq, hp, w).engine() == 'ffma'
