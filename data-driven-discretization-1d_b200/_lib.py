@@ -60,6 +60,8 @@ _SIGNATURES = {
     'ddd1d_space_derivatives': (ctypes.c_int, [_P, _P, _P, ctypes.c_int, _P]),
     'ddd1d_integrate': (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, _P, _P, _P, ctypes.c_int, ctypes.c_int, _P]),
+    'ddd1d_integrate_adaptive': (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                ctypes.c_double, _P, _P, _P, _P, _P, ctypes.c_int, ctypes.c_int, _P]),
     'ddd1d_rhs_host': (ctypes.c_int, [_P, ctypes.c_double, _P, _P, ctypes.c_int, ctypes.c_int]),
     'ddd1d_integrate_host': (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, _P, _P, _P, ctypes.c_int,

@@ -62,6 +62,8 @@ struct ddd1d_handle {
   void* d_stage_in = nullptr;
   void* d_stage_out = nullptr;
   int* d_stage_bad = nullptr;
+  double* d_times = nullptr;
+  size_t times_cap = 0;
   size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_bad_bytes = 0;
 };
 
@@ -106,10 +108,10 @@ double plan_cost(int cout, int N, int nwarps, int cg, int pbt) {
 }
 
 
-float tf32_hi(float v) {
+float tf32_hi(float v) {   // round to TF32 (10 explicit mantissa bits), as ddd1d::tc::round_tf32
   uint32_t b;
   memcpy(&b, &v, 4);
-  b &= 0xffffe000u;
+  b = (b + 0x1000u) & 0xffffe000u;
   float r;
   memcpy(&r, &b, 4);
   return r;
@@ -194,7 +196,7 @@ int finalize_tc(ddd1d_handle* h) {
           const float w = hl.kernel[((size_t)k * F + ci) * F + co];
           const size_t idx = ((size_t)(k * tc::kChunks + ci / 4) * F + co) * 4 + (ci % 4);
           hi[idx] = tf32_hi(w);
-          lo[idx] = w - hi[idx];
+          lo[idx] = tf32_hi(w - hi[idx]);
         }
   }
   // last layer with the projection folded in: W'[k][ci][q] = sum_c W[k][ci][c] pm[c][q]
@@ -213,7 +215,7 @@ int finalize_tc(ddd1d_handle* h) {
           const float w = (float)acc;
           const size_t idx = ((size_t)(k * tc::kChunks + ci / 4) * NL + q) * 4 + (ci % 4);
           hi[idx] = tf32_hi(w);
-          lo[idx] = w - hi[idx];
+          lo[idx] = tf32_hi(w - hi[idx]);
         }
     for (int q = 0; q < Q; ++q) {
       double acc = pbias[q];
@@ -233,7 +235,7 @@ int finalize_tc(ddd1d_handle* h) {
   P.tc_t_ust = t; t += align_up((N + 2 * kHalo) * 4, 16);
   P.tc_t_k = t; t += kMaxStages * N * 4;
   P.tc_t_flux = t; t += N * 4;
-  P.tc_t_fs = t; t += align_up((4 * kMaxModes + 4) * 4, 16);
+  P.tc_t_fs = t; t += align_up((2 * kMaxModes + 3 * kMaxForcing + 4) * 4, 16);
   P.tc_team_stride = align_up(t, 128);
   P.off_bar = 0;
   P.tc_off_slot = 112;
@@ -253,7 +255,7 @@ int finalize_tc(ddd1d_handle* h) {
   CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   P.blob = h->d_blob_tc;
   CUDA_TRY(h, cudaFuncSetAttribute(tc::tc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  h->tc_threads = P.tc_teams * N + 32;
+  h->tc_threads = P.tc_teams * (N + 32);     // N threads + one MMA-issuer warp per team
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_row_kernel, h->tc_threads, P.smem_bytes));
   if (occ < 1) {
@@ -392,9 +394,11 @@ int finalize(ddd1d_handle* h) {
   P.off_blob = off; off += P.blob_floats * 4;
   P.off_ust = off; off += align_up((N + 2 * kHalo) * 4, 16);
   P.off_ydbl = off; off += align_up(N * 8, 16);
+  P.off_ynew = off; off += align_up(N * 8, 16);
+  P.off_red = off; off += 34 * 8;
   P.off_k = off; off += align_up(kMaxStages * N * 4, 16);
   P.off_flux = off; off += align_up((N + 1) * 4, 16);
-  P.off_fs = off; off += 2 * kMaxModes * 4;
+  P.off_fs = off; off += (2 * kMaxModes + 3 * kMaxForcing) * 4;
   P.off_act0 = off;
   P.off_act1 = off;
   if (c.mode == DDD1D_MODE_LEARNED) {
@@ -451,7 +455,7 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
                 W.sample_offset + W.batch, P.fcap);
   CUDA_TRY(h, cudaSetDevice(c.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (use_tc(h)) {
+  if (use_tc(h) && W.op != OP_ADAPTIVE) {
     const Params& T = h->Ptc;
     const int teams_needed = (W.batch + T.tc_teams - 1) / T.tc_teams;
     const int grid_tc = std::min(teams_needed, h->num_sms);
@@ -557,6 +561,7 @@ int ddd1d_destroy(ddd1d_handle* h) {
   cudaFree(h->d_stage_in);
   cudaFree(h->d_stage_out);
   cudaFree(h->d_stage_bad);
+  cudaFree(h->d_times);
   delete h;
   return DDD1D_OK;
 }
@@ -622,6 +627,8 @@ int ddd1d_set_forcing(ddd1d_handle* h, const double* a, const double* omega, con
     M = std::max(M, (int)std::fabs(kk));
   }
   if (M > kMaxModes) return fail(h, DDD1D_EUNSUPPORTED, "|k| up to %d supported, got %d", kMaxModes, M);
+  if (nparams > kMaxForcing)
+    return fail(h, DDD1D_EUNSUPPORTED, "up to %d forcing terms per sample supported, got %d", kMaxForcing, nparams);
   if (M == 0) M = 1;
   std::vector<float> fp((size_t)batch * 4 * P);
   for (int b = 0; b < batch; ++b)
@@ -708,6 +715,34 @@ int ddd1d_integrate(ddd1d_handle* h, double t0, double dt, int num_steps, int sa
   W.op = OP_INTEGRATE; W.batch = batch; W.sample_offset = sample_offset; W.u = u0; W.snaps = snapshots;
   W.first_bad = first_bad_step; W.t0 = t0; W.dt = dt; W.nsteps = num_steps; W.save_every = save_every;
   W.scheme = scheme;
+  return launch(h, W, stream);
+}
+
+int ddd1d_integrate_adaptive(ddd1d_handle* h, const double* times, int num_times, double rtol, double atol,
+                             double max_step, const float* u0, const double* u0_f64, double* y_out, int* nfev,
+                             int* status, int batch, int sample_offset, void* stream) {
+  if (!h) return fail(h, DDD1D_EINVAL, "null handle");
+  if (!times || num_times < 2) return fail(h, DDD1D_EINVAL, "need at least two output times");
+  for (int i = 1; i < num_times; ++i)
+    if (!(times[i] > times[i - 1])) return fail(h, DDD1D_EINVAL, "times must be strictly increasing");
+  if (!(rtol > 0) || !(atol >= 0) || !(max_step > 0)) return fail(h, DDD1D_EINVAL, "bad tolerances");
+  if (batch == 0) return DDD1D_OK;
+  if ((!u0 && !u0_f64) || !y_out) return fail(h, DDD1D_EINVAL, "null argument");
+  int rc = finalize(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (h->times_cap < (size_t)num_times) {
+    if (h->d_times) CUDA_TRY(h, cudaFree(h->d_times));
+    h->d_times = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->d_times, (size_t)num_times * sizeof(double)));
+    h->times_cap = (size_t)num_times;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_times, times, (size_t)num_times * sizeof(double), cudaMemcpyHostToDevice, st));
+  Work W = blank_work();
+  W.op = OP_ADAPTIVE; W.batch = batch; W.sample_offset = sample_offset; W.u = u0; W.u64 = u0_f64;
+  W.times = h->d_times; W.ntimes = num_times; W.rtol = rtol; W.atol = atol; W.max_step = max_step;
+  W.y_out = y_out; W.nfev = nfev; W.status = status;
   return launch(h, W, stream);
 }
 

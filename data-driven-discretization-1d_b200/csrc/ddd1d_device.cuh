@@ -21,8 +21,9 @@ constexpr int kHalo = 3;        // halo of the raw stage row
 constexpr int kMaxLayers = 6;
 constexpr int kMaxStages = 4;
 constexpr int kMaxModes = 8;
+constexpr int kMaxForcing = 32;  // forcing terms per sample (the reference uses 20 / 10)
 
-enum Op { OP_RHS = 0, OP_COEF = 1, OP_DERIV = 2, OP_INTEGRATE = 3 };
+enum Op { OP_RHS = 0, OP_COEF = 1, OP_DERIV = 2, OP_INTEGRATE = 3, OP_ADAPTIVE = 4 };
 enum Mode { MODE_STENCIL = 0, MODE_LEARNED = 1, MODE_WENO = 2 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_TANH = 3, ACT_SOFTPLUS = 4, ACT_ELU = 5 };
 enum Proj { PROJ_NULLSPACE = 0, PROJ_RAW = 1, PROJ_RAW_UNBIASED = 2 };
@@ -56,7 +57,7 @@ struct Params {
   const float* fparams;     // [fcap][4][P]: a, omega, phi, signed k
   const float* fbasis;      // [2M][N]: resampled cos(2 pi m x/L), sin(2 pi m x/L), m = 1..M
   // shared memory carve-up (byte offsets)
-  int off_bar, off_blob, off_ust, off_ydbl, off_k, off_flux, off_fs, off_act0, off_act1;
+  int off_bar, off_blob, off_ust, off_ydbl, off_ynew, off_red, off_k, off_flux, off_fs, off_act0, off_act1;
   int smem_bytes;
   int use_bulk_copy;
   // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
@@ -77,7 +78,18 @@ struct Work {
   int nsteps, save_every, scheme;
   float* snaps;        // [nsteps/save_every][batch][N]
   int* first_bad;      // [batch] or null
+  // OP_ADAPTIVE (scipy RK23 twin): output times, tolerances, float64 record
+  const double* times; // device [ntimes], increasing; times[0] is the start time
+  int ntimes;
+  double rtol, atol, max_step;
+  double* y_out;       // [ntimes][batch][N], NaN where the solver gave up
+  int* nfev;           // [batch]
+  int* status;         // [batch]: 0 reached the end, -1 step size underflow
 };
+
+// The one dynamic shared-memory window of every kernel in this library.  Device functions that
+// are not inlined re-derive their pointers from this symbol so loads stay LDS/STS.
+extern __shared__ __align__(128) unsigned char dyn_smem[];
 
 // ---------------------------------------------------------------------------------
 // Runge-Kutta tableaus.  RK3 is Bogacki-Shampine as in scipy/integrate/_ivp/rk.py
@@ -368,9 +380,11 @@ struct Smem {
   float* blob;
   float* ust;     // raw stage row, index x + kHalo, halo filled
   double* ydbl;   // float64 state
+  double* ynew;   // float64 trial state (adaptive stepping)
+  double* red;    // reduction scratch [34]
   float* k;       // [kMaxStages][N] stage slopes
   float* flux;    // [N + 1]
-  float* fs;      // [2 * kMaxModes] forcing mode amplitudes
+  float* fs;      // [2*kMaxModes] mode amplitudes | [2*kMaxForcing] per-term sin/cos parts | [kMaxForcing] |k|
   float* act0;
   float* act1;
 };
@@ -381,6 +395,8 @@ __device__ __forceinline__ Smem carve(const Params& P, unsigned char* base) {
   s.blob = reinterpret_cast<float*>(base + P.off_blob);
   s.ust = reinterpret_cast<float*>(base + P.off_ust);
   s.ydbl = reinterpret_cast<double*>(base + P.off_ydbl);
+  s.ynew = reinterpret_cast<double*>(base + P.off_ynew);
+  s.red = reinterpret_cast<double*>(base + P.off_red);
   s.k = reinterpret_cast<float*>(base + P.off_k);
   s.flux = reinterpret_cast<float*>(base + P.off_flux);
   s.fs = reinterpret_cast<float*>(base + P.off_fs);
@@ -402,26 +418,45 @@ __device__ __forceinline__ void write_stage_row(const Params& P, const Smem& S, 
   }
 }
 
-// Forcing mode amplitudes at time t for one sample:
+// Forcing at time t for one sample:
 //   F(x,t) = sum_p a_p sin(w_p t + 2 pi k_p x / L + phi_p)           (equations.py:214-219)
 //          = sum_m [sum_{|k_p|=m} a_p sin(w_p t + phi_p)] cos(2 pi m x/L)
 //                + [sum_{|k_p|=m} sgn(k_p) a_p cos(w_p t + phi_p)] sin(2 pi m x/L)
-__device__ __forceinline__ void forcing_amplitudes(const Params& P, const Smem& S, int sample, float t) {
-  const int M = P.M;
-  if (threadIdx.x < 2 * M) {
+// Term p lives in the registers of thread p for the whole row (ForcingTerm); each RHS evaluation
+// costs one sincosf on P threads (forcing_terms), a barrier the caller already has, and a
+// P-term sum on 2M threads (forcing_reduce).
+struct ForcingTerm { float a, w, phi, k; };
+
+__device__ __forceinline__ ForcingTerm load_forcing_term(const Params& P, int sample, int q) {
+  ForcingTerm f = {0.f, 0.f, 0.f, 0.f};
+  if (P.P > 0 && q < P.P) {
     const float* fp = P.fparams + (size_t)sample * 4 * P.P;
-    const int m = (threadIdx.x < M ? threadIdx.x : threadIdx.x - M) + 1;
-    const bool is_cos_amp = threadIdx.x < M;
+    f.a = __ldg(fp + q); f.w = __ldg(fp + P.P + q); f.phi = __ldg(fp + 2 * P.P + q); f.k = __ldg(fp + 3 * P.P + q);
+  }
+  return f;
+}
+
+// fs layout: [0, 2*kMaxModes) amplitudes, then 2*kMaxForcing per-term parts, then kMaxForcing |k|
+__device__ __forceinline__ void forcing_terms(const Params& P, float* fs, const ForcingTerm& f, int q, float t) {
+  if (q < P.P) {
+    float sn, cs;
+    sincosf(fmaf(f.w, t, f.phi), &sn, &cs);
+    float* parts = fs + 2 * kMaxModes;
+    parts[q] = f.a * sn;
+    parts[kMaxForcing + q] = (f.k < 0.f ? -f.a : f.a) * cs;
+    parts[2 * kMaxForcing + q] = fabsf(f.k);
+  }
+}
+
+__device__ __forceinline__ void forcing_reduce(const Params& P, float* fs, int j) {
+  if (j < 2 * P.M) {
+    const float* parts = fs + 2 * kMaxModes;
+    const float m = (float)((j < P.M ? j : j - P.M) + 1);
+    const float* src = parts + (j < P.M ? 0 : kMaxForcing);
     float acc = 0.f;
-    for (int q = 0; q < P.P; ++q) {
-      float kk = fp[3 * P.P + q];
-      if (fabsf(kk) != (float)m) continue;
-      float ph = fmaf(fp[P.P + q], t, fp[2 * P.P + q]);
-      float sn, cs;
-      sincosf(ph, &sn, &cs);
-      acc += is_cos_amp ? fp[q] * sn : (kk < 0.f ? -fp[q] : fp[q]) * cs;
-    }
-    S.fs[threadIdx.x] = acc;
+    for (int q = 0; q < P.P; ++q)
+      if (parts[2 * kMaxForcing + q] == m) acc += src[q];
+    fs[j] = acc;
   }
 }
 
@@ -530,15 +565,17 @@ __device__ __forceinline__ bool eq_conservative(int eq) { return (eq % 3) != 0; 
 __device__ __forceinline__ bool eq_forced(int eq) { return eq < 3; }   // Burgers family, equations.py:276-277
 
 // Cooperative RHS evaluation.  Preconditions: S.ust holds the stage row (halo
-// filled) and a __syncthreads() has made it visible.  Postcondition: kout[p],
+// filled) and a __syncthreads() has made it visible.  Postcondition: S.k[kslot][p],
 // p < N, holds dy/dt (float32) and is visible to all threads.
 template <int MODE>
-__device__ void row_rhs(const Params& P, const Smem& S, int sample, float t, float* kout, int op,
-                        float* gout_row) {
+__device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, float t, int kslot, int op,
+                                     float* gout_row) {
+  const Smem S = carve(P, dyn_smem);
+  float* kout = S.k + kslot * P.N;
   const int N = P.N;
   const float* net = nullptr;
   const bool forced = eq_forced(P.eq) && P.P > 0 && op != OP_COEF && op != OP_DERIV;
-  if (forced) forcing_amplitudes(P, S, sample, t);
+  if (forced) forcing_terms(P, S.fs, fterm, threadIdx.x, t);
 
   if (MODE == MODE_LEARNED) {
     // net = inputs / standard_deviation (model.py:450-451), channel 0 of act0
@@ -550,6 +587,7 @@ __device__ void row_rhs(const Params& P, const Smem& S, int sample, float t, flo
       for (int q = p + N; q < N + kr; q += N) S.act0[q + kl] = v;
     }
     __syncthreads();
+    if (forced) forcing_reduce(P, S.fs, threadIdx.x);   // visible after the conv barriers
     float* in = S.act0;
     float* out = S.act1;
     for (int l = 0; l < P.nlayers; ++l) {
@@ -571,8 +609,10 @@ __device__ void row_rhs(const Params& P, const Smem& S, int sample, float t, flo
       float* tmp = in; in = out; out = tmp;
     }
     net = in;
-  } else {
-    __syncthreads();   // forcing amplitudes visible
+  } else if (forced) {
+    __syncthreads();
+    forcing_reduce(P, S.fs, threadIdx.x);
+    __syncthreads();
   }
 
   const bool cons = eq_conservative(P.eq);
@@ -608,14 +648,177 @@ __device__ void row_rhs(const Params& P, const Smem& S, int sample, float t, flo
   __syncthreads();
 }
 
+
+// ---------------------------------------------------------------------------------
+// Adaptive Bogacki-Shampine 3(2): a per-row twin of scipy.integrate.solve_ivp(method='RK23',
+// rtol, atol, max_step, t_eval) as driven by integrate.odeint (integrate.py:143-169), following
+// scipy/integrate/_ivp/{rk.py,base.py,common.py,ivp.py}: select_initial_step, the step-size
+// controller (SAFETY 0.9, MIN_FACTOR 0.2, MAX_FACTOR 10, exponent -1/3, RMS norm), FSAL, and the
+// cubic dense output at t_eval.  float64 state and slopes-as-float64, float32 right-hand side.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(const Smem& S, double v) {
+  // deterministic: warp shuffles then a fixed-order sum over the warp partials, broadcast via shared
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) S.red[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < nwarps; ++w) t += S.red[w];
+    S.red[32] = t;
+  }
+  __syncthreads();
+  return S.red[32];
+}
+
+template <int MODE>
+__device__ void row_adaptive(const Params& P, const Smem& S, const Work& W, int row, const ForcingTerm& fterm) {
+  const int N = P.N;
+  const double t_start = W.times[0], t_bound = W.times[W.ntimes - 1];
+  const double rtol = W.rtol, atol = W.atol, max_step = W.max_step;
+  const double inv_sqrt_n = 1.0 / sqrt((double)N);
+  float* K0 = S.k;
+  float* K1 = S.k + N;
+  float* K2 = S.k + 2 * N;
+  float* K3 = S.k + 3 * N;
+  int nfev = 0, status = 0, next_out = 0;
+  double t = t_start;
+
+  // f0 = fun(t0, y0)
+  write_stage_row(P, S, [&](int p) { return (float)S.ydbl[p]; });
+  __syncthreads();
+  row_rhs<MODE>(P, fterm, (float)t, 0, OP_RHS, nullptr);
+  nfev++;
+
+  // select_initial_step (common.py)
+  double h_abs;
+  {
+    const double interval = fabs(t_bound - t_start);
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      const double sc = atol + fabs(S.ydbl[p]) * rtol;
+      const double a = S.ydbl[p] / sc, b = (double)K0[p] / sc;
+      s0 += a * a;
+      s1 += b * b;
+    }
+    const double d0 = sqrt(block_sum(S, s0)) * inv_sqrt_n;
+    const double d1 = sqrt(block_sum(S, s1)) * inv_sqrt_n;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, interval);
+    write_stage_row(P, S, [&](int p) { return (float)(S.ydbl[p] + h0 * (double)K0[p]); });
+    __syncthreads();
+    row_rhs<MODE>(P, fterm, (float)(t + h0), 1, OP_RHS, nullptr);
+    nfev++;
+    double s2 = 0.0;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      const double sc = atol + fabs(S.ydbl[p]) * rtol;
+      const double a = ((double)K1[p] - (double)K0[p]) / sc;
+      s2 += a * a;
+    }
+    const double d2 = sqrt(block_sum(S, s2)) * inv_sqrt_n / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 3.0);
+    h_abs = fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
+  }
+
+  // t_eval points at (or before) the start are the initial state itself (ivp.py: side='right')
+  while (next_out < W.ntimes && W.times[next_out] <= t) {
+    double* dst = W.y_out + ((size_t)next_out * W.batch + row) * N;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) dst[p] = S.ydbl[p];
+    ++next_out;
+  }
+
+  while (t < t_bound) {
+    const double min_step = 10.0 * fabs(nextafter(t, CUDART_INF) - t);
+    if (h_abs > max_step) h_abs = max_step;
+    else if (h_abs < min_step) h_abs = min_step;
+    bool accepted = false, rejected = false;
+    double h = 0.0, t_new = t;
+    while (!accepted) {
+      if (h_abs < min_step) { status = -1; break; }
+      h = h_abs;
+      t_new = t + h;
+      if (t_new - t_bound > 0.0) t_new = t_bound;
+      h = t_new - t;
+      h_abs = fabs(h);
+      // rk_step (rk.py): K0 = f (FSAL), two inner stages, y_new, f_new
+      write_stage_row(P, S, [&](int p) { return (float)(S.ydbl[p] + (0.5 * (double)K0[p]) * h); });
+      __syncthreads();
+      row_rhs<MODE>(P, fterm, (float)(t + 0.5 * h), 1, OP_RHS, nullptr);
+      write_stage_row(P, S, [&](int p) { return (float)(S.ydbl[p] + (0.75 * (double)K1[p]) * h); });
+      __syncthreads();
+      row_rhs<MODE>(P, fterm, (float)(t + 0.75 * h), 2, OP_RHS, nullptr);
+      for (int p = threadIdx.x; p < N; p += blockDim.x)
+        S.ynew[p] = S.ydbl[p] + h * ((2.0 / 9.0) * (double)K0[p] + (1.0 / 3.0) * (double)K1[p] +
+                                     (4.0 / 9.0) * (double)K2[p]);
+      write_stage_row(P, S, [&](int p) { return (float)S.ynew[p]; });
+      __syncthreads();
+      row_rhs<MODE>(P, fterm, (float)(t + h), 3, OP_RHS, nullptr);
+      nfev += 3;
+      double se = 0.0;
+      for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const double sc = atol + fmax(fabs(S.ydbl[p]), fabs(S.ynew[p])) * rtol;
+        const double e = ((5.0 / 72.0) * (double)K0[p] + (-1.0 / 12.0) * (double)K1[p] +
+                          (-1.0 / 9.0) * (double)K2[p] + (1.0 / 8.0) * (double)K3[p]) * h / sc;
+        se += e * e;
+      }
+      const double err = sqrt(block_sum(S, se)) * inv_sqrt_n;
+      if (err < 1.0) {
+        double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -1.0 / 3.0));
+        if (rejected) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        accepted = true;
+      } else {
+        // NaN error norms land here too: python's max(0.2, nan) is 0.2
+        const double shrink = 0.9 * pow(err, -1.0 / 3.0);
+        h_abs *= (shrink > 0.2) ? shrink : 0.2;
+        rejected = true;
+      }
+    }
+    if (!accepted) break;
+    // dense output (RkDenseOutput with P of RK23) for every requested time in (t, t_new]
+    while (next_out < W.ntimes && W.times[next_out] <= t_new) {
+      const double xq = (W.times[next_out] - t) / h;
+      double* dst = W.y_out + ((size_t)next_out * W.batch + row) * N;
+      for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const double k0 = K0[p], k1 = K1[p], k2 = K2[p], k3 = K3[p];
+        const double q0 = k0;
+        const double q1 = (-4.0 / 3.0) * k0 + k1 + (4.0 / 3.0) * k2 - k3;
+        const double q2 = (5.0 / 9.0) * k0 + (-2.0 / 3.0) * k1 + (-8.0 / 9.0) * k2 + k3;
+        dst[p] = S.ydbl[p] + h * (q0 * xq + q1 * (xq * xq) + q2 * (xq * xq * xq));
+      }
+      ++next_out;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      S.ydbl[p] = S.ynew[p];
+      K0[p] = K3[p];          // FSAL
+    }
+    t = t_new;
+    __syncthreads();
+  }
+  // the reference pads what the solver did not reach with NaN (integrate.py:161-167)
+  for (; next_out < W.ntimes; ++next_out) {
+    double* dst = W.y_out + ((size_t)next_out * W.batch + row) * N;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) dst[p] = CUDART_NAN;
+  }
+  if (threadIdx.x == 0) {
+    if (W.nfev) W.nfev[row] = nfev;
+    if (W.status) W.status[row] = status;
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------
 // The persistent row kernel
 // ---------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
-    row_kernel(const Params P, const Work W) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Smem S = carve(P, smem_raw);
+    row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
+  const Smem S = carve(P, dyn_smem);
   const int N = P.N;
 
   // ---- stage the constant blob (filters, biases, window tables) once per CTA ----
@@ -644,6 +847,7 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
 
   for (int row = blockIdx.x; row < W.batch; row += gridDim.x) {
     const int sample = W.sample_offset + row;
+    const ForcingTerm fterm = load_forcing_term(P, sample, threadIdx.x);
     // ---- load the row: float64 master copy + float32 stage row ----
     if (W.u64) {
       for (int p = threadIdx.x; p < N; p += blockDim.x) S.ydbl[p] = W.u64[(size_t)row * N + p];
@@ -658,13 +862,17 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
     }
     __syncthreads();
 
+    if (W.op == OP_ADAPTIVE) {
+      row_adaptive<MODE>(P, S, W, row, fterm);
+      continue;
+    }
     if (W.op != OP_INTEGRATE) {
       write_stage_row(P, S, [&](int p) { return (float)S.ydbl[p]; });
       __syncthreads();
       float* gout = nullptr;
       if (W.op == OP_COEF) gout = W.out + (size_t)row * N * P.D * P.S;
       if (W.op == OP_DERIV) gout = W.out + (size_t)row * N * P.D;
-      row_rhs<MODE>(P, S, sample, (float)W.t0, S.k, W.op, gout);
+      row_rhs<MODE>(P, fterm, (float)W.t0, 0, W.op, gout);
       if (W.op == OP_RHS) {
         if (W.out64) {
           for (int p = threadIdx.x; p < N; p += blockDim.x) W.out64[(size_t)row * N + p] = (double)S.k[p];
@@ -692,7 +900,7 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
           return (float)(s == 0 ? S.ydbl[p] : S.ydbl[p] + W.dt * acc);
         });
         __syncthreads();
-        row_rhs<MODE>(P, S, sample, (float)(t + tab.c[s] * W.dt), S.k + s * N, OP_RHS, nullptr);
+        row_rhs<MODE>(P, fterm, (float)(t + tab.c[s] * W.dt), s, OP_RHS, nullptr);
       }
       const bool save = ((step + 1) % W.save_every) == 0;
       float* snap = save ? W.snaps + ((size_t)save_idx * W.batch + row) * N : nullptr;
@@ -712,7 +920,7 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
     if (W.first_bad) {
       // min over the CTA of the first non-finite step (-1 = none)
       unsigned int key = first_bad < 0 ? 0xffffffffu : (unsigned int)first_bad;
-      unsigned int* slot = reinterpret_cast<unsigned int*>(S.fs);
+      unsigned int* slot = reinterpret_cast<unsigned int*>(S.red);
       if (threadIdx.x == 0) *slot = 0xffffffffu;
       __syncthreads();
       atomicMin(slot, key);
@@ -729,8 +937,7 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
 template <typename T>
 __global__ void weno_kernel(const T* __restrict__ u, T* __restrict__ left, T* __restrict__ right, int batch,
                             int N) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* row = reinterpret_cast<T*>(smem_raw);   // index x + 3, halo 3 + 4
+  T* row = reinterpret_cast<T*>(dyn_smem);   // index x + 3, halo 3 + 4
   for (int r = blockIdx.x; r < batch; r += gridDim.x) {
     for (int q = threadIdx.x; q < N + 7; q += blockDim.x) row[q] = u[(size_t)r * N + wrap(q - 3, N)];
     __syncthreads();

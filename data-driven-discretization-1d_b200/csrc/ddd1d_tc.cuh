@@ -142,10 +142,14 @@ __device__ __forceinline__ void team_sync(int team, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(threads) : "memory");
 }
 
-// x = hi + lo, hi exactly representable in TF32
+// x = hi + lo with hi = x rounded to TF32 (round-half-up on the magnitude) and lo = the exact
+// remainder, itself rounded to TF32, so the tensor core's truncation of its inputs never acts.
+__device__ __forceinline__ float round_tf32(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  lo = v - hi;
+  hi = round_tf32(v);
+  lo = round_tf32(v - hi);
 }
 
 // ---- shared layouts ----------------------------------------------------------------------------
@@ -159,26 +163,43 @@ struct TcView {
   unsigned char* team_base;
 };
 
-// Issue all MMAs of one layer for one team (one thread).
+// Issue all MMAs of one layer for one team (one thread).  Descriptors are kept as (lo, hi) 32-bit
+// halves: hi (stride offset | version) never changes, lo = start>>4 | lbo>>4 << 16 advances by plain
+// 32-bit adds, so one (tap, ci-block) step costs four adds and three tcgen05.mma.
+__device__ __forceinline__ void mma_tf32_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __noinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes,
-                                            uint32_t b_hi, uint32_t b_lo, uint32_t b_plane_bytes, int tiles,
-                                            uint32_t tmem_col0, uint32_t idesc) {
+                                         uint32_t b_hi, uint32_t b_lo, uint32_t b_plane_bytes, int tiles,
+                                         uint32_t tmem_col0, uint32_t idesc) {
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1 (bits 32..47)
+  const uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
+  const uint32_t a_field = plane16 << 16, b_field = bplane16 << 16;   // LBO fields
+  const uint32_t ah0 = ((act_hi >> 4) & 0x3FFFu) | a_field, al0 = ((act_lo >> 4) & 0x3FFFu) | a_field;
+  const uint32_t bh0 = ((b_hi >> 4) & 0x3FFFu) | b_field, bl0 = ((b_lo >> 4) & 0x3FFFu) | b_field;
   for (int m = 0; m < tiles; ++m) {
     const uint32_t d = tmem_col0 + (uint32_t)m * 32u;
     uint32_t accumulate = 0;
+    uint32_t ah = ah0 + (uint32_t)m * 128u, al = al0 + (uint32_t)m * 128u;   // 128 rows * 16 B >> 4
+    uint32_t bh = bh0, bl = bl0;
 #pragma unroll
     for (int k = 0; k < kTaps; ++k) {
 #pragma unroll
       for (int kb = 0; kb < kChunks / 2; ++kb) {
-        const uint32_t a_off = (uint32_t)(2 * kb) * plane_bytes + (uint32_t)(128 * m + k) * 16u;
-        const uint32_t b_off = (uint32_t)(k * kChunks + 2 * kb) * b_plane_bytes;
-        const uint64_t ah = smem_desc(act_hi + a_off, plane_bytes, 128);
-        const uint64_t al = smem_desc(act_lo + a_off, plane_bytes, 128);
-        const uint64_t bh = smem_desc(b_hi + b_off, b_plane_bytes, 128);
-        const uint64_t bl = smem_desc(b_lo + b_off, b_plane_bytes, 128);
-        mma_tf32(d, ah, bh, idesc, accumulate);
-        mma_tf32(d, al, bh, idesc, 1);
-        mma_tf32(d, ah, bl, idesc, 1);
+        const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+        const uint32_t bo = (uint32_t)(k * kChunks + 2 * kb) * bplane16;
+        mma_tf32_split(d, ah + ao, bh + bo, desc_hi, idesc, accumulate);
+        mma_tf32_split(d, al + ao, bh + bo, desc_hi, idesc, 1);
+        mma_tf32_split(d, ah + ao, bl + bo, desc_hi, idesc, 1);
         accumulate = 1;
       }
     }
@@ -237,12 +258,13 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Work W) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
+  unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = P.N, R = P.tc_teams, tiles = N / 128;
   const int team_warps = N / 32;
-  const bool is_mma_warp = warp == R * team_warps;
+  const bool is_mma_warp = warp >= R * team_warps;       // one issuer warp per team, after the team warps
+  const bool is_alloc_warp = warp == R * team_warps;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot);
   float* blob = reinterpret_cast<float*>(smem_raw + P.off_blob);
@@ -267,7 +289,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
     mbar_expect_tx(&bars[0], bytes);
     bulk_copy_g2s(blob, P.blob, bytes, &bars[0]);
   }
-  if (is_mma_warp) tmem_alloc(tmem_slot, 128);
+  if (is_alloc_warp) tmem_alloc(tmem_slot, 128);
   mbar_wait_guarded(&bars[0], 0);
   fence_before();
   __syncthreads();
@@ -279,60 +301,37 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
   const int rhs_per_row = (W.op == OP_INTEGRATE) ? W.nsteps * stages_of : 1;
 
   if (is_mma_warp) {
-    // ---------------- MMA issuer: serve whichever team has posted a request ----------------
-    uint32_t remaining[4], parity[4], layer_idx[4];
-    uint32_t total = 0;
-    for (int t = 0; t < 4; ++t) {
-      remaining[t] = 0; parity[t] = 0; layer_idx[t] = 0;
-      if (t < R) {
-        const int g = blockIdx.x * R + t;
-        const int rows = g < W.batch ? (W.batch - g + total_teams - 1) / total_teams : 0;
-        remaining[t] = (uint32_t)rows * (uint32_t)rhs_per_row * (uint32_t)requests_per_rhs;
-        total += remaining[t];
-      }
-    }
+    // ---------------- MMA issuer of team t: wait for a request, issue the layer, commit ----------------
+    const int t = warp - R * team_warps;
+    const int g = blockIdx.x * R + t;
+    const int rows = g < W.batch ? (W.batch - g + total_teams - 1) / total_teams : 0;
+    const uint32_t requests = (uint32_t)rows * (uint32_t)rhs_per_row * (uint32_t)requests_per_rhs;
     const uint32_t idesc_h = instr_desc_tf32(128, 32);
     const uint32_t idesc_l = instr_desc_tf32(128, NL);
     const uint32_t blob_s = smem_u32(blob);
-    uint32_t spins = 0;
-    long long spin_start = 0;
-    while (total > 0) {
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (t >= R || remaining[t] == 0) continue;
-        if (!mbar_test(&bars[1 + t], parity[t])) {
-          if ((++spins & 1023u) == 0) {
-            const long long now = clock64();
-            if (spin_start == 0) spin_start = now;
-            else if (now - spin_start > kSpinCycles) asm volatile("trap;");
-          }
-          continue;
+    unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)t * P.tc_team_stride;
+    const uint32_t act_hi = smem_u32(tb + P.tc_t_act_hi), act_lo = smem_u32(tb + P.tc_t_act_lo);
+    const uint32_t col0 = tmem_base + (uint32_t)(t * tiles) * 32u;
+    uint32_t parity = 0;
+    int layer_idx = 0;
+    for (uint32_t r = 0; r < requests; ++r) {
+      mbar_wait_guarded(&bars[1 + t], parity);
+      parity ^= 1u;
+      fence_after();
+      if (lane == 0) {
+        if (layer_idx != hidden_tc_layers) {
+          const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
+          issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_bhid_lo * 4u,
+                      32 * 16, tiles, col0, idesc_h);
+        } else {
+          const uint32_t off = (uint32_t)P.tc_blast_off * 4u;
+          issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_blast_lo * 4u,
+                      (uint32_t)NL * 16u, tiles, col0, idesc_l);
         }
-        spins = 0;
-        spin_start = 0;
-        fence_after();
-        if (lane == 0) {
-          unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)t * P.tc_team_stride;
-          const uint32_t act_hi = smem_u32(tb + P.tc_t_act_hi), act_lo = smem_u32(tb + P.tc_t_act_lo);
-          const uint32_t col0 = tmem_base + (uint32_t)(t * tiles) * 32u;
-          const bool last = (int)layer_idx[t] == hidden_tc_layers;
-          if (!last) {
-            const uint32_t off = (uint32_t)(P.tc_bhid_off + (int)layer_idx[t] * P.tc_bhid_stride) * 4u;
-            issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_bhid_lo * 4u,
-                        32 * 16, tiles, col0, idesc_h);
-          } else {
-            const uint32_t off = (uint32_t)P.tc_blast_off * 4u;
-            issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_blast_lo * 4u,
-                        (uint32_t)NL * 16u, tiles, col0, idesc_l);
-          }
-          mma_commit(&bars[1 + R + t]);
-        }
-        __syncwarp();
-        parity[t] ^= 1u;
-        layer_idx[t] = (layer_idx[t] + 1 == (uint32_t)requests_per_rhs) ? 0u : layer_idx[t] + 1;
-        remaining[t] -= 1;
-        total -= 1;
+        mma_commit(&bars[1 + R + t]);
       }
+      __syncwarp();
+      layer_idx = (layer_idx + 1 == requests_per_rhs) ? 0 : layer_idx + 1;
     }
   } else {
     // ---------------- row team ----------------
@@ -348,7 +347,6 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
     uint64_t* req = &bars[1 + team];
     uint64_t* done = &bars[1 + R + team];
     uint32_t done_parity = 0;
-    uint32_t fsel = 0;                                   // forcing amplitudes are double buffered per stage
     const int tile = x >> 7;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 32);
     const Tableau& tab = *tab_s;
@@ -361,6 +359,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
     const int g = blockIdx.x * R + team;
     for (int row = g; row < W.batch; row += total_teams) {
       const int sample = W.sample_offset + row;
+      const ForcingTerm fterm = load_forcing_term(P, sample, x);
       double y = W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
       int first_bad = -1, save_idx = 0;
       const int nsteps = (W.op == OP_INTEGRATE) ? W.nsteps : 1;
@@ -379,22 +378,9 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
           if (x >= N - kHalo) ust[x + kHalo - N] = us;
           const float tstage = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[s] * W.dt : W.t0);
           const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
-          fsel ^= 1u;
-          float* fs_cur = fs + fsel * (2 * kMaxModes);
-          if (forced && x < 2 * P.M) {
-            const float* fp = P.fparams + (size_t)sample * 4 * P.P;
-            const int m = (x < P.M ? x : x - P.M) + 1;
-            float a = 0.f;
-            for (int q = 0; q < P.P; ++q) {
-              const float kk = fp[3 * P.P + q];
-              if (fabsf(kk) != (float)m) continue;
-              float sn, cs;
-              sincosf(fmaf(fp[P.P + q], tstage, fp[2 * P.P + q]), &sn, &cs);
-              a += (x < P.M) ? fp[q] * sn : (kk < 0.f ? -fp[q] : fp[q]) * cs;
-            }
-            fs_cur[x] = a;
-          }
+          if (forced) forcing_terms(P, fs, fterm, x, tstage);
           team_sync(team, N);
+          if (forced) forcing_reduce(P, fs, x);          // visible to the team after the mbarrier rounds below
           float u7[kWin];
 #pragma unroll
           for (int j = 0; j < kWin; ++j) u7[j] = ust[x + j];
@@ -460,8 +446,8 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
           if (forced) {
             float f = 0.f;
             for (int m = 0; m < P.M; ++m) {
-              f = fmaf(fs_cur[m], __ldg(P.fbasis + (size_t)m * N + x), f);
-              f = fmaf(fs_cur[P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
+              f = fmaf(fs[m], __ldg(P.fbasis + (size_t)m * N + x), f);
+              f = fmaf(fs[P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
             }
             r = __fadd_rn(r, f);
           }
@@ -485,7 +471,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
         }
       }
       if (W.op == OP_INTEGRATE && W.first_bad) {
-        unsigned int* slot = reinterpret_cast<unsigned int*>(fs + 4 * kMaxModes);
+        unsigned int* slot = reinterpret_cast<unsigned int*>(fs + 2 * kMaxModes + 3 * kMaxForcing);
         if (x == 0) *slot = 0xffffffffu;
         team_sync(team, N);
         atomicMin(slot, first_bad < 0 ? 0xffffffffu : (unsigned int)first_bad);
@@ -498,7 +484,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const Params P, const Wo
   fence_before();
   __syncthreads();
   fence_after();
-  if (is_mma_warp) tmem_dealloc(tmem_base, 128);
+  if (is_alloc_warp) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -511,7 +497,7 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
                                                           const float* __restrict__ w_hi,
                                                           const float* __restrict__ w_lo, float* __restrict__ out,
                                                           int nout) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t plane_bytes = 132u * 16u;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);

@@ -359,6 +359,24 @@ class BatchIntegrator(object):
     return self.solver.integrate(u0, t0, dt, num_steps, save_every, scheme, sample_offset,
                                  return_first_bad)
 
+  def odeint(self, u0=None, times=_DEFAULT_TIMES, method='RK23', rtol=1e-3, atol=1e-6, max_step=0.01):
+    """Batched twin of odeint(): every sample runs SciPy's adaptive RK23 (same controller,
+    FSAL, dense output, NaN padding) inside one kernel launch.
+    Returns (y float64 [sample, time, x], nfev [sample])."""
+    if method != 'RK23':
+      raise NotImplementedError('only RK23 (the reference default, integrate.py:146) runs on the device')
+    u0 = np.stack([e.initial_value() for e in self.equations]) if u0 is None else u0
+    y, nfev, _ = self.solver.odeint(u0, times, rtol, atol, max_step)
+    return y.permute(1, 0, 2).cpu().numpy(), nfev.cpu().numpy()
+
+  def integrate_adaptive(self, u0=None, times=_DEFAULT_TIMES, **kwargs):
+    """{y: (sample, time, x)} + num_evals per sample, the batched form of integrate()."""
+    y, nfev = self.odeint(u0, times, **kwargs)
+    return make_dataset(
+        {'y': (('sample', 'time', 'x'), y), 'num_evals': (('sample',), nfev)},
+        {'time': np.asarray(times), 'x': self.equation.grid.solution_x,
+         'sample': np.array([e.random_seed for e in self.equations][:y.shape[0]])})
+
   def integrate_times(self, u0=None, times=_DEFAULT_TIMES, dt=None, scheme='rk3'):
     """Fixed-step twin of integrate(): samples at `times` (uniformly spaced, spacing a
     multiple of dt).  Rows that diverged are NaN from the first bad sample on, like

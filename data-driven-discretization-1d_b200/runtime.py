@@ -260,6 +260,25 @@ class RowSolver(object):
         rows.data_ptr(), snaps.data_ptr(), bad.data_ptr(), rows.shape[0], sample_offset, self._stream()))
     return (snaps, bad) if return_first_bad else snaps
 
+  def odeint(self, u0, times, rtol=1e-3, atol=1e-6, max_step=0.01, sample_offset=0):
+    """SciPy-RK23 twin on the device for every row (ddd1d_integrate_adaptive).
+    Returns (y float64 [len(times), batch, N] with NaN padding, nfev int32 [batch],
+    status int32 [batch])."""
+    torch = _torch()
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    src = torch.as_tensor(u0)
+    f64 = src.dtype == torch.float64
+    rows = self._rows(src, torch.float64 if f64 else torch.float32)
+    self._offset_ok(rows.shape[0], sample_offset)
+    y = torch.empty((len(times),) + tuple(rows.shape), device=self.device, dtype=torch.float64)
+    nfev = torch.zeros(rows.shape[0], device=self.device, dtype=torch.int32)
+    status = torch.zeros(rows.shape[0], device=self.device, dtype=torch.int32)
+    self._check(self._lib.ddd1d_integrate_adaptive(
+        self._handle, _lib.host_ptr(times), len(times), float(rtol), float(atol), float(max_step),
+        None if f64 else rows.data_ptr(), rows.data_ptr() if f64 else None, y.data_ptr(),
+        nfev.data_ptr(), status.data_ptr(), rows.shape[0], sample_offset, self._stream()))
+    return y, nfev, status
+
   def integrate_host(self, u0, t0, dt, num_steps, save_every=1, scheme='rk3', sample_offset=0):
     """Host buffers in and out through ddd1d_integrate_host (copies inside the library)."""
     u0 = np.ascontiguousarray(u0, dtype=np.float32).reshape(-1, self.num_points)

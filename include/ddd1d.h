@@ -178,6 +178,22 @@ int ddd1d_integrate(ddd1d_handle* handle, double t0, double dt, int num_steps, i
                     int scheme, const float* u0, float* snapshots, int* first_bad_step,
                     int batch, int sample_offset, void* stream);
 
+/* Adaptive twin of integrate.odeint for a whole batch: every row runs SciPy's RK23
+ * (Bogacki-Shampine 3(2) with the scipy.integrate.solve_ivp step-size controller,
+ * FSAL, cubic dense output at `times`) on the device, rows independent
+ * (integrate.py:143-169 -> scipy/integrate/_ivp/rk.py).
+ *   times    HOST float64 [num_times], strictly increasing; times[0] is the start
+ *   u0 / u0_f64  device float32 or float64 [batch][N] (exactly one non-NULL)
+ *   y_out    device float64 [num_times][batch][N]; samples the solver did not reach
+ *            are NaN (the reference's NaN padding, integrate.py:161-167)
+ *   nfev     device int32 [batch] or NULL: right-hand-side evaluations, as sol.nfev
+ *   status   device int32 [batch] or NULL: 0 = reached times[-1], -1 = step size underflow
+ * The conv stack runs on the FFMA engine for this entry point. */
+int ddd1d_integrate_adaptive(ddd1d_handle* handle, const double* times, int num_times, double rtol,
+                             double atol, double max_step, const float* u0, const double* u0_f64,
+                             double* y_out, int* nfev, int* status, int batch, int sample_offset,
+                             void* stream);
+
 /* Host-buffer forms (copies inside): what a caller without device memory uses. */
 int ddd1d_rhs_host(ddd1d_handle* handle, double t, const double* u, double* dudt, int batch,
                    int sample_offset);

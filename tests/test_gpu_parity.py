@@ -202,6 +202,59 @@ def test_fixed_step_c1_twin_matches_scipy_fixture(golden):
   np.testing.assert_allclose(y[1], g['c1_seed2/y'], rtol=0, atol=5e-4)
 
 
+def test_device_adaptive_rk23_matches_scipy_fixtures(golden):
+  """ddd1d_integrate_adaptive: SciPy's RK23 controller, FSAL and dense output re-implemented
+  per row on the device.  Against trajectories the reference's own odeint produced (with
+  the reference's graph code on the NumPy shim): same number of RHS evaluations, same
+  samples.  c1_seed1 (nfev 1031) is a run where the controller is NOT pinned at max_step."""
+  from ddd1d_b200 import integrate, equations
+  g = golden('trajectories')
+  eqs = [equations.BurgersEquation(64, random_seed=s) for s in (0, 1, 2)]
+  y, nfev = integrate.BatchIntegrator.baseline(eqs, 1).odeint(times=g['c1/times'])
+  assert y.shape == (3, 5, 64) and y.dtype == np.float64
+  for i, tag in enumerate(('c1', 'c1_seed1', 'c1_seed2')):
+    assert nfev[i] == int(g[tag + '/nfev']), (tag, nfev[i])
+    np.testing.assert_allclose(y[i], g[tag + '/y'], rtol=0, atol=5e-5)
+  eq = equations.ConservativeBurgersEquation(32, resample_factor=4, random_seed=3)
+  y, nfev = integrate.BatchIntegrator.baseline([eq], 1).odeint(times=g['cons_burgers/times'])
+  assert nfev[0] == int(g['cons_burgers/nfev'])
+  np.testing.assert_allclose(y[0], g['cons_burgers/y'], rtol=0, atol=5e-5)
+  eq = equations.BurgersEquation(32, random_seed=4)
+  solver = integrate.BatchIntegrator.learned([eq], G.product_hparams('burgers', 'plain', 32),
+                                             weights_from(g, 'learned_burgers'))
+  y, nfev = solver.odeint(times=g['learned_burgers/times'])
+  assert nfev[0] == int(g['learned_burgers/nfev'])
+  np.testing.assert_allclose(y[0], g['learned_burgers/y'], rtol=0, atol=5e-5)
+  eq = equations.KdVEquation(32, random_seed=2)
+  solver = integrate.BatchIntegrator.learned([eq], G.product_hparams('kdv', 'plain', 32),
+                                             weights_from(g, 'learned_kdv'))
+  y, nfev = solver.odeint(times=g['learned_kdv/times'])
+  assert nfev[0] == int(g['learned_kdv/nfev'])
+  np.testing.assert_allclose(y[0], g['learned_kdv/y'], rtol=0, atol=1e-4)
+  eq = equations.GodunovBurgersEquation(64, random_seed=1)
+  y, nfev = integrate.BatchIntegrator.weno([eq]).odeint(times=g['weno_burgers/times'])
+  assert nfev[0] == int(g['weno_burgers/nfev'])
+  np.testing.assert_allclose(y[0], g['weno_burgers/y'], rtol=0, atol=5e-5)   # float32 WENO vs float64 reference
+
+
+def test_device_adaptive_nan_padding_and_status():
+  """A run whose step size underflows stops early: later samples are NaN, status -1
+  (integrate.py:161-167), other rows of the batch are unaffected."""
+  from ddd1d_b200 import integrate, equations
+  eqs = [equations.KdVEquation(64, random_seed=s) for s in range(2)]
+  solver = integrate.BatchIntegrator.baseline(eqs, 1)
+  u0 = solver.initial_values().astype(np.float64)
+  u0[1, 10] = np.inf                      # poisons row 1 only
+  times = np.linspace(0, 0.02, 5)
+  y, nfev, status = solver.solver.odeint(u0, times)
+  y, status = cpu(y), cpu(status)
+  assert status[0] == 0 and np.isfinite(y[:, 0]).all()
+  assert status[1] == -1 and np.isnan(y[1:, 1]).all()
+  want, nf = O.odeint(u0[0], O.PolynomialDifferentiator(G.oracle_equation('kdv', 'plain', 64, seed=0), 1), times)
+  assert int(cpu(nfev)[0]) == nf
+  np.testing.assert_allclose(y[:, 0], want, rtol=0, atol=5e-5)
+
+
 # ---------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties + oracle on a row subset
 # ---------------------------------------------------------------------------------
