@@ -182,30 +182,29 @@ int finalize_tc(ddd1d_handle* h) {
   const int nhid = L - 2;
   P.tc_bh_off = reserve((size_t)std::max(nhid, 1) * F);
   P.tc_bl_off = reserve(32);
-  P.tc_bhid_stride = 2 * K * tc::kChunks * F * 4;
-  P.tc_bhid_lo = K * tc::kChunks * F * 4;
+  P.tc_bhid_stride = 2 * K * tc::kChunks * F * 4;   // planes [tap*8+chunk][2F rows: Whi then Wlo][4]
+  P.tc_bhid_lo = 0;
   P.tc_bhid_off = reserve((size_t)std::max(nhid, 0) * P.tc_bhid_stride);
   for (int l = 0; l < nhid; ++l) {
     const HostLayer& hl = h->layers[1 + l];
     for (int co = 0; co < F; ++co) blob[P.tc_bh_off + l * F + co] = hl.bias[co];
-    float* hi = blob.data() + P.tc_bhid_off + (size_t)l * P.tc_bhid_stride;
-    float* lo = hi + P.tc_bhid_lo;
+    float* cat = blob.data() + P.tc_bhid_off + (size_t)l * P.tc_bhid_stride;
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
         for (int co = 0; co < F; ++co) {
           const float w = hl.kernel[((size_t)k * F + ci) * F + co];
-          const size_t idx = ((size_t)(k * tc::kChunks + ci / 4) * F + co) * 4 + (ci % 4);
-          hi[idx] = tf32_hi(w);
-          lo[idx] = tf32_hi(w - hi[idx]);
+          const size_t plane = (size_t)(k * tc::kChunks + ci / 4) * (2 * F) * 4;
+          const float whi = tf32_hi(w);
+          cat[plane + (size_t)co * 4 + (ci % 4)] = whi;
+          cat[plane + (size_t)(F + co) * 4 + (ci % 4)] = tf32_hi(w - whi);
         }
   }
   // last layer with the projection folded in: W'[k][ci][q] = sum_c W[k][ci][c] pm[c][q]
   const HostLayer& ll = h->layers[L - 1];
-  P.tc_blast_lo = K * tc::kChunks * NL * 4;
-  P.tc_blast_off = reserve((size_t)2 * P.tc_blast_lo);
+  P.tc_blast_lo = 0;
+  P.tc_blast_off = reserve((size_t)2 * K * tc::kChunks * NL * 4);
   {
-    float* hi = blob.data() + P.tc_blast_off;
-    float* lo = hi + P.tc_blast_lo;
+    float* cat = blob.data() + P.tc_blast_off;
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
         for (int q = 0; q < Q; ++q) {
@@ -213,9 +212,10 @@ int finalize_tc(ddd1d_handle* h) {
           for (int ch = 0; ch < c.net_outputs; ++ch)
             acc += (double)ll.kernel[((size_t)k * F + ci) * c.net_outputs + ch] * pm[(size_t)ch * Q + q];
           const float w = (float)acc;
-          const size_t idx = ((size_t)(k * tc::kChunks + ci / 4) * NL + q) * 4 + (ci % 4);
-          hi[idx] = tf32_hi(w);
-          lo[idx] = tf32_hi(w - hi[idx]);
+          const size_t plane = (size_t)(k * tc::kChunks + ci / 4) * (2 * NL) * 4;
+          const float whi = tf32_hi(w);
+          cat[plane + (size_t)q * 4 + (ci % 4)] = whi;
+          cat[plane + (size_t)(NL + q) * 4 + (ci % 4)] = tf32_hi(w - whi);
         }
     for (int q = 0; q < Q; ++q) {
       double acc = pbias[q];
@@ -226,8 +226,8 @@ int finalize_tc(ddd1d_handle* h) {
   blob.resize(align_up((int)blob.size(), 32), 0.f);
   P.blob_floats = (int)blob.size();
   P.tc_nlast = NL;
-  P.tc_teams = 512 / N;
-  // shared-memory plan
+  P.tc_debug = getenv("DDD1D_TC_DEBUG") ? atoi(getenv("DDD1D_TC_DEBUG")) : 0;
+  // shared-memory plan: as many row teams as fit (at most 512 / N)
   const int plane = (N + 4) * 16;
   int t = 0;
   P.tc_t_act_hi = t; t += tc::kChunks * plane;
@@ -242,6 +242,8 @@ int finalize_tc(ddd1d_handle* h) {
   P.tc_off_tab = 128;                       // Tableau (200 B)
   P.off_blob = 384;
   P.tc_off_team0 = align_up(P.off_blob + P.blob_floats * 4, 128);
+  P.tc_teams = 512 / N;
+  while (P.tc_teams > 1 && P.tc_off_team0 + P.tc_teams * P.tc_team_stride > 227 * 1024) P.tc_teams -= 1;
   P.smem_bytes = P.tc_off_team0 + P.tc_teams * P.tc_team_stride;
   if (P.smem_bytes > 227 * 1024) {
     h->tc_why = "shared memory plan does not fit";
@@ -255,7 +257,7 @@ int finalize_tc(ddd1d_handle* h) {
   CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   P.blob = h->d_blob_tc;
   CUDA_TRY(h, cudaFuncSetAttribute(tc::tc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  h->tc_threads = P.tc_teams * (N + 32);     // N threads + one MMA-issuer warp per team
+  h->tc_threads = P.tc_teams * (N + 32 * (N / 128));   // team threads + one MMA-issuer warp per 128-point tile
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_row_kernel, h->tc_threads, P.smem_bytes));
   if (occ < 1) {
@@ -825,13 +827,12 @@ int ddd1d_engine(const ddd1d_handle* handle) {
   return use_tc(h) ? DDD1D_ENGINE_TENSOR : DDD1D_ENGINE_FFMA;
 }
 
-int ddd1d_debug_tc_probe(int device, const float* x, const float* w_hi, const float* w_lo, float* out, int nout,
-                         void* stream) {
-  if (!x || !w_hi || !w_lo || !out || (nout != 16 && nout != 32)) return fail(nullptr, DDD1D_EINVAL, "bad argument");
+int ddd1d_debug_tc_probe(int device, const float* x, const float* w_cat, float* out, int nout, void* stream) {
+  if (!x || !w_cat || !out || (nout != 16 && nout != 32)) return fail(nullptr, DDD1D_EINVAL, "bad argument");
   CUDA_TRY(nullptr, cudaSetDevice(device));
   const int smem = 128 + 2 * tc::kChunks * 132 * 16 + 2 * tc::kTaps * tc::kChunks * nout * 16;
   CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc::tc_probe_kernel<<<1, 160, smem, static_cast<cudaStream_t>(stream)>>>(x, w_hi, w_lo, out, nout);
+  tc::tc_probe_kernel<<<1, 160, smem, static_cast<cudaStream_t>(stream)>>>(x, w_cat, out, nout);
   CUDA_TRY(nullptr, cudaGetLastError());
   return DDD1D_OK;
 }

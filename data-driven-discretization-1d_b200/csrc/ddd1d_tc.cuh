@@ -6,16 +6,22 @@
 // A = activations kept in shared memory as K-major "chunk planes" [ci/4][position][4 floats]
 // (no swizzle), so the tap shift k is just +16 B on the descriptor start address and the periodic
 // halo is two extra positions per plane.  B = filters pre-packed on the host in the same canonical
-// layout.  FP32 fidelity on a TF32 pipe comes from the 3xTF32 split: x = hi + lo with hi = the top
-// 19 bits, and hi*Whi + lo*Whi + hi*Wlo accumulated in FP32 in TMEM (the dropped lo*Wlo term is
-// 2^-22 relative).  The polynomial-accuracy projection is folded into the last layer's filters on
+// layout.  FP32 fidelity on a TF32 pipe comes from the 3xTF32 split: x = hi + lo (both rounded to
+// TF32) and hi*Whi + lo*Whi + hi*Wlo accumulated in FP32 in TMEM (the dropped lo*Wlo term is 2^-22
+// relative).  B holds [Whi | Wlo] side by side, so one MMA of width 2*NB produces hi*Whi (the "main"
+// columns) and hi*Wlo (the "cross" columns) and a second one of width NB adds lo*Whi to the cross
+// columns: two instructions per (tap, ci-block) instead of three.  The tensor core truncates when it
+// adds into an accumulator (measured: error grows linearly with the number of accumulate steps, see
+// profiles/r01/tc_precision.txt), so the large main terms get their own columns, split once more
+// into even and odd taps (12 + 8 steps), and the epilogue adds the four partial sums in FP32.  The polynomial-accuracy projection is folded into the last layer's filters on
 // the host (W3' = W3 . nullspace, window form), so the last epilogue reads stencil coefficients
 // straight out of TMEM.
 //
 // Warp roles (one CTA per SM, persistent): R "row teams" of N threads (thread <-> grid point; the
 // team's warps are 4-aligned so each warp reads its own TMEM lane quadrant) run the whole
-// Runge-Kutta program of their row; one extra warp issues every tcgen05.mma for all teams and
-// signals completion with tcgen05.commit -> mbarrier.  While one team runs an epilogue on the CUDA
+// Runge-Kutta program of their row; four extra warps (one per 128-position tile, one per SM
+// sub-partition) issue the tcgen05.mma of their tile and signal completion with
+// tcgen05.commit -> mbarrier.  While one team runs an epilogue on the CUDA
 // cores, the tensor pipe works on another team's tile.
 #pragma once
 #include "ddd1d_device.cuh"
@@ -163,9 +169,18 @@ struct TcView {
   unsigned char* team_base;
 };
 
-// Issue all MMAs of one layer for one team (one thread).  Descriptors are kept as (lo, hi) 32-bit
-// halves: hi (stride offset | version) never changes, lo = start>>4 | lbo>>4 << 16 advances by plain
-// 32-bit adds, so one (tap, ci-block) step costs four adds and three tcgen05.mma.
+// One elected lane of a converged warp (CUTLASS's elect_one_sync): keeps the surrounding values in
+// uniform registers, so tcgen05.mma takes its descriptors without per-instruction R2UR shuffles.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mma_tf32_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                                uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -178,32 +193,36 @@ __device__ __forceinline__ void mma_tf32_split(uint32_t tmem_d, uint32_t a_lo, u
       : "memory");
 }
 
-__device__ __noinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes,
-                                         uint32_t b_hi, uint32_t b_lo, uint32_t b_plane_bytes, int tiles,
-                                         uint32_t tmem_col0, uint32_t idesc) {
+// Issue every MMA of one layer for one 128-position tile.  Must be called by a converged warp with
+// warp-uniform arguments; one elected lane issues.
+//   act_hi/act_lo : shared addresses of the tile's team planes (position 0 of the row)
+//   b             : shared address of the layer's [Whi | Wlo] planes, b_plane_bytes = 2*NB*16
+//   d_col         : TMEM column of the tile's accumulator block; layout
+//                   [even taps: main NB | cross NB][odd taps: main NB | cross NB]
+__device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes, uint32_t b,
+                                            uint32_t b_plane_bytes, int tile, uint32_t d_col, int nb) {
   const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1 (bits 32..47)
   const uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
-  const uint32_t a_field = plane16 << 16, b_field = bplane16 << 16;   // LBO fields
-  const uint32_t ah0 = ((act_hi >> 4) & 0x3FFFu) | a_field, al0 = ((act_lo >> 4) & 0x3FFFu) | a_field;
-  const uint32_t bh0 = ((b_hi >> 4) & 0x3FFFu) | b_field, bl0 = ((b_lo >> 4) & 0x3FFFu) | b_field;
-  for (int m = 0; m < tiles; ++m) {
-    const uint32_t d = tmem_col0 + (uint32_t)m * 32u;
-    uint32_t accumulate = 0;
-    uint32_t ah = ah0 + (uint32_t)m * 128u, al = al0 + (uint32_t)m * 128u;   // 128 rows * 16 B >> 4
-    uint32_t bh = bh0, bl = bl0;
+  const uint32_t ah0 = (((act_hi >> 4) + (uint32_t)tile * 128u) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t al0 = (((act_lo >> 4) + (uint32_t)tile * 128u) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t b0 = ((b >> 4) & 0x3FFFu) | (bplane16 << 16);
+  const uint32_t idesc_wide = instr_desc_tf32(128, 2 * nb), idesc_narrow = instr_desc_tf32(128, nb);
+  if (elect_one()) {
 #pragma unroll
     for (int k = 0; k < kTaps; ++k) {
+      const uint32_t d_main = d_col + (uint32_t)((k & 1) * 2 * nb);
+      const uint32_t d_cross = d_main + (uint32_t)nb;
 #pragma unroll
       for (int kb = 0; kb < kChunks / 2; ++kb) {
         const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
         const uint32_t bo = (uint32_t)(k * kChunks + 2 * kb) * bplane16;
-        mma_tf32_split(d, ah + ao, bh + bo, desc_hi, idesc, accumulate);
-        mma_tf32_split(d, al + ao, bh + bo, desc_hi, idesc, 1);
-        mma_tf32_split(d, ah + ao, bl + bo, desc_hi, idesc, 1);
-        accumulate = 1;
+        const uint32_t first = (k < 2 && kb == 0) ? 0u : 1u;     // first touch of the even / odd block
+        mma_tf32_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);   // hi*[Whi|Wlo] -> main | cross
+        mma_tf32_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);   // lo*Whi       -> cross
       }
     }
   }
+  __syncwarp();
 }
 
 // store 4 consecutive channels of one position into a plane (+ its wrapped halo copy)
@@ -225,6 +244,36 @@ __device__ __forceinline__ void store_split(unsigned char* hi_plane, unsigned ch
 }
 
 
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// sixteen outputs = (even main + odd main) + (even cross + odd cross); four loads in flight, one wait
+__device__ __forceinline__ void tmem_sum4x16(uint32_t t_em, uint32_t t_om, uint32_t t_ec, uint32_t t_oc, float* v) {
+  uint32_t a[16], b[16], c[16], d[16];
+  tmem_ld16_issue(t_em, a);
+  tmem_ld16_issue(t_om, b);
+  tmem_ld16_issue(t_ec, c);
+  tmem_ld16_issue(t_oc, d);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    v[i] = (__uint_as_float(a[i]) + __uint_as_float(b[i])) + (__uint_as_float(c[i]) + __uint_as_float(d[i]));
+}
+// NB = 32: block layout [even main 32 | even cross 32 | odd main 32 | odd cross 32]
+__device__ __forceinline__ void tmem_sum32(uint32_t taddr, float (&v)[32]) {
+  tmem_sum4x16(taddr, taddr + 64, taddr + 32, taddr + 96, v);
+  tmem_sum4x16(taddr + 16, taddr + 80, taddr + 48, taddr + 112, v + 16);
+}
+// NB = 16: block layout [even main 16 | even cross 16 | odd main 16 | odd cross 16]
+__device__ __forceinline__ void tmem_sum16(uint32_t taddr, float (&v)[16]) {
+  tmem_sum4x16(taddr, taddr + 32, taddr + 16, taddr + 48, v);
+}
+
 // Last-layer epilogue for one grid point: window coefficients = TMEM accumulators + folded bias,
 // then the stencil dot products (model.py:536-548).  NLV = TMEM columns of the last layer.
 template <int NLV>
@@ -232,8 +281,8 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
                                               const float* __restrict__ blast, const float (&u7)[kWin],
                                               int row, int x, float (&dv)[kMaxD]) {
   float cfv[NLV];
-  if (NLV == 16) tmem_ld16(taddr, reinterpret_cast<float(&)[16]>(cfv));
-  else tmem_ld32(taddr, reinterpret_cast<float(&)[32]>(cfv));
+  if (NLV == 16) tmem_sum16(taddr, reinterpret_cast<float(&)[16]>(cfv));
+  else tmem_sum32(taddr, reinterpret_cast<float(&)[32]>(cfv));
   fence_before();
   const int N = P.N;
 #pragma unroll
@@ -279,7 +328,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     mbar_init(&bars[0], 1);
     for (int t = 0; t < R; ++t) {
       mbar_init(&bars[1 + t], (uint32_t)N);
-      mbar_init(&bars[1 + R + t], 1);
+      mbar_init(&bars[1 + R + t], (uint32_t)tiles);   // one tcgen05.commit per tile issuer
     }
     mbar_fence_init();
   }
@@ -289,7 +338,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     mbar_expect_tx(&bars[0], bytes);
     bulk_copy_g2s(blob, P.blob, bytes, &bars[0]);
   }
-  if (is_alloc_warp) tmem_alloc(tmem_slot, 128);
+  if (is_alloc_warp) tmem_alloc(tmem_slot, 512);      // 4 tiles x 128 columns
   mbar_wait_guarded(&bars[0], 0);
   fence_before();
   __syncthreads();
@@ -301,35 +350,36 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
   const int rhs_per_row = (W.op == OP_INTEGRATE) ? W.nsteps * stages_of : 1;
 
   if (is_mma_warp) {
-    // ---------------- MMA issuer of team t: wait for a request, issue the layer, commit ----------------
-    const int t = warp - R * team_warps;
+    // ---------------- MMA issuer of (team t, tile m): wait for a request, issue the layer, commit ----------------
+    // everything below is warp-uniform (shuffled from lane 0) so the descriptors stay in uniform registers
+    const int mw = __shfl_sync(0xffffffffu, warp - R * team_warps, 0);
+    const int t = mw / tiles, tile_m = mw % tiles;
     const int g = blockIdx.x * R + t;
     const int rows = g < W.batch ? (W.batch - g + total_teams - 1) / total_teams : 0;
     const uint32_t requests = (uint32_t)rows * (uint32_t)rhs_per_row * (uint32_t)requests_per_rhs;
-    const uint32_t idesc_h = instr_desc_tf32(128, 32);
-    const uint32_t idesc_l = instr_desc_tf32(128, NL);
-    const uint32_t blob_s = smem_u32(blob);
-    unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)t * P.tc_team_stride;
-    const uint32_t act_hi = smem_u32(tb + P.tc_t_act_hi), act_lo = smem_u32(tb + P.tc_t_act_lo);
-    const uint32_t col0 = tmem_base + (uint32_t)(t * tiles) * 32u;
+    const uint32_t smem_s = smem_u32(dyn_smem);
+    const uint32_t blob_s = smem_s + (uint32_t)P.off_blob;
+    const uint32_t team_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)t * (uint32_t)P.tc_team_stride;
+    const uint32_t act_hi = team_s + (uint32_t)P.tc_t_act_hi, act_lo = team_s + (uint32_t)P.tc_t_act_lo;
+    const uint32_t d_col = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)((t * tiles + tile_m) * 128);
+    uint64_t* req_bar = &bars[1 + t];
+    uint64_t* done_bar = &bars[1 + R + t];
     uint32_t parity = 0;
     int layer_idx = 0;
     for (uint32_t r = 0; r < requests; ++r) {
-      mbar_wait_guarded(&bars[1 + t], parity);
+      mbar_wait_guarded(req_bar, parity);
       parity ^= 1u;
       fence_after();
-      if (lane == 0) {
-        if (layer_idx != hidden_tc_layers) {
-          const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
-          issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_bhid_lo * 4u,
-                      32 * 16, tiles, col0, idesc_h);
-        } else {
-          const uint32_t off = (uint32_t)P.tc_blast_off * 4u;
-          issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, blob_s + off + (uint32_t)P.tc_blast_lo * 4u,
-                      (uint32_t)NL * 16u, tiles, col0, idesc_l);
-        }
-        mma_commit(&bars[1 + R + t]);
+      if (P.tc_debug & 1) {
+        // timing experiment: no MMAs, the commit below completes immediately
+      } else if (layer_idx != hidden_tc_layers) {
+        const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
+        issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, 2u * 32u * 16u, tile_m, d_col, 32);
+      } else {
+        issue_layer(act_hi, act_lo, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u, 2u * (uint32_t)NL * 16u,
+                    tile_m, d_col, NL);
       }
+      if (elect_one()) mma_commit(done_bar);
       __syncwarp();
       layer_idx = (layer_idx + 1 == requests_per_rhs) ? 0 : layer_idx + 1;
     }
@@ -348,7 +398,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     uint64_t* done = &bars[1 + R + team];
     uint32_t done_parity = 0;
     const int tile = x >> 7;
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 32);
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 128);
     const Tableau& tab = *tab_s;
     const bool cons = eq_conservative(P.eq);
     const bool forced_eq = eq_forced(P.eq) && P.P > 0;
@@ -413,7 +463,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
             done_parity ^= 1u;
             fence_after();
             float acc[32];
-            tmem_ld32(taddr, acc);
+            tmem_sum32(taddr, acc);
             fence_before();
             const float* bias = blob + P.tc_bh_off + l * kF;
             const int act = P.layer[1 + l].act;
@@ -484,18 +534,18 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
   fence_before();
   __syncthreads();
   fence_after();
-  if (is_alloc_warp) tmem_dealloc(tmem_base, 128);
+  if (is_alloc_warp) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Probe: one 128-position tile of a 32 -> NOUT, 5-tap periodic-free conv through the same
 // descriptor / split / TMEM path.  Used by tests to validate layouts in isolation.
-//   x   [132][32] float  (positions -2..129)      w_hi/w_lo  packed B planes [5*8][NOUT][4]
-//   out [128][NOUT] float
+//   x     [132][32] float  (positions -2..129)
+//   w_cat packed B planes [5*8][2*NOUT][4]: rows 0..NOUT-1 = Whi, NOUT..2*NOUT-1 = Wlo
+//   out   [128][NOUT] float
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restrict__ xin,
-                                                          const float* __restrict__ w_hi,
-                                                          const float* __restrict__ w_lo, float* __restrict__ out,
+                                                          const float* __restrict__ w_cat, float* __restrict__ out,
                                                           int nout) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -504,13 +554,12 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
   unsigned char* a_hi = smem_raw + 128;
   unsigned char* a_lo = a_hi + kChunks * plane_bytes;
-  float* b_hi = reinterpret_cast<float*>(a_lo + kChunks * plane_bytes);
-  float* b_lo = b_hi + kTaps * kChunks * nout * 4;
+  float* b_cat = reinterpret_cast<float*>(a_lo + kChunks * plane_bytes);
   if (tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(slot, 32);
+  if (warp == 4) tmem_alloc(slot, 128);
   for (int i = tid; i < 132 * kChunks; i += blockDim.x) {
     const int pos = i / kChunks, c4 = i % kChunks;
     const float4 v = *reinterpret_cast<const float4*>(xin + (size_t)pos * kF + 4 * c4);
@@ -519,32 +568,30 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
     *reinterpret_cast<float4*>(a_hi + (size_t)c4 * plane_bytes + (size_t)pos * 16) = h;
     *reinterpret_cast<float4*>(a_lo + (size_t)c4 * plane_bytes + (size_t)pos * 16) = l;
   }
-  for (int i = tid; i < kTaps * kChunks * nout * 4; i += blockDim.x) {
-    b_hi[i] = w_hi[i];
-    b_lo[i] = w_lo[i];
-  }
+  for (int i = tid; i < kTaps * kChunks * 2 * nout * 4; i += blockDim.x) b_cat[i] = w_cat[i];
   fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *slot;
-  if (tid == 128) {
-    issue_layer(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_hi), smem_u32(b_lo), (uint32_t)nout * 16u,
-                1, tmem_base, instr_desc_tf32(128, nout));
-    mma_commit(bar);
-  }
-  if (warp < 4) {
+  if (warp == 4) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    issue_layer(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_cat), 2u * (uint32_t)nout * 16u, 0, base_u,
+                nout);
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+  } else {
     mbar_wait_guarded(bar, 0);
     fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     if (nout == 16) {
       float v[16];
-      tmem_ld16(taddr, v);
+      tmem_sum16(taddr, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) out[(size_t)tid * 16 + i] = v[i];
     } else {
       float v[32];
-      tmem_ld32(taddr, v);
+      tmem_sum32(taddr, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) out[(size_t)tid * 32 + i] = v[i];
     }
@@ -552,7 +599,7 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
   }
   __syncthreads();
   fence_after();
-  if (warp == 4) tmem_dealloc(tmem_base, 32);
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace tc

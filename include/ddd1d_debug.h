@@ -7,11 +7,10 @@ extern "C" {
 /* One 128-position tile of a 32 -> nout (16 | 32), 5-tap conv through the tcgen05 path
  * (same shared-memory descriptors, 3xTF32 split and TMEM read-back as the row kernel).
  *   x      device float [132][32]   inputs at positions -2..129
- *   w_hi   device float [5*8][nout][4]   filters packed as B planes, high TF32 part
- *   w_lo   device float [5*8][nout][4]   low part
+ *   w_cat  device float [5*8][2*nout][4]   filters packed as B planes: rows 0..nout-1 the TF32-rounded
+ *          weights, rows nout..2*nout-1 their TF32-rounded remainders
  *   out    device float [128][nout] */
-int ddd1d_debug_tc_probe(int device, const float* x, const float* w_hi, const float* w_lo, float* out,
-                         int nout, void* stream);
+int ddd1d_debug_tc_probe(int device, const float* x, const float* w_cat, float* out, int nout, void* stream);
 #ifdef __cplusplus
 }
 #endif

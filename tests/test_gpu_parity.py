@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import pde_oracle as O
-from tests.helpers import KINDS, VARIANTS, net_from_json, rel_err, weights_from
+from tests.helpers import KINDS, VARIANTS, assert_f32_faithful, net_from_json, rel_err, weights_from
 from tests import gpu_helpers as G
 
 pytestmark = pytest.mark.gpu
@@ -383,8 +383,11 @@ def test_odd_sizes_use_generic_path(n):
     w = O.glorot_weights(oeq, O.NetSpec(), seed=n, last_layer_scale=0.1, bias_scale=0.1)
     u = G.smooth_rows(3, n, seed=n)
     assert rel_err(cpu(model.predict_coefficients(u, hp, w)), O.predict_coefficients(u, oeq, O.NetSpec(), w)) < RHS_TOL
-    assert rel_err(cpu(model.predict_time_derivative(u, hp, w)),
-                   O.predict_time_derivative(u, oeq, O.NetSpec(), w)) < (RHS_TOL if variant == 'plain' else FLUX_TOL)
+    # 1/dx^n stencils amplify float32 rounding with N: bound by the float32 reference graph's own error
+    assert_f32_faithful(cpu(model.predict_time_derivative(u, hp, w)),
+                        O.predict_time_derivative(u, oeq, O.NetSpec(), w),
+                        O.predict_time_derivative(u, oeq, O.NetSpec(), w, dtype=np.float64),
+                        what='%s %s N=%d' % (kind, variant, n))
 
 
 def test_fast_and_generic_conv_paths_agree(monkeypatch):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import pde_oracle as O
-from tests.helpers import KINDS, VARIANTS, rel_err
+from tests.helpers import KINDS, VARIANTS, assert_f32_faithful, rel_err
 from tests import gpu_helpers as G
 
 pytestmark = pytest.mark.gpu
@@ -22,37 +22,44 @@ def cpu(t):
   return t.detach().cpu().numpy()
 
 
-def _split(w):
-  hi = (w.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
-  return hi, (w - hi).astype(np.float32)
+def _round_tf32(a):
+  return ((a.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
+
+
+def pack_b_planes(w):
+  """[5][32][nout] filters -> B planes [5*8][2*nout][4]: rows 0..nout-1 = TF32(w), the rest = TF32(w - TF32(w))."""
+  nout = w.shape[2]
+  packed = np.zeros((5 * 8, 2 * nout, 4), np.float32)
+  hi = _round_tf32(np.ascontiguousarray(w))
+  lo = _round_tf32((w - hi).astype(np.float32))
+  for k in range(5):
+    for ci in range(32):
+      packed[k * 8 + ci // 4, :nout, ci % 4] = hi[k, ci, :]
+      packed[k * 8 + ci // 4, nout:, ci % 4] = lo[k, ci, :]
+  return packed
 
 
 @pytest.mark.parametrize('nout', (32, 16))
 def test_descriptor_probe(nout):
   """One 128-position tile, 32 -> nout channels, 5 taps: validates the shared-memory
-  descriptors (tap shift by start address), the B packing, the 3xTF32 split and the
-  TMEM read-back in isolation."""
+  descriptors (tap shift by start address), the [Whi|Wlo] B packing, the 3xTF32 split, the
+  main/cross x even/odd accumulator layout and the TMEM read-back in isolation."""
   import torch
   from ddd1d_b200 import _lib
   lib = _lib.load()
   rs = np.random.RandomState(nout)
   x = rs.randn(132, 32).astype(np.float32)
   w = (rs.randn(5, 32, nout) / 8).astype(np.float32)
-  packed = np.zeros((5 * 8, nout, 4), np.float32)
-  for k in range(5):
-    for ci in range(32):
-      packed[k * 8 + ci // 4, :, ci % 4] = w[k, ci, :]
-  hi, lo = _split(packed)
-  dx, dhi, dlo = (torch.as_tensor(a).cuda().contiguous() for a in (x, hi, lo))
+  dx, dw = (torch.as_tensor(a).cuda().contiguous() for a in (x, pack_b_planes(w)))
   out = torch.zeros((128, nout), dtype=torch.float32, device='cuda')
-  _lib.check(lib.ddd1d_debug_tc_probe(0, dx.data_ptr(), dhi.data_ptr(), dlo.data_ptr(), out.data_ptr(), nout,
+  _lib.check(lib.ddd1d_debug_tc_probe(0, dx.data_ptr(), dw.data_ptr(), out.data_ptr(), nout,
                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
   torch.cuda.synchronize()
   want = np.zeros((128, nout))
   for k in range(5):
     want += x[k:k + 128].astype(np.float64) @ w[k].astype(np.float64)
   err = rel_err(cpu(out), want)
-  assert err < 2e-6, err
+  assert err < 1e-6, err
 
 
 def _solvers(kind, variant, n, seed=0):
@@ -70,21 +77,28 @@ def _solvers(kind, variant, n, seed=0):
 @pytest.mark.parametrize('kind', KINDS)
 @pytest.mark.parametrize('variant', VARIANTS)
 def test_tensor_engine_per_call_parity(kind, variant):
+  """Coefficients within RHS_TOL of the float32 oracle; derivatives and dy/dt (where 1/dx^n
+  stencils and flux differences amplify rounding) as accurate as the float32 reference graph
+  itself, measured against the float64 oracle; and the same bound for the FFMA engine."""
   n = 128
   tensor, ffma, oeq, w = _solvers(kind, variant, n)
   u = G.smooth_rows(5, n, seed=7)
   net = O.NetSpec()
-  want_c = O.predict_coefficients(u, oeq, net, w)
-  assert rel_err(cpu(tensor.coefficients(u)), want_c) < RHS_TOL
-  want_d = O.apply_coefficients(want_c, u)
-  assert rel_err(cpu(tensor.space_derivatives(u)), want_d) < RHS_TOL
-  tol = RHS_TOL if variant == 'plain' else FLUX_TOL
-  want_t = oeq.finalize_time_derivative(np.float32(0.4), O.predict_time_derivative(u[:1], oeq, net, w),
-                                        dtype=np.float32)
-  assert rel_err(cpu(tensor.rhs(0.4, u[:1])), want_t) < tol
-  assert rel_err(cpu(tensor.rhs(0.4, u[:1])), cpu(ffma.rhs(0.4, u[:1]))) < tol
+  c32 = O.predict_coefficients(u, oeq, net, w)
+  c64 = O.predict_coefficients(u, oeq, net, w, dtype=np.float64)
+  assert rel_err(cpu(tensor.coefficients(u)), c32) < RHS_TOL
+  assert_f32_faithful(cpu(tensor.coefficients(u)), c32, c64, what='coefficients')
+  d32, d64 = O.apply_coefficients(c32, u), O.apply_coefficients(c64, u.astype(np.float64))
+  assert_f32_faithful(cpu(tensor.space_derivatives(u)), d32, d64, what='space derivatives (tensor)')
+  assert_f32_faithful(cpu(ffma.space_derivatives(u)), d32, d64, what='space derivatives (ffma)')
+  t32 = oeq.finalize_time_derivative(np.float32(0.4), O.predict_time_derivative(u[:1], oeq, net, w),
+                                     dtype=np.float32)
+  t64 = oeq.finalize_time_derivative(0.4, O.predict_time_derivative(u[:1], oeq, net, w, dtype=np.float64))
+  assert_f32_faithful(cpu(tensor.rhs(0.4, u[:1])), t32, t64, what='dy/dt (tensor)')
+  assert_f32_faithful(cpu(ffma.rhs(0.4, u[:1])), t32, t64, what='dy/dt (ffma)')
+  assert rel_err(cpu(tensor.rhs(0.4, u[:1])), cpu(ffma.rhs(0.4, u[:1]))) < 3e-4      # sanity: same quantity
   # float64 rows (what SciPy hands over)
-  assert rel_err(cpu(tensor.rhs(0.4, u[:1].astype(np.float64))), want_t) < tol
+  assert_f32_faithful(cpu(tensor.rhs(0.4, u[:1].astype(np.float64))), t32, t64, what='dy/dt from float64 rows')
 
 
 @pytest.mark.parametrize('n,kind,dt', ((256, 'burgers', 1e-3), (128, 'kdv', 2.5e-5), (512, 'ks', 1e-5)))
@@ -126,7 +140,8 @@ def test_tensor_engine_other_nets_and_schemes():
     solver = runtime.learned_solver(eq, hp, w, engine='tensor', forcing=False)
     u = G.smooth_rows(3, n, seed=1)
     assert rel_err(cpu(solver.coefficients(u)), O.predict_coefficients(u, oeq, net, w)) < RHS_TOL, overrides
-    assert rel_err(cpu(solver.rhs(0.0, u)), O.predict_time_derivative(u, oeq, net, w)) < RHS_TOL, overrides
+    assert_f32_faithful(cpu(solver.rhs(0.0, u)), O.predict_time_derivative(u, oeq, net, w),
+                        O.predict_time_derivative(u, oeq, net, w, dtype=np.float64), what=str(overrides))
   snaps = solver.integrate(u, 0.0, 1e-3, 4, 2, 'midpoint')
   rhs = O.batched_rhs([oeq], net, w, mode='learned')
   # forcing disabled on the GPU side: compare with an unforced oracle RHS
