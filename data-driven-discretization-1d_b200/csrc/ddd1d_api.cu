@@ -21,7 +21,7 @@
 using namespace ddd1d;
 
 #ifndef DDD1D_AUTO_PREFERS_TENSOR
-#define DDD1D_AUTO_PREFERS_TENSOR 0
+#define DDD1D_AUTO_PREFERS_TENSOR 1
 #endif
 
 namespace {
@@ -227,12 +227,13 @@ int finalize_tc(ddd1d_handle* h) {
   P.blob_floats = (int)blob.size();
   P.tc_nlast = NL;
   P.tc_debug = getenv("DDD1D_TC_DEBUG") ? atoi(getenv("DDD1D_TC_DEBUG")) : 0;
+  P.tc_stagger_ns = getenv("DDD1D_TC_STAGGER_NS") ? atoi(getenv("DDD1D_TC_STAGGER_NS")) : 3000;
   // shared-memory plan: as many row teams as fit (at most 512 / N)
   const int plane = (N + 4) * 16;
   int t = 0;
   P.tc_t_act_hi = t; t += tc::kChunks * plane;
   P.tc_t_act_lo = t; t += tc::kChunks * plane;
-  P.tc_t_ust = t; t += align_up((N + 2 * kHalo) * 4, 16);
+  P.tc_t_ust = t; t += align_up(2 * (N + 2 * kHalo + 2) * 4, 16);   // raw row + row / sigma
   P.tc_t_k = t; t += kMaxStages * N * 4;
   P.tc_t_flux = t; t += N * 4;
   P.tc_t_fs = t; t += align_up((2 * kMaxModes + 3 * kMaxForcing + 4) * 4, 16);
@@ -266,7 +267,6 @@ int finalize_tc(ddd1d_handle* h) {
     return DDD1D_OK;
   }
   h->Ptc = P;
-  // AUTO currently resolves to the FFMA kernel unless DDD1D_ENGINE / cfg.engine asks for "tensor"
   h->tc_ok = true;
   return DDD1D_OK;
 }

@@ -61,7 +61,7 @@ struct Params {
   int smem_bytes;
   int use_bulk_copy;
   // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
-  int tc_teams, tc_nlast, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
+  int tc_teams, tc_nlast, tc_stagger_ns, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
   int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
   int tc_t_act_hi, tc_t_act_lo, tc_t_ust, tc_t_k, tc_t_flux, tc_t_fs;      // byte offsets inside a team region
   int tc_w1_off, tc_b1_off, tc_bh_off, tc_bl_off;                          // float offsets into the blob

@@ -225,22 +225,25 @@ __device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, ui
   __syncwarp();
 }
 
-// store 4 consecutive channels of one position into a plane (+ its wrapped halo copy)
-__device__ __forceinline__ void store_chunk(unsigned char* plane, int x, int N, float4 v) {
+// store 4 consecutive channels of one position into a plane (+ its wrapped halo copy).  `edge` is
+// warp-uniform: only the first and last warp of a team own positions that feed the halo.
+__device__ __forceinline__ void store_chunk(unsigned char* plane, int x, int N, bool edge, float4 v) {
   *reinterpret_cast<float4*>(plane + (size_t)(x + 2) * 16) = v;
-  if (x < 2) *reinterpret_cast<float4*>(plane + (size_t)(x + 2 + N) * 16) = v;
-  if (x >= N - 2) *reinterpret_cast<float4*>(plane + (size_t)(x + 2 - N) * 16) = v;
+  if (edge) {
+    if (x < 2) *reinterpret_cast<float4*>(plane + (size_t)(x + 2 + N) * 16) = v;
+    if (x >= N - 2) *reinterpret_cast<float4*>(plane + (size_t)(x + 2 - N) * 16) = v;
+  }
 }
 
 __device__ __forceinline__ void store_split(unsigned char* hi_plane, unsigned char* lo_plane, int x, int N,
-                                            float a, float b, float c, float d) {
+                                            bool edge, float a, float b, float c, float d) {
   float4 h, l;
   split_tf32(a, h.x, l.x);
   split_tf32(b, h.y, l.y);
   split_tf32(c, h.z, l.z);
   split_tf32(d, h.w, l.w);
-  store_chunk(hi_plane, x, N, h);
-  store_chunk(lo_plane, x, N, l);
+  store_chunk(hi_plane, x, N, edge, h);
+  store_chunk(lo_plane, x, N, edge, l);
 }
 
 
@@ -391,6 +394,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     unsigned char* act_hi = tb + P.tc_t_act_hi;
     unsigned char* act_lo = tb + P.tc_t_act_lo;
     float* ust = reinterpret_cast<float*>(tb + P.tc_t_ust);
+    float* unr = ust + (N + 2 * kHalo + 2);              // the same row divided by sigma
     float* kst = reinterpret_cast<float*>(tb + P.tc_t_k);
     float* flux = reinterpret_cast<float*>(tb + P.tc_t_flux);
     float* fs = reinterpret_cast<float*>(tb + P.tc_t_fs);
@@ -398,6 +402,8 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     uint64_t* done = &bars[1 + R + team];
     uint32_t done_parity = 0;
     const int tile = x >> 7;
+    const int warp_in_team = __shfl_sync(0xffffffffu, warp - team * team_warps, 0);
+    const bool edge = warp_in_team == 0 || warp_in_team == team_warps - 1;
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 128);
     const Tableau& tab = *tab_s;
     const bool cons = eq_conservative(P.eq);
@@ -406,6 +412,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     const float* b1 = blob + P.tc_b1_off;
     const float* blast = blob + P.tc_bl_off;            // folded bias of the last layer [32]
 
+    if (team > 0 && W.op == OP_INTEGRATE) __nanosleep((unsigned)team * (unsigned)P.tc_stagger_ns);
     const int g = blockIdx.x * R + team;
     for (int row = g; row < W.batch; row += total_teams) {
       const int sample = W.sample_offset + row;
@@ -423,9 +430,13 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
           for (int j = 0; j < kMaxStages; ++j)
             if (j < s && tab.a[s][j] != 0.0) accd += tab.a[s][j] * (double)kst[j * N + x];
           const float us = (float)(s == 0 ? y : y + W.dt * accd);
+          const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
           ust[x + kHalo] = us;
-          if (x < kHalo) ust[x + kHalo + N] = us;
-          if (x >= N - kHalo) ust[x + kHalo - N] = us;
+          unr[x + kHalo] = usn;
+          if (edge) {
+            if (x < kHalo) { ust[x + kHalo + N] = us; unr[x + kHalo + N] = usn; }
+            if (x >= N - kHalo) { ust[x + kHalo - N] = us; unr[x + kHalo - N] = usn; }
+          }
           const float tstage = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[s] * W.dt : W.t0);
           const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
           if (forced) forcing_terms(P, fs, fterm, x, tstage);
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
           {
             float un[kTaps];
 #pragma unroll
-            for (int k = 0; k < kTaps; ++k) un[k] = __fdiv_rn(u7[k + 1], P.sigma);   // model.py:450-451
+            for (int k = 0; k < kTaps; ++k) un[k] = unr[x + k + 1];
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
               float4 h = *reinterpret_cast<const float4*>(b1 + 4 * c4);
@@ -450,7 +461,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
                 h.z = fmaf(un[k], w.z, h.z); h.w = fmaf(un[k], w.w, h.w);
               }
               const int act = P.layer[0].act;
-              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N,
+              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
                           activate(h.x, act), activate(h.y, act), activate(h.z, act), activate(h.w, act));
             }
           }
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
               const float4 b = *reinterpret_cast<const float4*>(bias + 4 * c4);
-              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N,
+              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
                           activate(acc[4 * c4] + b.x, act), activate(acc[4 * c4 + 1] + b.y, act),
                           activate(acc[4 * c4 + 2] + b.z, act), activate(acc[4 * c4 + 3] + b.w, act));
             }
