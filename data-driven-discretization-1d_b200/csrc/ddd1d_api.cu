@@ -139,6 +139,7 @@ int finalize_tc(ddd1d_handle* h) {
   if (c.mode != DDD1D_MODE_LEARNED) h->tc_why = "not a learned-coefficient handle";
   else if (c.kernel_size != 5 || c.filter_size != tc::kF) h->tc_why = "needs kernel_size 5 and filter_size 32";
   else if (c.num_layers < 2 || c.num_layers > 3) h->tc_why = "needs 2 or 3 conv layers";
+  else if (c.activation != DDD1D_ACT_RELU) h->tc_why = "needs the relu nonlinearity";
   else if (N != 128 && N != 256 && N != 512) h->tc_why = "needs num_points in {128, 256, 512}";
   if (!h->tc_why.empty() || want == DDD1D_ENGINE_FFMA) {
     if (want == DDD1D_ENGINE_TENSOR)
@@ -258,7 +259,7 @@ int finalize_tc(ddd1d_handle* h) {
   CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   P.blob = h->d_blob_tc;
   CUDA_TRY(h, cudaFuncSetAttribute(tc::tc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  h->tc_threads = P.tc_teams * (N + 32 * (N / 128));   // team threads + one MMA-issuer warp per 128-point tile
+  h->tc_threads = P.tc_teams * N;            // thread <-> grid point; tile-leader warps issue the MMAs
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_row_kernel, h->tc_threads, P.smem_bytes));
   if (occ < 1) {

@@ -19,9 +19,9 @@
 //
 // Warp roles (one CTA per SM, persistent): R "row teams" of N threads (thread <-> grid point; the
 // team's warps are 4-aligned so each warp reads its own TMEM lane quadrant) run the whole
-// Runge-Kutta program of their row; four extra warps (one per 128-position tile, one per SM
-// sub-partition) issue the tcgen05.mma of their tile and signal completion with
-// tcgen05.commit -> mbarrier.  While one team runs an epilogue on the CUDA
+// Runge-Kutta program of their row.  The first warp of each 128-position tile issues that tile's
+// tcgen05.mma once the team's planes are complete and signals completion with
+// tcgen05.commit -> mbarrier; 16 warps per CTA keep 128 registers per thread (no spills).  While one team runs an epilogue on the CUDA
 // cores, the tensor pipe works on another team's tile.
 #pragma once
 #include "ddd1d_device.cuh"
@@ -255,17 +255,20 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
       : "r"(taddr)
       : "memory");
 }
-// sixteen outputs = (even main + odd main) + (even cross + odd cross); four loads in flight, one wait
+// sixteen outputs = (even main + odd main) + (even cross + odd cross); two loads in flight at a time
+// keeps the register peak at 48
 __device__ __forceinline__ void tmem_sum4x16(uint32_t t_em, uint32_t t_om, uint32_t t_ec, uint32_t t_oc, float* v) {
-  uint32_t a[16], b[16], c[16], d[16];
+  uint32_t a[16], b[16];
   tmem_ld16_issue(t_em, a);
   tmem_ld16_issue(t_om, b);
-  tmem_ld16_issue(t_ec, c);
-  tmem_ld16_issue(t_oc, d);
   tmem_wait_ld();
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    v[i] = (__uint_as_float(a[i]) + __uint_as_float(b[i])) + (__uint_as_float(c[i]) + __uint_as_float(d[i]));
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[i]) + __uint_as_float(b[i]);
+  tmem_ld16_issue(t_ec, a);
+  tmem_ld16_issue(t_oc, b);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += (__uint_as_float(a[i]) + __uint_as_float(b[i]));
 }
 // NB = 32: block layout [even main 32 | even cross 32 | odd main 32 | odd cross 32]
 __device__ __forceinline__ void tmem_sum32(uint32_t taddr, float (&v)[32]) {
@@ -310,13 +313,12 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
+__global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = P.N, R = P.tc_teams, tiles = N / 128;
   const int team_warps = N / 32;
-  const bool is_mma_warp = warp >= R * team_warps;       // one issuer warp per team, after the team warps
-  const bool is_alloc_warp = warp == R * team_warps;
+  const bool is_alloc_warp = warp == 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.off_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot);
   float* blob = reinterpret_cast<float*>(smem_raw + P.off_blob);
@@ -352,41 +354,7 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
   const int stages_of = tab_s->stages;
   const int rhs_per_row = (W.op == OP_INTEGRATE) ? W.nsteps * stages_of : 1;
 
-  if (is_mma_warp) {
-    // ---------------- MMA issuer of (team t, tile m): wait for a request, issue the layer, commit ----------------
-    // everything below is warp-uniform (shuffled from lane 0) so the descriptors stay in uniform registers
-    const int mw = __shfl_sync(0xffffffffu, warp - R * team_warps, 0);
-    const int t = mw / tiles, tile_m = mw % tiles;
-    const int g = blockIdx.x * R + t;
-    const int rows = g < W.batch ? (W.batch - g + total_teams - 1) / total_teams : 0;
-    const uint32_t requests = (uint32_t)rows * (uint32_t)rhs_per_row * (uint32_t)requests_per_rhs;
-    const uint32_t smem_s = smem_u32(dyn_smem);
-    const uint32_t blob_s = smem_s + (uint32_t)P.off_blob;
-    const uint32_t team_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)t * (uint32_t)P.tc_team_stride;
-    const uint32_t act_hi = team_s + (uint32_t)P.tc_t_act_hi, act_lo = team_s + (uint32_t)P.tc_t_act_lo;
-    const uint32_t d_col = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)((t * tiles + tile_m) * 128);
-    uint64_t* req_bar = &bars[1 + t];
-    uint64_t* done_bar = &bars[1 + R + t];
-    uint32_t parity = 0;
-    int layer_idx = 0;
-    for (uint32_t r = 0; r < requests; ++r) {
-      mbar_wait_guarded(req_bar, parity);
-      parity ^= 1u;
-      fence_after();
-      if (P.tc_debug & 1) {
-        // timing experiment: no MMAs, the commit below completes immediately
-      } else if (layer_idx != hidden_tc_layers) {
-        const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
-        issue_layer(act_hi, act_lo, plane_bytes, blob_s + off, 2u * 32u * 16u, tile_m, d_col, 32);
-      } else {
-        issue_layer(act_hi, act_lo, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u, 2u * (uint32_t)NL * 16u,
-                    tile_m, d_col, NL);
-      }
-      if (elect_one()) mma_commit(done_bar);
-      __syncwarp();
-      layer_idx = (layer_idx + 1 == requests_per_rhs) ? 0 : layer_idx + 1;
-    }
-  } else {
+  {
     // ---------------- row team ----------------
     const int team = warp / team_warps;
     const int x = tid - team * N;                      // this thread's grid point
@@ -404,6 +372,35 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     const int tile = x >> 7;
     const int warp_in_team = __shfl_sync(0xffffffffu, warp - team * team_warps, 0);
     const bool edge = warp_in_team == 0 || warp_in_team == team_warps - 1;
+    // The first warp of every 128-position tile also issues that tile's MMAs (asynchronous: it then
+    // waits for completion like everybody else).  All issue-side values are warp-uniform.
+    const bool issuer = (warp_in_team & 3) == 0;
+    const int tile_u = warp_in_team >> 2;
+    const int team_u = __shfl_sync(0xffffffffu, team, 0);
+    const uint32_t smem_s = smem_u32(dyn_smem);
+    const uint32_t blob_s = smem_s + (uint32_t)P.off_blob;
+    const uint32_t team_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)team_u * (uint32_t)P.tc_team_stride;
+    const uint32_t act_hi_s = team_s + (uint32_t)P.tc_t_act_hi, act_lo_s = team_s + (uint32_t)P.tc_t_act_lo;
+    const uint32_t d_col = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)((team_u * tiles + tile_u) * 128);
+    uint32_t req_parity = 0;
+    auto post_layer = [&](int layer_idx) {
+      if (issuer) {
+        mbar_wait_guarded(req, req_parity);          // every thread of the team has stored its planes
+        fence_after();
+        if (P.tc_debug & 1) {
+          // timing experiment: no MMAs
+        } else if (layer_idx != hidden_tc_layers) {
+          const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
+          issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, tile_u, d_col, 32);
+        } else {
+          issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
+                      2u * (uint32_t)NL * 16u, tile_u, d_col, NL);
+        }
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
+      }
+      req_parity ^= 1u;
+    };
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 128);
     const Tableau& tab = *tab_s;
     const bool cons = eq_conservative(P.eq);
@@ -412,7 +409,6 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
     const float* b1 = blob + P.tc_b1_off;
     const float* blast = blob + P.tc_bl_off;            // folded bias of the last layer [32]
 
-    if (team > 0 && W.op == OP_INTEGRATE) __nanosleep((unsigned)team * (unsigned)P.tc_stagger_ns);
     const int g = blockIdx.x * R + team;
     for (int row = g; row < W.batch; row += total_teams) {
       const int sample = W.sample_offset + row;
@@ -460,13 +456,14 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
                 h.x = fmaf(un[k], w.x, h.x); h.y = fmaf(un[k], w.y, h.y);
                 h.z = fmaf(un[k], w.z, h.z); h.w = fmaf(un[k], w.w, h.w);
               }
-              const int act = P.layer[0].act;
+              // hidden activations are ReLU on this engine (other nonlinearities use the FFMA engine)
               store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
-                          activate(h.x, act), activate(h.y, act), activate(h.z, act), activate(h.w, act));
+                          fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
             }
           }
           fence_async_smem();
           mbar_arrive(req);
+          post_layer(0);
 
           // ---- hidden layers on the tensor pipe; epilogue rewrites the planes in place ----
           for (int l = 0; l < hidden_tc_layers; ++l) {
@@ -477,16 +474,16 @@ __global__ void __launch_bounds__(640, 1) tc_row_kernel(const __grid_constant__ 
             tmem_sum32(taddr, acc);
             fence_before();
             const float* bias = blob + P.tc_bh_off + l * kF;
-            const int act = P.layer[1 + l].act;
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
               const float4 b = *reinterpret_cast<const float4*>(bias + 4 * c4);
               store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
-                          activate(acc[4 * c4] + b.x, act), activate(acc[4 * c4 + 1] + b.y, act),
-                          activate(acc[4 * c4 + 2] + b.z, act), activate(acc[4 * c4 + 3] + b.w, act));
+                          fmaxf(acc[4 * c4] + b.x, 0.f), fmaxf(acc[4 * c4 + 1] + b.y, 0.f),
+                          fmaxf(acc[4 * c4 + 2] + b.z, 0.f), fmaxf(acc[4 * c4 + 3] + b.w, 0.f));
             }
             fence_async_smem();
             mbar_arrive(req);
+            post_layer(l + 1);
           }
 
           // ---- last layer: stencil coefficients (projection folded in) straight from TMEM ----

@@ -78,7 +78,7 @@ enum {
 };
 
 /* conv-stack engine (learned mode).  AUTO picks the tcgen05 kernel when the net is
- * the shape it is built for (kernel_size 5, filter_size 32, >= 2 layers, N in
+ * the shape it is built for (kernel_size 5, filter_size 32, relu, 2 or 3 layers, N in
  * {128, 256, 512}) and the FP32-FFMA kernel otherwise; both satisfy the same
  * float32 tolerances (the tensor path uses the 3xTF32 split). */
 enum { DDD1D_ENGINE_AUTO = 0, DDD1D_ENGINE_FFMA = 1, DDD1D_ENGINE_TENSOR = 2 };

@@ -127,10 +127,10 @@ def test_tensor_engine_trajectories(n, kind, dt):
 
 
 def test_tensor_engine_other_nets_and_schemes():
-  """2-layer net, raw (accuracy-order 0) projection, tanh; midpoint scheme."""
+  """2-layer net, raw (accuracy-order 0) projections; midpoint scheme."""
   from ddd1d_b200 import runtime
   n = 128
-  for overrides in (dict(num_layers=2), dict(polynomial_accuracy_order=0), dict(nonlinearity='tanh'),
+  for overrides in (dict(num_layers=2), dict(polynomial_accuracy_order=0),
                     dict(polynomial_accuracy_order=0, ensure_unbiased_coefficients=True)):
     eq = G.product_equation('burgers', 'plain', n)
     hp = G.product_hparams('burgers', 'plain', n, **overrides)
@@ -157,4 +157,9 @@ def test_tensor_engine_rejects_unsupported_shapes():
   w = O.glorot_weights(G.oracle_equation('burgers', 'plain', 64), O.NetSpec(), seed=0)
   with pytest.raises(NotImplementedError):
     runtime.learned_solver(eq, hp, w, engine='tensor').engine()
+  assert runtime.learned_solver(eq, hp, w).engine() == 'ffma'
+  # a tanh net at a supported size also takes the FFMA engine
+  eq = G.product_equation('burgers', 'plain', 128)
+  hp = G.product_hparams('burgers', 'plain', 128, nonlinearity='tanh')
+  w = O.glorot_weights(G.oracle_equation('burgers', 'plain', 128), O.NetSpec(nonlinearity='tanh'), seed=0)
   assert runtime.learned_solver(eq, hp, w).engine() == 'ffma'
