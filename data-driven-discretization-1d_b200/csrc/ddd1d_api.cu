@@ -224,6 +224,12 @@ int finalize_tc(ddd1d_handle* h) {
       blob[P.tc_bl_off + q] = (float)acc;
     }
   }
+  for (int i = 0; i < K * F; ++i) P.tc_w1[i] = blob[P.tc_w1_off + i];
+  for (int i = 0; i < F; ++i) {
+    P.tc_b1[i] = blob[P.tc_b1_off + i];
+    P.tc_bh[i] = blob[P.tc_bh_off + i];
+    P.tc_bl[i] = blob[P.tc_bl_off + i];
+  }
   blob.resize(align_up((int)blob.size(), 32), 0.f);
   P.blob_floats = (int)blob.size();
   P.tc_nlast = NL;
@@ -237,10 +243,10 @@ int finalize_tc(ddd1d_handle* h) {
   P.tc_t_ust = t; t += align_up(2 * (N + 2 * kHalo + 2) * 4, 16);   // raw row + row / sigma
   P.tc_t_k = t; t += kMaxStages * N * 4;
   P.tc_t_flux = t; t += N * 4;
-  P.tc_t_fs = t; t += align_up((2 * kMaxModes + 3 * kMaxForcing + 4) * 4, 16);
+  P.tc_t_fs = t; t += align_up((kMaxStages * tc::kForcingStride + 4) * 4, 16);
   P.tc_team_stride = align_up(t, 128);
   P.off_bar = 0;
-  P.tc_off_slot = 112;
+  P.tc_off_slot = 96;                        // TMEM base (4 B) + tensor-pipe ticket lock (8 B)
   P.tc_off_tab = 128;                       // Tableau (200 B)
   P.off_blob = 384;
   P.tc_off_team0 = align_up(P.off_blob + P.blob_floats * 4, 128);

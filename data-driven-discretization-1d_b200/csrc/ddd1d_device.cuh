@@ -66,6 +66,11 @@ struct Params {
   int tc_t_act_hi, tc_t_act_lo, tc_t_ust, tc_t_k, tc_t_flux, tc_t_fs;      // byte offsets inside a team region
   int tc_w1_off, tc_b1_off, tc_bh_off, tc_bl_off;                          // float offsets into the blob
   int tc_bhid_off, tc_bhid_stride, tc_bhid_lo, tc_blast_off, tc_blast_lo;
+  // small tables read as constant-bank FFMA operands by every thread (no shared-memory traffic)
+  float tc_w1[5 * 32];      // first layer [tap][channel]
+  float tc_b1[32];          // first-layer bias
+  float tc_bh[32];          // bias of the (single) hidden tensor layer
+  float tc_bl[32];          // folded bias of the last layer
 };
 
 struct Work {

@@ -32,6 +32,7 @@ namespace tc {
 constexpr int kF = 32;             // hidden width this path is built for
 constexpr int kTaps = 5;
 constexpr int kChunks = kF / 4;    // 16-byte chunks along ci
+constexpr int kForcingStride = 2 * kMaxModes + 3 * kMaxForcing;   // floats of forcing scratch per RK stage
 constexpr long long kSpinCycles = 4000000000ll;   // ~2 s at 1.9 GHz: a protocol bug traps instead of hanging
 
 // ---- descriptors -------------------------------------------------------------------------------
@@ -284,7 +285,7 @@ __device__ __forceinline__ void tmem_sum16(uint32_t taddr, float (&v)[16]) {
 // then the stencil dot products (model.py:536-548).  NLV = TMEM columns of the last layer.
 template <int NLV>
 __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, uint32_t taddr,
-                                              const float* __restrict__ blast, const float (&u7)[kWin],
+                                              const float (&u7)[kWin],
                                               int row, int x, float (&dv)[kMaxD]) {
   float cfv[NLV];
   if (NLV == 16) tmem_sum16(taddr, reinterpret_cast<float(&)[16]>(cfv));
@@ -298,7 +299,7 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kWin; ++j) {
-      const float cf = cfv[d * kWin + j] + blast[d * kWin + j];
+      const float cf = cfv[d * kWin + j] + P.tc_bl[d * kWin + j];
       sum = fmaf(cf, u7[j], sum);
       if (W.op == OP_COEF) {
         const int i = j - P.wshift;
@@ -330,10 +331,12 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
   Tableau* tab_s = reinterpret_cast<Tableau*>(smem_raw + P.tc_off_tab);
   if (tid == 0) {
     *tab_s = make_tableau(W.scheme);
+    reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot + 4)[0] = 0u;
+    reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot + 4)[1] = 0u;
     mbar_init(&bars[0], 1);
     for (int t = 0; t < R; ++t) {
       mbar_init(&bars[1 + t], (uint32_t)N);
-      mbar_init(&bars[1 + R + t], (uint32_t)tiles);   // one tcgen05.commit per tile issuer
+      mbar_init(&bars[1 + R + t], 1);
     }
     mbar_fence_init();
   }
@@ -374,40 +377,62 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
     const bool edge = warp_in_team == 0 || warp_in_team == team_warps - 1;
     // The first warp of every 128-position tile also issues that tile's MMAs (asynchronous: it then
     // waits for completion like everybody else).  All issue-side values are warp-uniform.
-    const bool issuer = (warp_in_team & 3) == 0;
-    const int tile_u = warp_in_team >> 2;
+    const bool issuer = warp_in_team == 0;
     const int team_u = __shfl_sync(0xffffffffu, team, 0);
     const uint32_t smem_s = smem_u32(dyn_smem);
     const uint32_t blob_s = smem_s + (uint32_t)P.off_blob;
     const uint32_t team_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)team_u * (uint32_t)P.tc_team_stride;
     const uint32_t act_hi_s = team_s + (uint32_t)P.tc_t_act_hi, act_lo_s = team_s + (uint32_t)P.tc_t_act_lo;
-    const uint32_t d_col = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)((team_u * tiles + tile_u) * 128);
+    const uint32_t d_col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(team_u * tiles * 128);
+    // ticket lock on the tensor pipe: one team's MMAs in flight at a time, so they run at full speed
+    // while the other teams are in their CUDA-core phases (alternation instead of lockstep)
+    volatile uint32_t* lock = reinterpret_cast<volatile uint32_t*>(smem_raw + P.tc_off_slot + 4);  // [0] next ticket, [1] now serving
     uint32_t req_parity = 0;
+    bool holding = false;
     auto post_layer = [&](int layer_idx) {
       if (issuer) {
         mbar_wait_guarded(req, req_parity);          // every thread of the team has stored its planes
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(const_cast<uint32_t*>(lock), 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        long long start = 0;
+        uint32_t spins = 0;
+        while (lock[1] != ticket) {
+          if ((++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (start == 0) start = now;
+            else if (now - start > kSpinCycles) asm volatile("trap;");
+          }
+        }
         fence_after();
         if (P.tc_debug & 1) {
           // timing experiment: no MMAs
         } else if (layer_idx != hidden_tc_layers) {
           const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
-          issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, tile_u, d_col, 32);
+          for (int m = 0; m < tiles; ++m)
+            issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m, d_col0 + (uint32_t)m * 128u, 32);
         } else {
-          issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
-                      2u * (uint32_t)NL * 16u, tile_u, d_col, NL);
+          for (int m = 0; m < tiles; ++m)
+            issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
+                        2u * (uint32_t)NL * 16u, m, d_col0 + (uint32_t)m * 128u, NL);
         }
         if (elect_one()) mma_commit(done);
         __syncwarp();
+        holding = true;
       }
       req_parity ^= 1u;
+    };
+    // called right after a wait on `done`: the team's MMAs have completed, pass the pipe on
+    auto release_pipe = [&]() {
+      if (issuer && holding) {
+        if (lane == 0) atomicAdd(const_cast<uint32_t*>(lock + 1), 1u);
+        holding = false;
+      }
     };
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 128);
     const Tableau& tab = *tab_s;
     const bool cons = eq_conservative(P.eq);
     const bool forced_eq = eq_forced(P.eq) && P.P > 0;
-    const float* w1 = blob + P.tc_w1_off;               // [5][32]
-    const float* b1 = blob + P.tc_b1_off;
-    const float* blast = blob + P.tc_bl_off;            // folded bias of the last layer [32]
 
     const int g = blockIdx.x * R + team;
     for (int row = g; row < W.batch; row += total_teams) {
@@ -433,11 +458,18 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
             if (x < kHalo) { ust[x + kHalo + N] = us; unr[x + kHalo + N] = usn; }
             if (x >= N - kHalo) { ust[x + kHalo - N] = us; unr[x + kHalo - N] = usn; }
           }
-          const float tstage = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[s] * W.dt : W.t0);
           const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
-          if (forced) forcing_terms(P, fs, fterm, x, tstage);
+          if (forced && s == 0) {
+            // the sincos of every stage of this step, spread over nstages * P threads
+            const int sq = x / P.P, q = x - sq * P.P;
+            if (sq < nstages) {
+              const ForcingTerm fq = (sq == 0) ? fterm : load_forcing_term(P, sample, q);
+              const float ts = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[sq] * W.dt : W.t0);
+              forcing_terms(P, fs + sq * kForcingStride, fq, q, ts);
+            }
+          }
           team_sync(team, N);
-          if (forced) forcing_reduce(P, fs, x);          // visible to the team after the mbarrier rounds below
+          if (forced) forcing_reduce(P, fs + s * kForcingStride, x);   // visible to the team after the mbarrier rounds below
           float u7[kWin];
 #pragma unroll
           for (int j = 0; j < kWin; ++j) u7[j] = ust[x + j];
@@ -449,12 +481,13 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
             for (int k = 0; k < kTaps; ++k) un[k] = unr[x + k + 1];
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
-              float4 h = *reinterpret_cast<const float4*>(b1 + 4 * c4);
+              float4 h = make_float4(P.tc_b1[4 * c4], P.tc_b1[4 * c4 + 1], P.tc_b1[4 * c4 + 2], P.tc_b1[4 * c4 + 3]);
 #pragma unroll
-              for (int k = 0; k < kTaps; ++k) {
-                const float4 w = *reinterpret_cast<const float4*>(w1 + k * kF + 4 * c4);
-                h.x = fmaf(un[k], w.x, h.x); h.y = fmaf(un[k], w.y, h.y);
-                h.z = fmaf(un[k], w.z, h.z); h.w = fmaf(un[k], w.w, h.w);
+              for (int k = 0; k < kTaps; ++k) {      // filters are constant-bank operands of the FFMAs
+                h.x = fmaf(un[k], P.tc_w1[k * kF + 4 * c4], h.x);
+                h.y = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 1], h.y);
+                h.z = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 2], h.z);
+                h.w = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 3], h.w);
               }
               // hidden activations are ReLU on this engine (other nonlinearities use the FFMA engine)
               store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
@@ -469,14 +502,14 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
           for (int l = 0; l < hidden_tc_layers; ++l) {
             mbar_wait_guarded(done, done_parity);
             done_parity ^= 1u;
+            release_pipe();
             fence_after();
             float acc[32];
             tmem_sum32(taddr, acc);
             fence_before();
-            const float* bias = blob + P.tc_bh_off + l * kF;
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
-              const float4 b = *reinterpret_cast<const float4*>(bias + 4 * c4);
+              const float4 b = make_float4(P.tc_bh[4 * c4], P.tc_bh[4 * c4 + 1], P.tc_bh[4 * c4 + 2], P.tc_bh[4 * c4 + 3]);
               store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
                           fmaxf(acc[4 * c4] + b.x, 0.f), fmaxf(acc[4 * c4 + 1] + b.y, 0.f),
                           fmaxf(acc[4 * c4 + 2] + b.z, 0.f), fmaxf(acc[4 * c4 + 3] + b.w, 0.f));
@@ -489,10 +522,11 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
           // ---- last layer: stencil coefficients (projection folded in) straight from TMEM ----
           mbar_wait_guarded(done, done_parity);
           done_parity ^= 1u;
+          release_pipe();
           fence_after();
           float dv[kMaxD];
-          if (NL == 16) last_epilogue<16>(P, W, taddr, blast, u7, row, x, dv);
-          else last_epilogue<32>(P, W, taddr, blast, u7, row, x, dv);
+          if (NL == 16) last_epilogue<16>(P, W, taddr, u7, row, x, dv);
+          else last_epilogue<32>(P, W, taddr, u7, row, x, dv);
           if (W.op == OP_COEF || W.op == OP_DERIV) continue;
           float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
           if (cons) {
@@ -504,8 +538,8 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
           if (forced) {
             float f = 0.f;
             for (int m = 0; m < P.M; ++m) {
-              f = fmaf(fs[m], __ldg(P.fbasis + (size_t)m * N + x), f);
-              f = fmaf(fs[P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
+              f = fmaf(fs[s * kForcingStride + m], __ldg(P.fbasis + (size_t)m * N + x), f);
+              f = fmaf(fs[s * kForcingStride + P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
             }
             r = __fadd_rn(r, f);
           }
@@ -529,7 +563,7 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
         }
       }
       if (W.op == OP_INTEGRATE && W.first_bad) {
-        unsigned int* slot = reinterpret_cast<unsigned int*>(fs + 2 * kMaxModes + 3 * kMaxForcing);
+        unsigned int* slot = reinterpret_cast<unsigned int*>(fs + kMaxStages * kForcingStride);
         if (x == 0) *slot = 0xffffffffu;
         team_sync(team, N);
         atomicMin(slot, first_bad < 0 ? 0xffffffffu : (unsigned int)first_bad);
