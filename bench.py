@@ -261,6 +261,7 @@ def workload_config(args, batch):
       'parallelism': 'batch-sharded x%d, no data-path collective' % args.gpus,
       'l2': 'flushed between timed steps (256 MiB write)',
       'weights': 'seeded Glorot-uniform, last layer x1e-2, zero biases (random init of the reference architecture)',
+      'arithmetic': 'float32 state I/O, float64 RK accumulation; conv stack FP32 FFMA or 3xTF32 tensor (FP32-faithful, tests/test_gpu_tensor.py)',
   }
 
 
@@ -346,6 +347,18 @@ def run_ours(args):
   e2e_total = ddd.distributed.max_over_ranks(e2e_local)
   e2e_value = units_per_step * args.steps / e2e_total
 
+  # the one collective of the path: gather the final snapshots of all shards (NCCL over NVLink), untimed
+  gather_ms = None
+  if world > 1:
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record(stream)
+    full = ddd.distributed.gather_snapshots(out, batch * world, sample_axis=1)
+    g1.record(stream)
+    torch.cuda.synchronize(dev)
+    assert tuple(full.shape) == (1, batch * world, n)
+    gather_ms = ddd.distributed.max_over_ranks(g0.elapsed_time(g1))
+
   if rank != 0:
     if world > 1:
       torch.distributed.barrier()
@@ -358,6 +371,25 @@ def run_ours(args):
   achieved_gbs = 8.0 * gps_kernel / 1e9          # 8 algorithmic bytes per grid-point-step
   fl = flops_per_gps(kind, mode)
   shape = solver.launch_shape(batch)
+  engine = solver.engine() if mode == 'learned' else 'ffma'
+  kernel_name = 'ddd1d::tc::tc_row_kernel' if engine == 'tensor' else 'ddd1d::row_kernel<%s>' % mode
+  hbm = {'bound': 'hbm', 'achieved': achieved_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+         'frac': achieved_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_kind': peak_kind,
+         'algorithmic_bytes_per_launch': 8.0 * batch * n * rk,
+         'note': 'rows stay on chip for all RK steps of a launch (ncu: DRAM traffic ~7% of the algorithmic '
+                 'bytes), so HBM is idle by design; the binding resource is on-chip'}
+  achieved_tf = fl * gps_kernel / 1e12
+  if engine == 'tensor':
+    tf32_peak = peaks['bf16_tflops_sustained' if 'bf16_tflops_sustained' in peaks else 'bf16_tflops'] / 2.0
+    roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / tf32_peak, 'traffic': None, 'peak_kind': peak_kind,
+                'note': 'achieved = algorithmic FP32-equivalent FLOPs (%d per grid-point-step); peak = dense TF32 = '
+                        'half of the measured sustained bf16 cuBLAS rate.  The 3xTF32 split executes 3x the conv '
+                        'FLOPs on the tensor pipe, and each M128xN32xK8 MMA reads ~5 KB of shared-memory operands '
+                        'for 16 clk of math: the kernel is shared-memory-operand bound (profiles/r01)' % fl}
+  else:
+    roofline = dict(hbm)
+  roofline.update({'kernel': kernel_name, 'kernel_ms': kernel_ms})
   line = {
       'metric': 'grid-point-steps/sec', 'value': value, 'unit': 'grid-point-steps/s',
       'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
@@ -367,16 +399,14 @@ def run_ours(args):
       'e2e': {'value': e2e_value, 'unit': 'grid-point-steps/s',
               'h2d_bytes_per_step': batch * n * 4, 'd2h_bytes_per_step': batch * n * 4 + batch * 4},
       'gpu_launches': int(launches),
-      'roofline': {'bound': 'hbm', 'achieved': achieved_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                   'frac': achieved_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_kind': peak_kind,
-                   'kernel': 'ddd1d::row_kernel<%s>' % mode, 'kernel_ms': kernel_ms,
-                   'algorithmic_bytes_per_launch': 8.0 * batch * n * rk,
-                   'note': 'rows stay on chip for all RK steps of a launch, so the kernel is bound by the '
-                           'FP32 pipe, not HBM; see "compute"'},
-      'compute': {'bound': 'fp32-ffma', 'achieved_tflops': fl * gps_kernel / 1e12,
-                  'peak_tflops': FP32_PEAK_TFLOPS, 'frac': fl * gps_kernel / 1e12 / FP32_PEAK_TFLOPS,
-                  'flops_per_grid_point_step': fl, 'peak_kind': 'nominal 148 SM x 128 FMA x 1.965 GHz'},
-      'launch': shape, 'wall_s': wall,
+      'engine': engine,
+      'roofline': roofline,
+      'roofline_hbm': hbm,
+      'compute': {'bound': 'fp32-ffma', 'achieved_tflops': achieved_tf,
+                  'peak_tflops': FP32_PEAK_TFLOPS, 'frac': achieved_tf / FP32_PEAK_TFLOPS,
+                  'flops_per_grid_point_step': fl, 'peak_kind': 'nominal 148 SM x 128 FMA x 1.965 GHz',
+                  'note': 'FP32-equivalent algorithmic FLOPs against the CUDA-core peak (can exceed 1 on the tensor engine)'},
+      'launch': shape, 'wall_s': wall, 'final_gather_ms': gather_ms,
   }
   if not args.no_cpu:
     samples = 8

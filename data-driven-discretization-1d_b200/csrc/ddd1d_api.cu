@@ -310,6 +310,7 @@ int finalize(ddd1d_handle* h) {
     if (getenv("DDD1D_FORCE_GENERIC_CONV")) P.fast_conv = 0;
     P.pitch = align_up(N + K - 1, 4);
     h->threads = P.fast_conv ? std::min(512, 128 * ((N + 255) / 256)) : 256;
+    if (P.fast_conv && getenv("DDD1D_FFMA_THREADS")) h->threads = std::max(64, std::min(512, atoi(getenv("DDD1D_FFMA_THREADS")) / 32 * 32));
     const int nwarps = h->threads / 32;
     int cin = 1;
     for (int l = 0; l < c.num_layers; ++l) {

@@ -410,16 +410,26 @@ __device__ __forceinline__ Smem carve(const Params& P, unsigned char* base) {
   return s;
 }
 
-// stage row <- float(value) with its periodic halo; value(p) is evaluated per thread.
+// stage row <- float(value) with its periodic halo; value(p) is evaluated per thread.  In learned
+// mode the same pass writes the net input u / standard_deviation (model.py:450-451) as channel 0 of
+// act0, so the RHS evaluation starts at the first conv layer without another barrier.
 template <typename F>
 __device__ __forceinline__ void write_stage_row(const Params& P, const Smem& S, F value) {
   const int N = P.N;
+  const bool learned = P.mode == MODE_LEARNED;
+  const int kl = P.kleft, kr = P.K - 1 - P.kleft;
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
     float v = value(p);
     S.ust[p + kHalo] = v;
     // wrapped copies (also correct when N < kHalo: every halo slot is assigned by some p)
     for (int q = p - N; q >= -kHalo; q -= N) S.ust[q + kHalo] = v;
     for (int q = p + N; q < N + kHalo; q += N) S.ust[q + kHalo] = v;
+    if (learned) {
+      const float vn = __fdiv_rn(v, P.sigma);
+      S.act0[p + kl] = vn;
+      for (int q = p - N; q >= -kl; q -= N) S.act0[q + kl] = vn;
+      for (int q = p + N; q < N + kr; q += N) S.act0[q + kl] = vn;
+    }
   }
 }
 
@@ -583,16 +593,7 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
   if (forced) forcing_terms(P, S.fs, fterm, threadIdx.x, t);
 
   if (MODE == MODE_LEARNED) {
-    // net = inputs / standard_deviation (model.py:450-451), channel 0 of act0
-    const int kl = P.kleft, kr = P.K - 1 - P.kleft;
-    for (int p = threadIdx.x; p < N; p += blockDim.x) {
-      float v = __fdiv_rn(S.ust[p + kHalo], P.sigma);
-      S.act0[p + kl] = v;
-      for (int q = p - N; q >= -kl; q -= N) S.act0[q + kl] = v;
-      for (int q = p + N; q < N + kr; q += N) S.act0[q + kl] = v;
-    }
-    __syncthreads();
-    if (forced) forcing_reduce(P, S.fs, threadIdx.x);   // visible after the conv barriers
+    // act0 channel 0 already holds inputs / standard_deviation (write_stage_row)
     float* in = S.act0;
     float* out = S.act1;
     for (int l = 0; l < P.nlayers; ++l) {
@@ -603,9 +604,18 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
         else if (L.pbt == 2) conv5_layer<4, 2>(L, S.blob, in, out, N, P.pitch);
         else conv5_layer<4, 1>(L, S.blob, in, out, N, P.pitch);
         __syncthreads();
+        // the forcing terms written on entry are visible now; the sums become visible at the next barrier
+        if (forced && l == 0) {
+          forcing_reduce(P, S.fs, threadIdx.x);
+          if (P.nlayers == 1) __syncthreads();
+        }
       } else {
         conv_generic_layer(L, S.blob, in, out, N, P.pitch, P.K, P.kleft);
         __syncthreads();
+        if (forced && l == 0) {
+          forcing_reduce(P, S.fs, threadIdx.x);
+          if (P.nlayers == 1) __syncthreads();
+        }
         if (l + 1 < P.nlayers) {
           fill_halo(out, L.cout, N, P.pitch, P.K, P.kleft);
           __syncthreads();
