@@ -164,7 +164,9 @@ def synthetic_weights(kind, n):
   return out
 
 
-def initial_rows(batch, n, seed):
+def initial_rows(batch, n, seed, workload=None):
+  if workload == 'c1b':
+    return np.zeros((batch, n), np.float32)       # BurgersEquation.initial_value() (equations.py:256-257)
   rs = np.random.RandomState(seed)
   x = 2 * np.pi * np.arange(n) / n
   rows = np.zeros((batch, n))
@@ -193,7 +195,7 @@ def _cpu_one_sample(args):
     diff = O.WENODifferentiator(eq)
   else:
     diff = O.PolynomialDifferentiator(eq, 1)
-  y0 = initial_rows(1, n, seed)[0].astype(np.float64)
+  y0 = initial_rows(1, n, seed, workload)[0].astype(np.float64)
   t_end = rk_steps * dt
   # SciPy RK23 with the controller pinned at max_step (the reference's regime, integrate.py:154-155)
   sol = scipy.integrate.solve_ivp(diff, (0.0, t_end), y0, t_eval=[0.0, t_end], max_step=dt, method='RK23')
@@ -249,7 +251,7 @@ def run_reference(args):
                        'sample': sample},
       'e2e': {'value': value, 'unit': 'grid-point-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 def workload_config(args, batch):
@@ -282,7 +284,7 @@ def run_ours(args):
   integrator, dt, n = build_case(args.workload, batch, seed_offset=rank * batch)
   solver = integrator.solver
   rk = args.rk_steps
-  u0 = torch.as_tensor(initial_rows(batch, n, seed=1000 + rank)).to(dev)
+  u0 = torch.as_tensor(initial_rows(batch, n, seed=1000 + rank, workload=args.workload)).to(dev)
   flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
   stream = torch.cuda.current_stream(dev)
 
@@ -325,7 +327,7 @@ def run_ours(args):
   value = units_per_step / (ms_per_step * 1e-3)
 
   # ---- timed: end to end through the C ABI with pinned host buffers ----
-  host_in = torch.as_tensor(initial_rows(batch, n, seed=1000 + rank)).pin_memory()
+  host_in = torch.as_tensor(initial_rows(batch, n, seed=1000 + rank, workload=args.workload)).pin_memory()
   host_out = torch.empty((1, batch, n), dtype=torch.float32).pin_memory()
   host_bad = torch.empty(batch, dtype=torch.int32).pin_memory()
   import ctypes
@@ -417,13 +419,32 @@ def run_ours(args):
         'value': rate, 'unit': 'grid-point-steps/s', 'cores': 1, 'kind': 'port',
         'sample': '%d samples x %d RK3 steps, N=%d, scipy solve_ivp(RK23, max_step=dt) on the oracle port, '
                   '1 process, BLAS limited to 1 thread, %.1f s' % (samples, rk_cpu, n, elapsed)}
-  print(json.dumps(line))
+  emit(line)
   if world > 1:
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+  """Print the one JSON line on the real stdout (see main: fd 1 is pointed at stderr while
+  libraries such as NCCL chat)."""
+  data = (json.dumps(line) + '\n').encode()
+  if _RESULT_FD is None:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_RESULT_FD, data)
+
+
 def main():
+  global _RESULT_FD
+  # keep stdout for the single JSON line: NCCL prints its version banner on fd 1
+  sys.stdout.flush()
+  _RESULT_FD = os.dup(1)
+  os.dup2(2, 1)
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=10)
