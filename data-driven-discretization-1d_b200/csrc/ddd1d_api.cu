@@ -49,6 +49,8 @@ struct ddd1d_handle {
   float* d_blob = nullptr;
   float* d_fparams = nullptr;
   float* d_fbasis = nullptr;
+  double* d_fparams64 = nullptr;
+  double* d_fbasis64 = nullptr;
   int forcing_batch = 0, forcing_P = 0, forcing_M = 0;
   int threads = 0, blocks_per_sm = 0, num_sms = 0;
   long long launches = 0;
@@ -309,7 +311,8 @@ int finalize(ddd1d_handle* h) {
     P.fast_conv = (K == 5 && (N % 4) == 0 && N >= 4) ? 1 : 0;
     if (getenv("DDD1D_FORCE_GENERIC_CONV")) P.fast_conv = 0;
     P.pitch = align_up(N + K - 1, 4);
-    h->threads = P.fast_conv ? std::min(512, 128 * ((N + 255) / 256)) : 256;
+    // one thread per position (4x8 register tiles, 16 warps/SM at N=256: +12 % over 8x8 tiles on 8 warps)
+    h->threads = P.fast_conv ? std::min(512, std::max(128, align_up(N, 128))) : 256;
     if (P.fast_conv && getenv("DDD1D_FFMA_THREADS")) h->threads = std::max(64, std::min(512, atoi(getenv("DDD1D_FFMA_THREADS")) / 32 * 32));
     const int nwarps = h->threads / 32;
     int cin = 1;
@@ -396,6 +399,7 @@ int finalize(ddd1d_handle* h) {
   P.sigma = (float)c.standard_deviation;
   P.eta = (float)c.eta;
   P.inv_dx = (float)(1.0 / c.dx);
+  P.inv_dx_d = 1.0 / c.dx;
   P.blob_floats = (int)blob.size();
 
   // shared-memory carve-up
@@ -409,6 +413,14 @@ int finalize(ddd1d_handle* h) {
   P.off_k = off; off += align_up(kMaxStages * N * 4, 16);
   P.off_flux = off; off += align_up((N + 1) * 4, 16);
   P.off_fs = off; off += (2 * kMaxModes + 3 * kMaxForcing) * 4;
+  P.off_ustd = P.off_kd = P.off_fluxd = P.off_fsd = off;
+  if (c.mode == DDD1D_MODE_WENO && c.weno_real == DDD1D_REAL_F64) {
+    off = align_up(off, 16);
+    P.off_ustd = off; off += align_up((N + 2 * kHalo) * 8, 16);
+    P.off_kd = off; off += kMaxStages * N * 8;
+    P.off_fluxd = off; off += align_up((N + 1) * 8, 16);
+    P.off_fsd = off; off += (2 * kMaxModes + 3 * kMaxForcing) * 8;
+  }
   P.off_act0 = off;
   P.off_act1 = off;
   if (c.mode == DDD1D_MODE_LEARNED) {
@@ -430,6 +442,8 @@ int finalize(ddd1d_handle* h) {
   P.blob = h->d_blob;
   P.fparams = h->d_fparams;
   P.fbasis = h->d_fbasis;
+  P.fparams64 = h->d_fparams64;
+  P.fbasis64 = h->d_fbasis64;
   P.P = h->forcing_batch > 0 ? h->forcing_P : 0;
   P.M = h->forcing_M;
   P.fcap = h->forcing_batch;
@@ -438,9 +452,11 @@ int finalize(ddd1d_handle* h) {
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
   h->num_sms = prop.multiProcessorCount;
-  const void* fn = c.mode == DDD1D_MODE_LEARNED  ? (const void*)row_kernel<MODE_LEARNED>
-                   : c.mode == DDD1D_MODE_WENO   ? (const void*)row_kernel<MODE_WENO>
-                                                 : (const void*)row_kernel<MODE_STENCIL>;
+  const bool weno64 = c.mode == DDD1D_MODE_WENO && c.weno_real == DDD1D_REAL_F64;
+  const void* fn = c.mode == DDD1D_MODE_LEARNED  ? (const void*)row_kernel<MODE_LEARNED, float>
+                   : weno64                      ? (const void*)row_kernel<MODE_WENO, double>
+                   : c.mode == DDD1D_MODE_WENO   ? (const void*)row_kernel<MODE_WENO, float>
+                                                 : (const void*)row_kernel<MODE_STENCIL, float>;
   CUDA_TRY(h, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, h->threads, P.smem_bytes));
@@ -476,11 +492,13 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
   }
   const int grid = std::min(W.batch, h->num_sms * h->blocks_per_sm);
   if (c.mode == DDD1D_MODE_LEARNED)
-    row_kernel<MODE_LEARNED><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+    row_kernel<MODE_LEARNED, float><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+  else if (c.mode == DDD1D_MODE_WENO && c.weno_real == DDD1D_REAL_F64)
+    row_kernel<MODE_WENO, double><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
   else if (c.mode == DDD1D_MODE_WENO)
-    row_kernel<MODE_WENO><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+    row_kernel<MODE_WENO, float><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
   else
-    row_kernel<MODE_STENCIL><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
+    row_kernel<MODE_STENCIL, float><<<grid, h->threads, P.smem_bytes, st>>>(P, W);
   CUDA_TRY(h, cudaGetLastError());
   h->launches += 1;
   return DDD1D_OK;
@@ -530,9 +548,8 @@ int ddd1d_create(const ddd1d_config* config, ddd1d_handle** out) {
   if (!(c.dx > 0)) return fail(nullptr, DDD1D_EINVAL, "dx must be positive");
   if (c.mode == DDD1D_MODE_WENO && c.variant != DDD1D_GODUNOV)
     return fail(nullptr, DDD1D_EINVAL, "WENO mode needs a Godunov-flux equation (integrate.py:320-321)");
-  if (c.mode == DDD1D_MODE_WENO && c.weno_real != DDD1D_REAL_F32)
-    return fail(nullptr, DDD1D_EUNSUPPORTED, "float64 WENO inside the row kernel is not built yet; "
-                "use ddd1d_weno_reconstruct for float64 reconstructions");
+  if (c.weno_real != DDD1D_REAL_F32 && c.weno_real != DDD1D_REAL_F64)
+    return fail(nullptr, DDD1D_EINVAL, "unknown weno_real %d", c.weno_real);
   if (c.mode == DDD1D_MODE_LEARNED) {
     if (c.num_layers < 1 || c.num_layers > kMaxLayers)
       return fail(nullptr, c.num_layers == 0 ? DDD1D_EUNSUPPORTED : DDD1D_EINVAL,
@@ -568,6 +585,8 @@ int ddd1d_destroy(ddd1d_handle* h) {
   cudaFree(h->d_blob_tc);
   cudaFree(h->d_fparams);
   cudaFree(h->d_fbasis);
+  cudaFree(h->d_fparams64);
+  cudaFree(h->d_fbasis64);
   cudaFree(h->d_stage_in);
   cudaFree(h->d_stage_out);
   cudaFree(h->d_stage_bad);
@@ -624,6 +643,8 @@ int ddd1d_set_forcing(ddd1d_handle* h, const double* a, const double* omega, con
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if (h->d_fparams) { CUDA_TRY(h, cudaFree(h->d_fparams)); h->d_fparams = nullptr; }
   if (h->d_fbasis) { CUDA_TRY(h, cudaFree(h->d_fbasis)); h->d_fbasis = nullptr; }
+  if (h->d_fparams64) { CUDA_TRY(h, cudaFree(h->d_fparams64)); h->d_fparams64 = nullptr; }
+  if (h->d_fbasis64) { CUDA_TRY(h, cudaFree(h->d_fbasis64)); h->d_fbasis64 = nullptr; }
   h->forcing_batch = 0; h->forcing_P = 0; h->forcing_M = 0;
   h->dirty = true;
   if (batch == 0) return DDD1D_OK;
@@ -641,16 +662,18 @@ int ddd1d_set_forcing(ddd1d_handle* h, const double* a, const double* omega, con
     return fail(h, DDD1D_EUNSUPPORTED, "up to %d forcing terms per sample supported, got %d", kMaxForcing, nparams);
   if (M == 0) M = 1;
   std::vector<float> fp((size_t)batch * 4 * P);
+  std::vector<double> fp64((size_t)batch * 4 * P);
   for (int b = 0; b < batch; ++b)
     for (int q = 0; q < P; ++q) {
       size_t s = (size_t)b * P + q, base = (size_t)b * 4 * P;
-      fp[base + q] = (float)a[s];
-      fp[base + P + q] = (float)omega[s];
-      fp[base + 2 * P + q] = (float)phi[s];
-      fp[base + 3 * P + q] = (float)k[s];
+      fp[base + q] = (float)(fp64[base + q] = a[s]);
+      fp[base + P + q] = (float)(fp64[base + P + q] = omega[s]);
+      fp[base + 2 * P + q] = (float)(fp64[base + 2 * P + q] = phi[s]);
+      fp[base + 3 * P + q] = (float)(fp64[base + 3 * P + q] = k[s]);
     }
   // basis on the reference grid, resampled like Grid.resample (equations.py:65-68)
   std::vector<float> basis((size_t)2 * M * N);
+  std::vector<double> basis64((size_t)2 * M * N);
   const int Nref = N * resample_factor;
   const double two_pi = 6.283185307179586476925286766559;
   for (int m = 1; m <= M; ++m)
@@ -663,13 +686,17 @@ int ddd1d_set_forcing(ddd1d_handle* h, const double* a, const double* omega, con
         cs += std::cos(th);
         sn += std::sin(th);
       }
-      basis[(size_t)(m - 1) * N + x] = (float)(cs / count);
-      basis[(size_t)(M + m - 1) * N + x] = (float)(sn / count);
+      basis[(size_t)(m - 1) * N + x] = (float)(basis64[(size_t)(m - 1) * N + x] = cs / count);
+      basis[(size_t)(M + m - 1) * N + x] = (float)(basis64[(size_t)(M + m - 1) * N + x] = sn / count);
     }
   CUDA_TRY(h, cudaMalloc(&h->d_fparams, fp.size() * sizeof(float)));
   CUDA_TRY(h, cudaMemcpy(h->d_fparams, fp.data(), fp.size() * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMalloc(&h->d_fbasis, basis.size() * sizeof(float)));
   CUDA_TRY(h, cudaMemcpy(h->d_fbasis, basis.data(), basis.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMalloc(&h->d_fparams64, fp64.size() * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpy(h->d_fparams64, fp64.data(), fp64.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMalloc(&h->d_fbasis64, basis64.size() * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpy(h->d_fbasis64, basis64.data(), basis64.size() * sizeof(double), cudaMemcpyHostToDevice));
   h->forcing_batch = batch; h->forcing_P = P; h->forcing_M = M;
   return DDD1D_OK;
 }

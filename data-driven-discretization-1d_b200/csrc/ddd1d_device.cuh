@@ -44,6 +44,7 @@ struct LayerPlan {
 struct Params {
   int eq, mode, N, D, S, wshift, weno_real;
   float sigma, eta, inv_dx;
+  double inv_dx_d;          // 1 / dx in float64 (float64 WENO path)
   // conv net
   int nlayers, K, kleft, fast_conv, pitch;
   LayerPlan layer[kMaxLayers];
@@ -56,8 +57,11 @@ struct Params {
   int P, M, fcap;
   const float* fparams;     // [fcap][4][P]: a, omega, phi, signed k
   const float* fbasis;      // [2M][N]: resampled cos(2 pi m x/L), sin(2 pi m x/L), m = 1..M
+  const double* fparams64;  // float64 copies for the float64 WENO path (integrate.py:124-140)
+  const double* fbasis64;
   // shared memory carve-up (byte offsets)
   int off_bar, off_blob, off_ust, off_ydbl, off_ynew, off_red, off_k, off_flux, off_fs, off_act0, off_act1;
+  int off_ustd, off_kd, off_fluxd, off_fsd;   // float64 twins (float64 WENO path only)
   int smem_bytes;
   int use_bulk_copy;
   // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
@@ -392,6 +396,10 @@ struct Smem {
   float* fs;      // [2*kMaxModes] mode amplitudes | [2*kMaxForcing] per-term sin/cos parts | [kMaxForcing] |k|
   float* act0;
   float* act1;
+  double* ustd;   // float64 stage row (halo 3), float64 WENO path
+  double* kd;     // float64 stage slopes
+  double* fluxd;
+  double* fsd;    // float64 forcing scratch, same layout as fs
 };
 
 __device__ __forceinline__ Smem carve(const Params& P, unsigned char* base) {
@@ -407,8 +415,16 @@ __device__ __forceinline__ Smem carve(const Params& P, unsigned char* base) {
   s.fs = reinterpret_cast<float*>(base + P.off_fs);
   s.act0 = reinterpret_cast<float*>(base + P.off_act0);
   s.act1 = reinterpret_cast<float*>(base + P.off_act1);
+  s.ustd = reinterpret_cast<double*>(base + P.off_ustd);
+  s.kd = reinterpret_cast<double*>(base + P.off_kd);
+  s.fluxd = reinterpret_cast<double*>(base + P.off_fluxd);
+  s.fsd = reinterpret_cast<double*>(base + P.off_fsd);
   return s;
 }
+
+template <typename KT> __device__ __forceinline__ KT* slopes(const Smem& S);
+template <> __device__ __forceinline__ float* slopes<float>(const Smem& S) { return S.k; }
+template <> __device__ __forceinline__ double* slopes<double>(const Smem& S) { return S.kd; }
 
 // stage row <- float(value) with its periodic halo; value(p) is evaluated per thread.  In learned
 // mode the same pass writes the net input u / standard_deviation (model.py:450-451) as channel 0 of
@@ -418,12 +434,19 @@ __device__ __forceinline__ void write_stage_row(const Params& P, const Smem& S, 
   const int N = P.N;
   const bool learned = P.mode == MODE_LEARNED;
   const int kl = P.kleft, kr = P.K - 1 - P.kleft;
+  const bool f64 = P.mode == MODE_WENO && P.weno_real == 1;
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
-    float v = value(p);
+    const double vd = value(p);
+    const float v = (float)vd;         // the float32 placeholder feed (integrate.py:57-60,71)
     S.ust[p + kHalo] = v;
     // wrapped copies (also correct when N < kHalo: every halo slot is assigned by some p)
     for (int q = p - N; q >= -kHalo; q -= N) S.ust[q + kHalo] = v;
     for (int q = p + N; q < N + kHalo; q += N) S.ust[q + kHalo] = v;
+    if (f64) {                         // the float64 row the NumPy WENO code sees (integrate.py:137-138)
+      S.ustd[p + kHalo] = vd;
+      for (int q = p - N; q >= -kHalo; q -= N) S.ustd[q + kHalo] = vd;
+      for (int q = p + N; q < N + kHalo; q += N) S.ustd[q + kHalo] = vd;
+    }
     if (learned) {
       const float vn = __fdiv_rn(v, P.sigma);
       S.act0[p + kl] = vn;
@@ -664,6 +687,74 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
 }
 
 
+
+// float64 twin of the WENO right-hand side (WENODifferentiator.__call__, integrate.py:133-140):
+// u_minus / u_plus reconstructed from the float64 row, the remaining derivatives from the float32
+// stencils (a TF float32 graph in the reference, integrate.py:104-105,134), Godunov flux, flux
+// difference and forcing in float64 (NumPy semantics: python-scalar * float32 array stays float32).
+__device__ __noinline__ void row_rhs_weno_f64(const Params& P, int sample, double t, int kslot) {
+  const Smem S = carve(P, dyn_smem);
+  const int N = P.N;
+  double* kout = S.kd + kslot * N;
+  const bool forced = eq_forced(P.eq) && P.P > 0;
+  if (forced && threadIdx.x < P.P) {
+    const double* fp = P.fparams64 + (size_t)sample * 4 * P.P;
+    const int q = threadIdx.x;
+    double sn, cs;
+    sincos(fp[P.P + q] * t + fp[2 * P.P + q], &sn, &cs);
+    double* parts = S.fsd + 2 * kMaxModes;
+    const double a = fp[q], kk = fp[3 * P.P + q];
+    parts[q] = a * sn;
+    parts[kMaxForcing + q] = (kk < 0.0 ? -a : a) * cs;
+    parts[2 * kMaxForcing + q] = fabs(kk);
+  }
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    float dv[kMaxD];
+    point_derivatives<MODE_STENCIL>(P, S, nullptr, p, dv, nullptr);     // float32 stencil channels
+    double um, up;
+    weno_pair<double>(S.ustd + p + kHalo, um, up);
+    const double g = godunov_flux<double>(um, up);
+    double flux;
+    if (P.eq == EQ_BURGERS_GOD) flux = g - (double)__fmul_rn(P.eta, dv[2]);
+    else if (P.eq == EQ_KDV_GOD) flux = 6.0 * g + (double)dv[2];
+    else flux = (double)__fadd_rn(dv[3], dv[2]) + g;
+    S.fluxd[p] = flux;
+  }
+  __syncthreads();
+  if (forced && threadIdx.x < 2 * P.M) {
+    const int j = threadIdx.x;
+    const double* parts = S.fsd + 2 * kMaxModes;
+    const double m = (double)((j < P.M ? j : j - P.M) + 1);
+    const double* src = parts + (j < P.M ? 0 : kMaxForcing);
+    double acc = 0.0;
+    for (int q = 0; q < P.P; ++q)
+      if (parts[2 * kMaxForcing + q] == m) acc += src[q];
+    S.fsd[j] = acc;
+  }
+  if (forced) __syncthreads();
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    const double fwd = S.fluxd[p + 1 == N ? 0 : p + 1];
+    double r = -(P.inv_dx_d * (fwd - S.fluxd[p]));
+    if (forced) {
+      double f = 0.0;
+      for (int m = 0; m < P.M; ++m) {
+        f += S.fsd[m] * P.fbasis64[(size_t)m * N + p];
+        f += S.fsd[P.M + m] * P.fbasis64[(size_t)(P.M + m) * N + p];
+      }
+      r += f;
+    }
+    kout[p] = r;
+  }
+  __syncthreads();
+}
+
+// One RHS evaluation into slope slot `kslot`: float32 graph (KT = float) or the float64 WENO twin.
+template <int MODE, typename KT>
+__device__ __forceinline__ void eval_rhs(const Params& P, const ForcingTerm& fterm, int sample, double t, int kslot) {
+  if (sizeof(KT) == sizeof(double)) row_rhs_weno_f64(P, sample, t, kslot);
+  else row_rhs<MODE>(P, fterm, (float)t, kslot, OP_RHS, nullptr);
+}
+
 // ---------------------------------------------------------------------------------
 // Adaptive Bogacki-Shampine 3(2): a per-row twin of scipy.integrate.solve_ivp(method='RK23',
 // rtol, atol, max_step, t_eval) as driven by integrate.odeint (integrate.py:143-169), following
@@ -688,23 +779,24 @@ __device__ __forceinline__ double block_sum(const Smem& S, double v) {
   return S.red[32];
 }
 
-template <int MODE>
-__device__ void row_adaptive(const Params& P, const Smem& S, const Work& W, int row, const ForcingTerm& fterm) {
+template <int MODE, typename KT>
+__device__ void row_adaptive(const Params& P, const Smem& S, const Work& W, int row, int sample,
+                             const ForcingTerm& fterm) {
   const int N = P.N;
   const double t_start = W.times[0], t_bound = W.times[W.ntimes - 1];
   const double rtol = W.rtol, atol = W.atol, max_step = W.max_step;
   const double inv_sqrt_n = 1.0 / sqrt((double)N);
-  float* K0 = S.k;
-  float* K1 = S.k + N;
-  float* K2 = S.k + 2 * N;
-  float* K3 = S.k + 3 * N;
+  KT* K0 = slopes<KT>(S);
+  KT* K1 = K0 + N;
+  KT* K2 = K0 + 2 * N;
+  KT* K3 = K0 + 3 * N;
   int nfev = 0, status = 0, next_out = 0;
   double t = t_start;
 
   // f0 = fun(t0, y0)
-  write_stage_row(P, S, [&](int p) { return (float)S.ydbl[p]; });
+  write_stage_row(P, S, [&](int p) { return S.ydbl[p]; });
   __syncthreads();
-  row_rhs<MODE>(P, fterm, (float)t, 0, OP_RHS, nullptr);
+  eval_rhs<MODE, KT>(P, fterm, sample, t, 0);
   nfev++;
 
   // select_initial_step (common.py)
@@ -722,9 +814,9 @@ __device__ void row_adaptive(const Params& P, const Smem& S, const Work& W, int 
     const double d1 = sqrt(block_sum(S, s1)) * inv_sqrt_n;
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     h0 = fmin(h0, interval);
-    write_stage_row(P, S, [&](int p) { return (float)(S.ydbl[p] + h0 * (double)K0[p]); });
+    write_stage_row(P, S, [&](int p) { return S.ydbl[p] + h0 * (double)K0[p]; });
     __syncthreads();
-    row_rhs<MODE>(P, fterm, (float)(t + h0), 1, OP_RHS, nullptr);
+    eval_rhs<MODE, KT>(P, fterm, sample, t + h0, 1);
     nfev++;
     double s2 = 0.0;
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
@@ -760,18 +852,18 @@ __device__ void row_adaptive(const Params& P, const Smem& S, const Work& W, int 
       h = t_new - t;
       h_abs = fabs(h);
       // rk_step (rk.py): K0 = f (FSAL), two inner stages, y_new, f_new
-      write_stage_row(P, S, [&](int p) { return (float)(S.ydbl[p] + (0.5 * (double)K0[p]) * h); });
+      write_stage_row(P, S, [&](int p) { return S.ydbl[p] + (0.5 * (double)K0[p]) * h; });
       __syncthreads();
-      row_rhs<MODE>(P, fterm, (float)(t + 0.5 * h), 1, OP_RHS, nullptr);
-      write_stage_row(P, S, [&](int p) { return (float)(S.ydbl[p] + (0.75 * (double)K1[p]) * h); });
+      eval_rhs<MODE, KT>(P, fterm, sample, t + 0.5 * h, 1);
+      write_stage_row(P, S, [&](int p) { return S.ydbl[p] + (0.75 * (double)K1[p]) * h; });
       __syncthreads();
-      row_rhs<MODE>(P, fterm, (float)(t + 0.75 * h), 2, OP_RHS, nullptr);
+      eval_rhs<MODE, KT>(P, fterm, sample, t + 0.75 * h, 2);
       for (int p = threadIdx.x; p < N; p += blockDim.x)
         S.ynew[p] = S.ydbl[p] + h * ((2.0 / 9.0) * (double)K0[p] + (1.0 / 3.0) * (double)K1[p] +
                                      (4.0 / 9.0) * (double)K2[p]);
-      write_stage_row(P, S, [&](int p) { return (float)S.ynew[p]; });
+      write_stage_row(P, S, [&](int p) { return S.ynew[p]; });
       __syncthreads();
-      row_rhs<MODE>(P, fterm, (float)(t + h), 3, OP_RHS, nullptr);
+      eval_rhs<MODE, KT>(P, fterm, sample, t + h, 3);
       nfev += 3;
       double se = 0.0;
       for (int p = threadIdx.x; p < N; p += blockDim.x) {
@@ -830,11 +922,12 @@ __device__ void row_adaptive(const Params& P, const Smem& S, const Work& W, int 
 // ---------------------------------------------------------------------------------
 // The persistent row kernel
 // ---------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, typename KT>
 __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
     row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
   const Smem S = carve(P, dyn_smem);
   const int N = P.N;
+  KT* const K = slopes<KT>(S);
 
   // ---- stage the constant blob (filters, biases, window tables) once per CTA ----
   if (P.blob_floats > 0) {
@@ -878,21 +971,22 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
     __syncthreads();
 
     if (W.op == OP_ADAPTIVE) {
-      row_adaptive<MODE>(P, S, W, row, fterm);
+      row_adaptive<MODE, KT>(P, S, W, row, sample, fterm);
       continue;
     }
     if (W.op != OP_INTEGRATE) {
-      write_stage_row(P, S, [&](int p) { return (float)S.ydbl[p]; });
+      write_stage_row(P, S, [&](int p) { return S.ydbl[p]; });
       __syncthreads();
       float* gout = nullptr;
       if (W.op == OP_COEF) gout = W.out + (size_t)row * N * P.D * P.S;
       if (W.op == OP_DERIV) gout = W.out + (size_t)row * N * P.D;
-      row_rhs<MODE>(P, fterm, (float)W.t0, 0, W.op, gout);
+      if (W.op == OP_RHS) eval_rhs<MODE, KT>(P, fterm, sample, W.t0, 0);
+      else row_rhs<MODE>(P, fterm, (float)W.t0, 0, W.op, gout);
       if (W.op == OP_RHS) {
         if (W.out64) {
-          for (int p = threadIdx.x; p < N; p += blockDim.x) W.out64[(size_t)row * N + p] = (double)S.k[p];
+          for (int p = threadIdx.x; p < N; p += blockDim.x) W.out64[(size_t)row * N + p] = (double)K[p];
         } else {
-          for (int p = threadIdx.x; p < N; p += blockDim.x) W.out[(size_t)row * N + p] = S.k[p];
+          for (int p = threadIdx.x; p < N; p += blockDim.x) W.out[(size_t)row * N + p] = (float)K[p];
         }
       }
       __syncthreads();
@@ -911,11 +1005,11 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
           double acc = 0.0;
 #pragma unroll
           for (int j = 0; j < kMaxStages; ++j)
-            if (j < s && tab.a[s][j] != 0.0) acc += tab.a[s][j] * (double)S.k[j * N + p];
-          return (float)(s == 0 ? S.ydbl[p] : S.ydbl[p] + W.dt * acc);
+            if (j < s && tab.a[s][j] != 0.0) acc += tab.a[s][j] * (double)K[j * N + p];
+          return s == 0 ? S.ydbl[p] : S.ydbl[p] + W.dt * acc;
         });
         __syncthreads();
-        row_rhs<MODE>(P, fterm, (float)(t + tab.c[s] * W.dt), s, OP_RHS, nullptr);
+        eval_rhs<MODE, KT>(P, fterm, sample, t + tab.c[s] * W.dt, s);
       }
       const bool save = ((step + 1) % W.save_every) == 0;
       float* snap = save ? W.snaps + ((size_t)save_idx * W.batch + row) * N : nullptr;
@@ -923,7 +1017,7 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < kMaxStages; ++j)
-          if (j < tab.stages && tab.b[j] != 0.0) acc += tab.b[j] * (double)S.k[j * N + p];
+          if (j < tab.stages && tab.b[j] != 0.0) acc += tab.b[j] * (double)K[j * N + p];
         double yn = S.ydbl[p] + W.dt * acc;
         S.ydbl[p] = yn;
         if (first_bad < 0 && !isfinite(yn)) first_bad = step;

@@ -147,13 +147,16 @@ class SpectralDifferentiator(Differentiator):
 
 
 class WENODifferentiator(Differentiator):
-  """5th-order WENO for Godunov-flux equations (integrate.py:124-140)."""
+  """5th-order WENO for Godunov-flux equations (integrate.py:124-140).  Like the reference, the
+  reconstruction, flux and forcing are float64 and only the non-WENO stencil is float32;
+  weno_real='float32' selects the all-float32 kernel (what model.baseline_space_derivatives does
+  in TF, model.py:81-97)."""
 
-  def __init__(self, equation, non_weno_accuracy_order=3):
+  def __init__(self, equation, non_weno_accuracy_order=3, weno_real='float64'):
     if equation.VARIANT != 'godunov':
       raise ValueError('invalid equation: {}'.format(equation))
     self.equation = equation
-    self.solver = runtime.weno_solver(equation, non_weno_accuracy_order)
+    self.solver = runtime.weno_solver(equation, non_weno_accuracy_order, weno_real=weno_real)
 
   def __call__(self, t, y):
     return self.solver.rhs_host(t, y)

@@ -99,12 +99,23 @@ def test_weno_against_reference_fixture(golden):
   eq = equations.GodunovBurgersEquation(32, random_seed=11)
   sd = model.baseline_space_derivatives(gb['burgers/godunov/32/exact/u'], eq, None)
   assert rel_err(cpu(sd), gb['burgers/godunov/32/exact/space_derivatives']) < 2e-5
-  # WENODifferentiator (integrate.py:124-140); the reference runs the reconstruction in
-  # float64, this build in float32 -> looser tolerance, stated
+  # WENODifferentiator (integrate.py:124-140): float64 reconstruction / flux / forcing with the
+  # float32 4-point stencil, as in the reference; and the all-float32 kernel at a looser tolerance
   gt = golden('trajectories')
   eqw = equations.GodunovBurgersEquation(64, random_seed=1)
   d = integrate.WENODifferentiator(eqw)
-  assert rel_err(d(0.4, gt['weno_burgers/rhs_u']), gt['weno_burgers/rhs']) < 2e-5
+  assert rel_err(d(0.4, gt['weno_burgers/rhs_u']), gt['weno_burgers/rhs']) < 3e-7
+  d32 = integrate.WENODifferentiator(eqw, weno_real='float32')
+  assert rel_err(d32(0.4, gt['weno_burgers/rhs_u']), gt['weno_burgers/rhs']) < 2e-5
+  # the reference's own consistency test (integrate_test.py:146-155): exact == weno
+  y, nfev = integrate.odeint(eqw.initial_value(), d, gt['weno_burgers/times'])
+  assert nfev == int(gt['weno_burgers/nfev'])
+  np.testing.assert_allclose(y, gt['weno_burgers/y'], rtol=0, atol=1e-6)
+  for kind in ('kdv', 'ks'):                       # Godunov KdV / KS through the same float64 path
+    eqk = equations.FLUX_EQUATION_TYPES[kind](64, random_seed=2)
+    oeq = G.oracle_equation(kind, 'godunov', 64, seed=2)
+    u = G.smooth_rows(1, 64, seed=3)[0].astype(np.float64)
+    assert rel_err(integrate.WENODifferentiator(eqk)(0.1, u), O.WENODifferentiator(oeq)(0.1, u)) < 3e-7
 
 
 # ---------------------------------------------------------------------------------
@@ -235,6 +246,9 @@ def test_device_adaptive_rk23_matches_scipy_fixtures(golden):
   y, nfev = integrate.BatchIntegrator.weno([eq]).odeint(times=g['weno_burgers/times'])
   assert nfev[0] == int(g['weno_burgers/nfev'])
   np.testing.assert_allclose(y[0], g['weno_burgers/y'], rtol=0, atol=5e-5)   # float32 WENO vs float64 reference
+  y, nfev = integrate.BatchIntegrator.weno([eq], weno_real='float64').odeint(times=g['weno_burgers/times'])
+  assert nfev[0] == int(g['weno_burgers/nfev'])
+  np.testing.assert_allclose(y[0], g['weno_burgers/y'], rtol=0, atol=1e-6)   # float64 WENO twin
 
 
 def test_device_adaptive_nan_padding_and_status():
