@@ -486,3 +486,54 @@ def test_host_buffer_entry_points():
   r = solver.rhs_host(0.3, u0.astype(np.float64))
   np.testing.assert_array_equal(r, cpu(solver.rhs(0.3, u0)).astype(np.float64))
   assert solver.launch_count() >= 3
+
+
+# ---------------------------------------------------------------------------------
+# the reference's integrate_test.py scenarios on the drop-in surface
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('kind,conservative,numerical_flux', (
+    ('burgers', False, False), ('burgers', True, False), ('burgers', True, True), ('kdv', True, False)))
+def test_integrate_exact_baseline_and_model(kind, conservative, numerical_flux):
+  """integrate_test.py:56-127 with explicit weights instead of an in-test training run:
+  dims, zero-mean exact solution, identical (resampled) initial conditions, and y_baseline
+  equal to a stand-alone integrate_baseline run."""
+  import json
+  from ddd1d_b200 import integrate, equations, training, duckarray, runtime
+  fine_points, factor = 128, 4
+  hp = training.create_hparams(kind, conservative=conservative, numerical_flux=numerical_flux,
+                               resample_factor=factor, num_layers=1, filter_size=32,
+                               equation_kwargs=json.dumps({'num_points': fine_points}))
+  _, coarse = equations.from_hparams(hp, random_seed=0)
+  shapes = runtime.expected_layer_shapes(coarse, hp)
+  rs = np.random.RandomState(0)
+  weights = [(1e-3 * rs.randn(*s).astype(np.float32), np.zeros(s[2], np.float32)) for s in shapes]
+  times = np.linspace(0, 0.02 if kind == 'kdv' else 0.2, 3)
+  ds = integrate.integrate_exact_baseline_and_model(weights, hparams=hp, random_seed=0, times=times)
+  y_exact, y_base, y_model = (np.asarray(ds[k].data) for k in ('y_exact', 'y_baseline', 'y_model'))
+  assert y_exact.shape == (3, fine_points) and y_base.shape == (3, fine_points // factor) == y_model.shape
+  assert abs(y_exact.mean(axis=1)).max() < 1e-3
+  resample = duckarray.resample_mean if conservative else duckarray.subsample
+  np.testing.assert_allclose(resample(y_exact[0], factor), y_base[0])
+  np.testing.assert_allclose(resample(y_exact[0], factor), y_model[0])
+  assert np.isfinite(y_model).all()
+  ds2 = integrate.integrate_baseline(type(coarse)(fine_points // factor, resample_factor=factor, random_seed=0),
+                                     times=times)
+  np.testing.assert_allclose(y_base, np.asarray(ds2['y'].data), atol=1e-5)
+
+
+def test_spectral_exact_and_warmup(golden):
+  """integrate_test.py:157-167 (exact == spectral for KdV) against the reference's own
+  SpectralDifferentiator trajectory, and the warm-up + resample branch of integrate()."""
+  from ddd1d_b200 import integrate, equations
+  g = golden('trajectories')
+  eq = equations.KdVEquation(64, random_seed=0)
+  exact = integrate.integrate_exact(eq, times=g['spectral_kdv/times'])
+  spectral = integrate.integrate_spectral(eq, times=g['spectral_kdv/times'])
+  np.testing.assert_allclose(np.asarray(exact['y'].data), np.asarray(spectral['y'].data), atol=1e-10)
+  np.testing.assert_allclose(np.asarray(exact['y'].data), g['spectral_kdv/y'], rtol=0, atol=1e-9)
+  coarse = equations.ConservativeKdVEquation(16, resample_factor=4, random_seed=0)
+  ds = integrate.integrate_baseline(coarse, times=np.linspace(0, 0.01, 3), warmup=0.01)
+  y = np.asarray(ds['y'].data)
+  assert y.shape == (3, 16) and np.isfinite(y).all()
+  np.testing.assert_allclose(np.asarray(ds['time'].data if hasattr(ds['time'], 'data') else ds['time']),
+                             0.01 + np.linspace(0, 0.01, 3))
