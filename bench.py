@@ -380,11 +380,17 @@ def run_ours(args):
          'algorithmic_bytes_per_launch': 8.0 * batch * n * rk,
          'note': 'rows stay on chip for all RK steps of a launch (ncu: DRAM traffic ~7% of the algorithmic '
                  'bytes), so HBM is idle by design; the binding resource is on-chip'}
+  traffic = None
+  tpath = os.path.join(ROOT, 'profiles', 'r01', 'traffic.json')
+  if os.path.exists(tpath) and args.workload == 'c2' and rk == 50 and batch == 4096:
+    with open(tpath) as f:
+      traffic = json.load(f).get(kernel_name, {}).get('dram_bytes_per_launch')   # ncu --set full, same launch shape
+  hbm['traffic'] = traffic
   achieved_tf = fl * gps_kernel / 1e12
   if engine == 'tensor':
     tf32_peak = peaks['bf16_tflops_sustained' if 'bf16_tflops_sustained' in peaks else 'bf16_tflops'] / 2.0
     roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / tf32_peak, 'traffic': None, 'peak_kind': peak_kind,
+                'frac': achieved_tf / tf32_peak, 'traffic': traffic, 'peak_kind': peak_kind,
                 'note': 'achieved = algorithmic FP32-equivalent FLOPs (%d per grid-point-step); peak = dense TF32 = '
                         'half of the measured sustained bf16 cuBLAS rate.  The 3xTF32 split executes 3x the conv '
                         'FLOPs on the tensor pipe, and each M128xN32xK8 MMA reads ~5 KB of shared-memory operands '
