@@ -77,6 +77,7 @@ _SIGNATURES = {
 # test-only entry points (include/ddd1d_debug.h)
 _DEBUG_SIGNATURES = {
     'ddd1d_debug_tc_probe': (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_int, _P]),
+    'ddd1d_debug_tc_rate': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
 }
 
 

@@ -523,6 +523,18 @@ int ensure_stage(ddd1d_handle* h, void** buf, size_t* have, size_t need) {
 
 }  // namespace
 
+namespace {
+template <int KIND, int N1, int N2, int BROWS, int ALT>
+int run_rate(int reps, int blocks, long long* d) {
+  const int smem = 128 + 2 * tc::kChunks * 516 * 16 + tc::kTaps * tc::kChunks * BROWS * 16;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT><<<blocks, 128, smem>>>(reps, d);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int ddd1d_version(void) { return DDD1D_VERSION; }
@@ -849,6 +861,36 @@ int ddd1d_weno_reconstruct(int device, int real, const void* u, void* left, void
     return fail(nullptr, DDD1D_EINVAL, "unknown real type %d", real);
   }
   CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+
+// variant: index into a fixed table of compile-time MMA patterns (scripts/tc_rate.py lists them)
+int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long* cycles_host) {
+  if (reps < 1 || blocks < 1 || !cycles_host) return fail(nullptr, DDD1D_EINVAL, "bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  long long* d = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * sizeof(long long)));
+  int rc = DDD1D_EINVAL;
+  switch (variant) {
+    case 0: rc = run_rate<0, 16, 0, 16, 1>(reps, blocks, d); break;
+    case 1: rc = run_rate<0, 32, 0, 32, 1>(reps, blocks, d); break;
+    case 2: rc = run_rate<0, 64, 0, 64, 1>(reps, blocks, d); break;
+    case 3: rc = run_rate<0, 128, 0, 128, 1>(reps, blocks, d); break;
+    case 4: rc = run_rate<0, 32, 0, 64, 1>(reps, blocks, d); break;    // N=32 out of a 64-row plane
+    case 5: rc = run_rate<0, 32, 0, 32, 0>(reps, blocks, d); break;    // single accumulator
+    case 6: rc = run_rate<0, 64, 32, 64, 1>(reps, blocks, d); break;   // production hidden layer
+    case 7: rc = run_rate<0, 32, 16, 32, 1>(reps, blocks, d); break;   // production last layer
+    case 8: rc = run_rate<0, 32, 32, 32, 1>(reps, blocks, d); break;
+    case 9: rc = run_rate<1, 32, 0, 32, 1>(reps, blocks, d); break;    // bf16 K=16
+    case 10: rc = run_rate<1, 64, 0, 64, 1>(reps, blocks, d); break;
+    case 11: rc = run_rate<1, 96, 0, 96, 1>(reps, blocks, d); break;
+    case 12: rc = run_rate<1, 96, 64, 96, 1>(reps, blocks, d); break;  // bf16x3 first two of a step
+    case 13: rc = run_rate<1, 128, 0, 128, 1>(reps, blocks, d); break;
+    default: return fail(nullptr, DDD1D_EINVAL, "unknown variant");
+  }
+  if (rc) return rc;
+  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
   return DDD1D_OK;
 }
 

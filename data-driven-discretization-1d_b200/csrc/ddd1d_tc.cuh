@@ -644,5 +644,94 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
   if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
+// ------------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark (debug): one warp issues reps x 20 (tap, ci-block) steps on planes of
+// arbitrary data; the CTA measures the clocks until tcgen05.commit fires.  Per step up to two MMAs:
+//   first : A = plane set 0, N = n1, D columns at d_off1 (+ 128 * (k & 1) when alt != 0)
+//   second: A = plane set `a2`, N = n2, D columns at d_off2 (same alternation)
+// n == 0 skips that MMA.  kind 0 = tf32 (K = 8, 4-byte elements), 1 = bf16 (kind::f16, K = 16).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t instr_desc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int KIND, int N1, int N2, int BROWS, int ALT>
+__global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, long long* __restrict__ cycles) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t plane_bytes = 516u * 16u;
+  constexpr uint32_t b_plane_bytes = (uint32_t)BROWS * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned char* a_0 = smem_raw + 128;
+  unsigned char* a_1 = a_0 + kChunks * plane_bytes;
+  unsigned char* b_cat = a_1 + kChunks * plane_bytes;
+  for (uint32_t i = tid; i < (2 * kChunks * plane_bytes + kTaps * kChunks * b_plane_bytes) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(a_0)[i] = 0x3c003c00u + (i & 63u);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  long long t0 = 0;
+  if (warp == 0) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
+    const uint32_t a00 = ((smem_u32(a_0) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t a10 = ((smem_u32(a_1) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t b0 = ((smem_u32(b_cat) >> 4) & 0x3FFFu) | (bplane16 << 16);
+    const uint32_t id1 = KIND ? instr_desc_bf16(128, N1 ? N1 : 16) : instr_desc_tf32(128, N1 ? N1 : 16);
+    const uint32_t id2 = KIND ? instr_desc_bf16(128, N2 ? N2 : 16) : instr_desc_tf32(128, N2 ? N2 : 16);
+    t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+#pragma unroll
+          for (int kb = 0; kb < kChunks / 2; ++kb) {
+            const uint32_t dsel = ALT ? (uint32_t)(k & 1) * 256u : 0u;
+            const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+            const uint32_t bo = (uint32_t)(k * kChunks + 2 * kb) * bplane16;
+            if (N1) {
+              if (KIND) mma_bf16_split(base_u + dsel, a00 + ao, b0 + bo, desc_hi, id1, 1u);
+              else mma_tf32_split(base_u + dsel, a00 + ao, b0 + bo, desc_hi, id1, 1u);
+            }
+            if (N2) {
+              if (KIND) mma_bf16_split(base_u + dsel + 128u, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+              else mma_tf32_split(base_u + dsel + 128u, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+    mbar_wait_guarded(bar, 0);
+    if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace tc
 }  // namespace ddd1d

@@ -11,6 +11,9 @@ extern "C" {
  *          weights, rows nout..2*nout-1 their TF32-rounded remainders
  *   out    device float [128][nout] */
 int ddd1d_debug_tc_probe(int device, const float* x, const float* w_cat, float* out, int nout, void* stream);
+/* MMA issue-rate microbenchmark: `blocks` CTAs each issue reps x 20 (tap, ci-block) steps of the
+ * tensor engine's MMA pattern (mode: see csrc/ddd1d_tc.cuh) and report the clocks until completion. */
+int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long* cycles_host);
 #ifdef __cplusplus
 }
 #endif
