@@ -14,6 +14,7 @@ PLAIN, CONSERVATIVE, GODUNOV = 0, 1, 2
 MODE_STENCIL, MODE_LEARNED, MODE_WENO = 0, 1, 2
 ACTIVATIONS = {None: 0, 'none': 0, 'relu': 1, 'relu6': 2, 'tanh': 3, 'softplus': 4, 'elu': 5}
 PROJ_NULLSPACE, PROJ_RAW, PROJ_RAW_UNBIASED = 0, 1, 2
+PROJ_DERIVATIVES, PROJ_TIME_DERIVATIVE, PROJ_FLUX = 3, 4, 5
 SCHEMES = {'rk3': 0, 'RK23': 0, 'bogacki_shampine': 0, 'midpoint': 1, 'euler': 2, 'rk4': 3}
 REAL_F32, REAL_F64 = 0, 1
 ENGINES = {'auto': 0, 'ffma': 1, 'tensor': 2}

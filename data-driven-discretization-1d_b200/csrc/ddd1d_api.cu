@@ -142,6 +142,7 @@ int finalize_tc(ddd1d_handle* h) {
   else if (c.kernel_size != 5 || c.filter_size != tc::kF) h->tc_why = "needs kernel_size 5 and filter_size 32";
   else if (c.num_layers < 2 || c.num_layers > 3) h->tc_why = "needs 2 or 3 conv layers";
   else if (c.activation != DDD1D_ACT_RELU) h->tc_why = "needs the relu nonlinearity";
+  else if (c.projection > DDD1D_PROJ_RAW_UNBIASED) h->tc_why = "only model_target='coefficients'";
   else if (N != 128 && N != 256 && N != 512) h->tc_why = "needs num_points in {128, 256, 512}";
   if (!h->tc_why.empty() || want == DDD1D_ENGINE_FFMA) {
     if (want == DDD1D_ENGINE_TENSOR)
@@ -236,7 +237,6 @@ int finalize_tc(ddd1d_handle* h) {
   P.blob_floats = (int)blob.size();
   P.tc_nlast = NL;
   P.tc_debug = getenv("DDD1D_TC_DEBUG") ? atoi(getenv("DDD1D_TC_DEBUG")) : 0;
-  P.tc_stagger_ns = getenv("DDD1D_TC_STAGGER_NS") ? atoi(getenv("DDD1D_TC_STAGGER_NS")) : 3000;
   // shared-memory plan: as many row teams as fit (at most 512 / N)
   const int plane = (N + 4) * 16;
   int t = 0;
@@ -372,9 +372,11 @@ int finalize(ddd1d_handle* h) {
         for (int j = 0; j < kWin; ++j)
           blob[P.ns_off + ch * kWinPad + j] = (float)h->nullspace[(size_t)ch * kWin + j];
     } else {
-      if (c.net_outputs != D * c.stencil_size)
-        return fail(h, DDD1D_EINVAL, "raw projection needs net_outputs == D*S (%d != %d*%d)",
-                    c.net_outputs, D, c.stencil_size);
+      const int want_out = c.projection == DDD1D_PROJ_DERIVATIVES ? D
+                           : c.projection >= DDD1D_PROJ_TIME_DERIVATIVE ? 1 : D * c.stencil_size;
+      if (c.net_outputs != want_out)
+        return fail(h, DDD1D_EINVAL, "projection %d needs net_outputs == %d, got %d", c.projection, want_out,
+                    c.net_outputs);
       P.ns_off = 0;
       for (int d = 0; d <= kMaxD; ++d) P.cstart[d] = 0;
     }
@@ -571,9 +573,9 @@ int ddd1d_create(const ddd1d_config* config, ddd1d_handle** out) {
     if (c.filter_size < 1 || c.net_outputs < 1) return fail(nullptr, DDD1D_EINVAL, "bad net widths");
     if (c.activation < 0 || c.activation > DDD1D_ACT_ELU)
       return fail(nullptr, DDD1D_EINVAL, "unknown activation %d", c.activation);
-    if (c.projection < 0 || c.projection > DDD1D_PROJ_RAW_UNBIASED)
+    if (c.projection < 0 || c.projection > DDD1D_PROJ_FLUX)
       return fail(nullptr, DDD1D_EINVAL, "unknown projection %d", c.projection);
-    if (c.stencil_size < 1 || c.stencil_size > kWin)
+    if (c.projection <= DDD1D_PROJ_RAW_UNBIASED && (c.stencil_size < 1 || c.stencil_size > kWin))
       return fail(nullptr, DDD1D_EUNSUPPORTED,
                   "coefficient grid of %d points exceeds the %d-point window", c.stencil_size, kWin);
     if (!(c.standard_deviation > 0)) return fail(nullptr, DDD1D_EINVAL, "standard_deviation must be positive");
@@ -738,6 +740,8 @@ int ddd1d_coefficients(ddd1d_handle* h, const float* u, float* coefficients, int
   if (batch == 0) return DDD1D_OK;
   if (!u || !coefficients) return fail(h, DDD1D_EINVAL, "null argument");
   if (h->cfg.mode != DDD1D_MODE_LEARNED) return fail(h, DDD1D_EINVAL, "handle has no conv net");
+  if (h->cfg.projection > DDD1D_PROJ_RAW_UNBIASED)
+    return fail(h, DDD1D_EINVAL, "this model_target predicts no coefficients");
   Work W = blank_work();
   W.op = OP_COEF; W.batch = batch; W.u = u; W.out = coefficients;
   return launch(h, W, stream);
@@ -747,6 +751,8 @@ int ddd1d_space_derivatives(ddd1d_handle* h, const float* u, float* derivatives,
   if (!h) return fail(h, DDD1D_EINVAL, "null handle");
   if (batch == 0) return DDD1D_OK;
   if (!u || !derivatives) return fail(h, DDD1D_EINVAL, "null argument");
+  if (h->cfg.mode == DDD1D_MODE_LEARNED && h->cfg.projection > DDD1D_PROJ_DERIVATIVES)
+    return fail(h, DDD1D_EINVAL, "this model_target predicts no space derivatives");
   Work W = blank_work();
   W.op = OP_DERIV; W.batch = batch; W.u = u; W.out = derivatives;
   return launch(h, W, stream);

@@ -26,7 +26,7 @@ constexpr int kMaxForcing = 32;  // forcing terms per sample (the reference uses
 enum Op { OP_RHS = 0, OP_COEF = 1, OP_DERIV = 2, OP_INTEGRATE = 3, OP_ADAPTIVE = 4 };
 enum Mode { MODE_STENCIL = 0, MODE_LEARNED = 1, MODE_WENO = 2 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_TANH = 3, ACT_SOFTPLUS = 4, ACT_ELU = 5 };
-enum Proj { PROJ_NULLSPACE = 0, PROJ_RAW = 1, PROJ_RAW_UNBIASED = 2 };
+enum Proj { PROJ_NULLSPACE = 0, PROJ_RAW = 1, PROJ_RAW_UNBIASED = 2, PROJ_DERIVS = 3, PROJ_TIME = 4, PROJ_FLUX = 5 };
 // eq code = equation * 3 + variant
 enum Eq {
   EQ_BURGERS = 0, EQ_BURGERS_CONS = 1, EQ_BURGERS_GOD = 2,
@@ -65,7 +65,7 @@ struct Params {
   int smem_bytes;
   int use_bulk_copy;
   // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
-  int tc_teams, tc_nlast, tc_stagger_ns, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
+  int tc_teams, tc_nlast, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
   int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
   int tc_t_act_hi, tc_t_act_lo, tc_t_ust, tc_t_k, tc_t_flux, tc_t_fs;      // byte offsets inside a team region
   int tc_w1_off, tc_b1_off, tc_bh_off, tc_bl_off;                          // float offsets into the blob
@@ -522,6 +522,11 @@ __device__ __forceinline__ void point_derivatives(const Params& P, const Smem& S
     dv[d] = 0.f;
     if (d >= P.D) continue;
     float cf[kWin];
+    if (MODE == MODE_LEARNED && P.projection >= PROJ_DERIVS) {
+      // model_target='space_derivatives': the net's channels ARE the derivatives (model.py:571-576)
+      dv[d] = (P.projection == PROJ_DERIVS) ? net[d * P.pitch + p + P.kleft] : 0.f;
+      continue;
+    }
     if (MODE == MODE_LEARNED) {
       if (P.projection == PROJ_NULLSPACE) {
         // coef = bias + z @ nullspace (polynomials.py:266-277), window-aligned on the host
@@ -653,7 +658,8 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
     __syncthreads();
   }
 
-  const bool cons = eq_conservative(P.eq);
+  const bool direct_flux = MODE == MODE_LEARNED && P.projection == PROJ_FLUX;
+  const bool cons = eq_conservative(P.eq) && !(MODE == MODE_LEARNED && P.projection == PROJ_TIME);
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
     float dv[kMaxD];
     float* gc = (op == OP_COEF) ? gout_row + (size_t)p * P.D * P.S : nullptr;
@@ -664,6 +670,17 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
         if (d < P.D) gout_row[(size_t)p * P.D + d] = dv[d];
     }
     if (op == OP_COEF || op == OP_DERIV) continue;
+    if (MODE == MODE_LEARNED && P.projection == PROJ_TIME) {
+      // model_target='time_derivative': the single channel is dy/dt (model.py:603-606)
+      float r = net[p + P.kleft];
+      if (forced) r = __fadd_rn(r, forcing_at(P, S, p));
+      kout[p] = r;
+      continue;
+    }
+    if (MODE == MODE_LEARNED && P.projection == PROJ_FLUX) {
+      S.flux[p] = net[p + P.kleft];      // model_target='flux' (model.py:609-615)
+      continue;
+    }
     float r = equation_point(P.eq, S.ust[p + kHalo], dv, P.eta);
     if (cons) {
       S.flux[p] = r;
@@ -673,12 +690,14 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
     }
   }
   if (op == OP_COEF || op == OP_DERIV) return;
-  if (cons) {
+  if (cons || direct_flux) {
     __syncthreads();
-    // y_t = -(1/dx) (flux[x+1] - flux[x])  (equations.py:305-320)
+    // y_t = -(1/dx) (flux[x+1] - flux[x])  (equations.py:305-320); predict_flux_directly returns
+    // +staggered_first_derivative(flux) without the minus sign (model.py:615)
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
       float fwd = S.flux[p + 1 == N ? 0 : p + 1];
-      float r = -__fmul_rn(P.inv_dx, __fsub_rn(fwd, S.flux[p]));
+      float r = __fmul_rn(P.inv_dx, __fsub_rn(fwd, S.flux[p]));
+      if (!direct_flux) r = -r;
       if (forced) r = __fadd_rn(r, forcing_at(P, S, p));
       kout[p] = r;
     }

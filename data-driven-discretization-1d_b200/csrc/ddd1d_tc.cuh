@@ -326,7 +326,6 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
   const uint32_t plane_bytes = (uint32_t)(N + 4) * 16u;
   const int NL = P.tc_nlast;                         // 16 or 32 columns for the last layer
   const int hidden_tc_layers = P.nlayers - 2;        // layers between the first and the last
-  const int requests_per_rhs = hidden_tc_layers + 1;
 
   Tableau* tab_s = reinterpret_cast<Tableau*>(smem_raw + P.tc_off_tab);
   if (tid == 0) {
@@ -354,8 +353,6 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_teams = gridDim.x * R;
-  const int stages_of = tab_s->stages;
-  const int rhs_per_row = (W.op == OP_INTEGRATE) ? W.nsteps * stages_of : 1;
 
   {
     // ---------------- row team ----------------

@@ -71,8 +71,8 @@ def apply_coefficients(coefficients, inputs):
 def predict_space_derivatives(inputs, hparams, weights=None, reuse=None):
   """[batch, x] -> [batch, x, derivative] (model.py:579-600)."""
   del reuse
-  if hparams.model_target != 'coefficients':
-    raise NotImplementedError('unrecognized or unbuilt model_target: {}'.format(hparams.model_target))
+  if hparams.model_target not in ('coefficients', 'space_derivatives'):
+    raise NotImplementedError('unrecognized model_target: {}'.format(hparams.model_target))   # model.py:599-600
   equation, solver = _learned(hparams, weights)
   assert_consistent_solution(equation, inputs)
   return solver.space_derivatives(inputs)
@@ -82,9 +82,7 @@ def predict_time_derivative(inputs, hparams, weights=None, reuse=None):
   """[batch, x] -> [batch, x], the equation of motion applied to the predicted
   derivatives, WITHOUT finalize_time_derivative (model.py:618-640)."""
   del reuse
-  if hparams.model_target != 'coefficients':
-    raise NotImplementedError('unrecognized or unbuilt model_target: {}'.format(hparams.model_target))
-  equation, solver = _learned(hparams, weights)
+  equation, solver = _learned(hparams, weights)      # every model_target (model.py:632-640)
   assert_consistent_solution(equation, inputs)
   return solver.rhs(0.0, inputs)
 

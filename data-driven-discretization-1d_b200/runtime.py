@@ -70,7 +70,14 @@ def accuracy_layers(equation, hparams):
 def expected_layer_shapes(equation, hparams):
   """[(kernel_size, cin, cout)] of the conv stack (model.py:455-458,464-467,492-495)."""
   grid_size = coefficient_grid(equation, hparams).size
-  if hparams.polynomial_accuracy_order:
+  target = getattr(hparams, 'model_target', 'coefficients')
+  if target == 'space_derivatives':                       # model.py:571-576
+    outputs = len(equation.DERIVATIVE_ORDERS)
+  elif target in ('time_derivative', 'flux'):             # model.py:603-615
+    outputs = 1
+  elif target != 'coefficients':
+    raise NotImplementedError('unrecognized model_target: {}'.format(target))
+  elif hparams.polynomial_accuracy_order:
     outputs = sum(layer.input_size for layer in accuracy_layers(equation, hparams))
   else:
     outputs = len(equation.DERIVATIVE_ORDERS) * grid_size
@@ -113,9 +120,6 @@ class RowSolver(object):
     cfg.engine = _lib.ENGINES[engine]
     layers = None
     if mode == _lib.MODE_LEARNED:
-      if hparams.model_target != 'coefficients':
-        raise NotImplementedError('model_target=%r is not built; only "coefficients" '
-                                  '(model.py:595-600)' % hparams.model_target)
       if hparams.num_layers == 0:
         raise NotImplementedError('num_layers=0 (a constant learned stencil) is not built')
       if hparams.nonlinearity not in _lib.ACTIVATIONS:
@@ -134,7 +138,12 @@ class RowSolver(object):
       cfg.activation = _lib.ACTIVATIONS[hparams.nonlinearity]
       cfg.net_outputs = shapes[-1][2]
       cfg.stencil_size = grid_size
-      if hparams.polynomial_accuracy_order:
+      target = getattr(hparams, 'model_target', 'coefficients')
+      if target != 'coefficients':
+        cfg.projection = {'space_derivatives': _lib.PROJ_DERIVATIVES,
+                          'time_derivative': _lib.PROJ_TIME_DERIVATIVE, 'flux': _lib.PROJ_FLUX}[target]
+        cfg.stencil_size = 1
+      elif hparams.polynomial_accuracy_order:
         cfg.projection = _lib.PROJ_NULLSPACE
         layers = accuracy_layers(eq, hparams)
       elif hparams.ensure_unbiased_coefficients:

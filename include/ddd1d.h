@@ -66,7 +66,11 @@ enum { DDD1D_ACT_NONE = 0, DDD1D_ACT_RELU = 1, DDD1D_ACT_RELU6 = 2, DDD1D_ACT_TA
 enum {
   DDD1D_PROJ_NULLSPACE = 0,   /* coef_d = bias_d + net[slice_d] @ nullspace_d  (polynomials.py:266-277) */
   DDD1D_PROJ_RAW = 1,         /* polynomial_accuracy_order == 0: coef = reshape(net, [D, S]) */
-  DDD1D_PROJ_RAW_UNBIASED = 2 /* ... minus the mean over the stencil (ensure_unbiased_coefficients) */
+  DDD1D_PROJ_RAW_UNBIASED = 2,/* ... minus the mean over the stencil (ensure_unbiased_coefficients) */
+  /* the other hparams.model_target values (model.py:551-640): no stencil is applied */
+  DDD1D_PROJ_DERIVATIVES = 3, /* 'space_derivatives': net_outputs == D, channels are the derivatives */
+  DDD1D_PROJ_TIME_DERIVATIVE = 4, /* 'time_derivative': net_outputs == 1, the channel is dy/dt */
+  DDD1D_PROJ_FLUX = 5         /* 'flux': net_outputs == 1, dy/dt = staggered_first_derivative(channel) */
 };
 
 /* explicit Runge-Kutta schemes for the fused fixed-step integrator */

@@ -14,12 +14,15 @@ Parity pinning (see DESIGN.md, section "Oracle"):
     fixtures in tests/golden/*.npz), and against the reference's known-answer
     tests (layers_test.py, polynomials_test.py, weno_test.py, equations_test.py,
     duckarray_test.py) which tests/test_oracle_kat.py re-expresses without TF;
-  * the TF-graph-only pieces (tf.layers.conv1d stack, extract_image_patches,
-    einsum, Saver) cannot run here (tensorflow<2 is not installable offline), so
-    for the learned conv stack the parity is "unpinned beyond the alignment KATs":
-    the reference holds no golden vector for it (integrate_test.py:50-54 trains on
-    noise inside the test and asserts only shapes).  torch.nn.functional.conv1d
-    on CPU is used as an independent second opinion in tests/test_oracle_kat.py.
+  * the TF-graph-only pieces (model.predict_coefficients / predict_time_derivative /
+    baseline_space_derivatives, layers.pad_periodic, polynomials.reconstruct) cannot run on
+    TensorFlow here (tensorflow<2 is not installable offline); they are pinned against the
+    reference's own graph-construction code executed on a NumPy-eager stand-in for the primitive
+    TF ops (tests/golden/_tf_numpy_shim.py: VALID conv1d, einsum, extract_image_patches, ... with
+    TF's documented semantics).  What stays unpinned is only the float32 summation order of TF's
+    real conv kernels; the reference itself holds no golden vector for the learned path
+    (integrate_test.py:50-54 trains on noise inside the test and asserts only shapes).
+    torch.nn.functional.conv1d on CPU is an independent second opinion in tests/test_oracle_kat.py.
 
 All file:line citations are into /root/reference/pde_superresolution/.
 """
@@ -416,7 +419,8 @@ class NetSpec(object):
 
   def __init__(self, num_layers=3, filter_size=32, kernel_size=5, nonlinearity='relu',
                polynomial_accuracy_order=1, polynomial_accuracy_scale=1.0,
-               coefficient_grid_min_size=6, ensure_unbiased_coefficients=False):
+               coefficient_grid_min_size=6, ensure_unbiased_coefficients=False,
+               model_target='coefficients'):
     self.num_layers = num_layers
     self.filter_size = filter_size
     self.kernel_size = kernel_size
@@ -425,6 +429,7 @@ class NetSpec(object):
     self.polynomial_accuracy_scale = polynomial_accuracy_scale
     self.coefficient_grid_min_size = coefficient_grid_min_size
     self.ensure_unbiased_coefficients = ensure_unbiased_coefficients
+    self.model_target = model_target
 
 
 def coefficient_grid(eq, net):
@@ -443,7 +448,11 @@ def accuracy_layers(eq, net):
 
 def layer_shapes(eq, net):
   """Kernel shapes [(k, cin, cout), ...] of the conv stack (model.py:455-458,492-495)."""
-  if net.polynomial_accuracy_order:
+  if net.model_target == 'space_derivatives':                         # model.py:571-576
+    cout = len(eq.orders)
+  elif net.model_target in ('time_derivative', 'flux'):               # model.py:603-615
+    cout = 1
+  elif net.polynomial_accuracy_order:
     cout = sum(l.input_size for l in accuracy_layers(eq, net))
   else:
     cout = len(eq.orders) * coefficient_grid(eq, net).size             # model.py:464-467
@@ -544,9 +553,26 @@ def apply_space_derivatives(derivs, inputs, eq):
   return eq.equation_of_motion(inputs, d)
 
 
+def multilayer_conv1d(inputs, eq, net, weights, dtype=np.float32):
+  """model.py:551-568: the normalised conv stack with a linear last layer, [b, x] -> [b, x, targets]."""
+  x = np.asarray(inputs, dtype=dtype)[:, :, None] / np.dtype(dtype).type(eq.standard_deviation)
+  for i, (w, b) in enumerate(weights):
+    act = net.nonlinearity if i < len(weights) - 1 else None
+    x = conv1d_periodic_layer(x, w.astype(dtype), b.astype(dtype), act)
+  return x
+
+
 def predict_time_derivative(inputs, eq, net, weights, dtype=np.float32):
-  """model.py:618-640 with model_target='coefficients'."""
+  """model.py:618-640, every model_target."""
   inputs = np.asarray(inputs, dtype=dtype)
+  if net.model_target == 'time_derivative':                            # :603-606
+    return multilayer_conv1d(inputs, eq, net, weights, dtype)[..., 0]
+  if net.model_target == 'flux':                                       # :609-615 (note: no minus sign)
+    return staggered_first_derivative(multilayer_conv1d(inputs, eq, net, weights, dtype)[..., 0],
+                                      np.dtype(dtype).type(eq.dx)).astype(dtype)
+  if net.model_target == 'space_derivatives':                          # :571-576
+    derivs = multilayer_conv1d(inputs, eq, net, weights, dtype)
+    return apply_space_derivatives(derivs, inputs, eq).astype(dtype)
   coefs = predict_coefficients(inputs, eq, net, weights, dtype=dtype)
   derivs = apply_coefficients(coefs, inputs)
   return apply_space_derivatives(derivs, inputs, eq).astype(dtype)

@@ -64,7 +64,11 @@ def conv_shapes(hp, equation):
   """Kernel shapes the reference's predict_coefficients will ask for (model.py:455-495)."""
   grid = polynomials.regular_grid(equation.GRID_OFFSET, 0, hp.coefficient_grid_min_size,
                                   equation.grid.solution_dx)
-  if hp.polynomial_accuracy_order:
+  if hp.model_target == 'space_derivatives':
+    cout = len(equation.DERIVATIVE_ORDERS)
+  elif hp.model_target in ('time_derivative', 'flux'):
+    cout = 1
+  elif hp.polynomial_accuracy_order:
     method = (polynomials.Method.FINITE_VOLUMES if equation.CONSERVATIVE
               else polynomials.Method.FINITE_DIFFERENCES)
     cout = sum(
@@ -218,6 +222,31 @@ def golden_learned():
       set_store(weights)
       out[key + '/time_derivative'] = model.predict_time_derivative(tf.Tensor(u), hp).a
   np.savez_compressed(os.path.join(HERE, 'learned.npz'), **out)
+  return len(out)
+
+
+def golden_targets():
+  """The other hparams.model_target values (model.py:551-640), reference code on the shim."""
+  out = {}
+  rs = np.random.RandomState(4321)
+  for target in ('space_derivatives', 'time_derivative', 'flux'):
+    for kind, variant in (('burgers', 'plain'), ('burgers', 'conservative'), ('ks', 'godunov')):
+      n = 32
+      hp = make_hparams(kind, variant, n, model_target=target)
+      eq = equation_class(kind, variant)(n, random_seed=5)
+      weights = random_weights(conv_shapes(hp, eq), seed=len(out), last_scale=1.0)
+      u = (0.6 * rs.randn(3, n)).astype(np.float32)
+      key = '%s/%s/%s' % (target, kind, variant)
+      out.update(flat_weights(key, weights))
+      out[key + '/u'] = u
+      set_store(weights)
+      out[key + '/time_derivative'] = model.predict_time_derivative(tf.Tensor(u), hp).a
+      if target == 'space_derivatives':
+        set_store(weights)
+        out[key + '/space_derivatives'] = model.predict_space_derivatives(tf.Tensor(u), hp).a
+      d = EagerModelDifferentiator(eq, hp, weights)
+      out[key + '/differentiator'] = d(0.61, u[0].astype(np.float64))
+  np.savez_compressed(os.path.join(HERE, 'targets.npz'), **out)
   return len(out)
 
 
@@ -380,7 +409,10 @@ def golden_layers():
 
 
 if __name__ == '__main__':
-  for fn in (golden_tables, golden_learned, golden_baseline, golden_pointwise,
+  only = sys.argv[1:]
+  for fn in (golden_tables, golden_learned, golden_targets, golden_baseline, golden_pointwise,
              golden_trajectories, golden_layers):
+    if only and fn.__name__ not in only:
+      continue
     print(fn.__name__, fn())
   os.system('ls -la %s/*.npz' % HERE)

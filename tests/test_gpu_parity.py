@@ -539,3 +539,26 @@ def test_spectral_exact_and_warmup(golden):
   assert y.shape == (3, 16) and np.isfinite(y).all()
   np.testing.assert_allclose(np.asarray(ds['time'].data if hasattr(ds['time'], 'data') else ds['time']),
                              0.01 + np.linspace(0, 0.01, 3))
+
+
+def test_model_targets_against_reference_fixture(golden):
+  """The other hparams.model_target values: the net predicts derivatives, dy/dt or a flux
+  directly (model.py:551-640)."""
+  from ddd1d_b200 import model, integrate
+  g = golden('targets')
+  for target in ('space_derivatives', 'time_derivative', 'flux'):
+    for kind, variant in (('burgers', 'plain'), ('burgers', 'conservative'), ('ks', 'godunov')):
+      key = '%s/%s/%s' % (target, kind, variant)
+      hp = G.product_hparams(kind, variant, 32, model_target=target)
+      w = weights_from(g, key)
+      u = g[key + '/u']
+      assert rel_err(cpu(model.predict_time_derivative(u, hp, w)), g[key + '/time_derivative']) < FLUX_TOL, key
+      if target == 'space_derivatives':
+        assert rel_err(cpu(model.predict_space_derivatives(u, hp, w)), g[key + '/space_derivatives']) < RHS_TOL
+      else:
+        with pytest.raises(NotImplementedError):
+          model.predict_space_derivatives(u, hp, w)
+      with pytest.raises(ValueError):
+        model.predict_coefficients(u, hp, w)
+      d = integrate.SavedModelDifferentiator(w, G.product_equation(kind, variant, 32, seed=5), hp)
+      assert rel_err(d(0.61, u[0].astype(np.float64)), g[key + '/differentiator']) < FLUX_TOL, key

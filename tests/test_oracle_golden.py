@@ -199,3 +199,21 @@ def test_trajectories(golden):
   y, nfev = O.odeint(eq.initial_value(), O.SpectralDifferentiator(eq), g['spectral_kdv/times'])
   assert nfev == int(g['spectral_kdv/nfev'])
   np.testing.assert_allclose(y, g['spectral_kdv/y'], rtol=1e-12, atol=1e-12)
+
+
+def test_model_targets(golden):
+  """hparams.model_target in {space_derivatives, time_derivative, flux} (model.py:551-640)."""
+  g = golden('targets')
+  for target in ('space_derivatives', 'time_derivative', 'flux'):
+    for kind, variant in (('burgers', 'plain'), ('burgers', 'conservative'), ('ks', 'godunov')):
+      key = '%s/%s/%s' % (target, kind, variant)
+      eq = O.EquationSpec(kind, variant, num_points=32, random_seed=5)
+      net = O.NetSpec(model_target=target)
+      w = weights_from(g, key)
+      assert [k.shape for k, _ in w] == O.layer_shapes(eq, net)
+      u = g[key + '/u']
+      assert rel_err(O.predict_time_derivative(u, eq, net, w), g[key + '/time_derivative']) < 1e-5, key
+      if target == 'space_derivatives':
+        assert rel_err(O.multilayer_conv1d(u, eq, net, w), g[key + '/space_derivatives']) < F32_TOL
+      d = O.ModelDifferentiator(eq, net, w)
+      assert rel_err(d(0.61, u[0].astype(np.float64)), g[key + '/differentiator']) < 1e-5, key
