@@ -175,6 +175,33 @@ int finalize_tc(ddd1d_handle* h) {
   }
   std::vector<float> blob;
   auto reserve = [&](size_t n) { size_t off = blob.size(); blob.resize(off + n, 0.f); return (int)off; };
+  // Operand format of the tensor layers: fp16 x 2 planes (K = 16 per MMA) unless DDD1D_TC_F16=0 asks for the
+  // TF32 hi/lo planes (K = 8 per MMA).  Both carry ~22 significant bits per operand.
+  const bool f16 = !(getenv("DDD1D_TC_F16") && atoi(getenv("DDD1D_TC_F16")) == 0);
+  P.tc_f16 = f16 ? 1 : 0;
+  const int planes = f16 ? tc::kChunks / 2 : tc::kChunks;     // chunk planes per tap
+  const int cpp = f16 ? 8 : 4;                                // input channels per 16-byte chunk
+  auto pow2_scale = [](double maxabs) {                       // largest 2^e with maxabs * 2^e < 2^14
+    if (!(maxabs > 0.0)) return 1.0;
+    int e;
+    std::frexp(maxabs, &e);
+    return std::ldexp(1.0, std::min(14 - e, 60));
+  };
+  // writes one filter value into a [Whi | Wlo] plane pair (rows = 2 * nb)
+  auto put_weight = [&](float* cat, int nb, int k, int ci, int col, double w, double sw) {
+    const size_t plane = (size_t)(k * planes + ci / cpp) * (2 * nb) * 4;      // in floats (16 B per row)
+    if (f16) {
+      __half* hp = reinterpret_cast<__half*>(cat + plane);
+      const float v = (float)(w * sw);
+      const __half hi = __float2half_rn(v);
+      hp[(size_t)col * 8 + (ci % 8)] = hi;
+      hp[(size_t)(nb + col) * 8 + (ci % 8)] = __float2half_rn((v - __half2float(hi)) * 2048.f);
+    } else {
+      const float wf = (float)w, whi = tf32_hi(wf);
+      cat[plane + (size_t)col * 4 + (ci % 4)] = whi;
+      cat[plane + (size_t)(nb + col) * 4 + (ci % 4)] = tf32_hi(wf - whi);
+    }
+  };
   // first layer [5][32] + bias
   const HostLayer& l0 = h->layers[0];
   P.tc_w1_off = reserve(K * F);
@@ -186,41 +213,58 @@ int finalize_tc(ddd1d_handle* h) {
   const int nhid = L - 2;
   P.tc_bh_off = reserve((size_t)std::max(nhid, 1) * F);
   P.tc_bl_off = reserve(32);
-  P.tc_bhid_stride = 2 * K * tc::kChunks * F * 4;   // planes [tap*8+chunk][2F rows: Whi then Wlo][4]
+  P.tc_bhid_stride = 2 * K * planes * F * 4;   // planes [tap*planes+chunk][2F rows: Whi then Wlo][16 B]
+  P.tc_w1abs = P.tc_b1abs = P.tc_whabs = P.tc_bhabs = 0.f;
+  P.tc_sw_hid = P.tc_sw_last = 1.f;
+  for (int co = 0; co < F; ++co) {
+    double a = 0.0;
+    for (int k = 0; k < K; ++k) a += std::fabs((double)l0.kernel[(size_t)k * F + co]);
+    P.tc_w1abs = std::max(P.tc_w1abs, (float)(a * (1.0 + 1e-6)));
+    P.tc_b1abs = std::max(P.tc_b1abs, std::fabs(l0.bias[co]));
+  }
   P.tc_bhid_lo = 0;
   P.tc_bhid_off = reserve((size_t)std::max(nhid, 0) * P.tc_bhid_stride);
   for (int l = 0; l < nhid; ++l) {
     const HostLayer& hl = h->layers[1 + l];
     for (int co = 0; co < F; ++co) blob[P.tc_bh_off + l * F + co] = hl.bias[co];
     float* cat = blob.data() + P.tc_bhid_off + (size_t)l * P.tc_bhid_stride;
+    double wmax = 0.0;
+    for (size_t i = 0; i < (size_t)K * F * F; ++i) wmax = std::max(wmax, std::fabs((double)hl.kernel[i]));
+    const double sw = f16 ? pow2_scale(wmax) : 1.0;
+    P.tc_sw_hid = (float)sw;
+    for (int co = 0; co < F; ++co) {
+      double a = 0.0;
+      for (int k = 0; k < K; ++k)
+        for (int ci = 0; ci < F; ++ci) a += std::fabs((double)hl.kernel[((size_t)k * F + ci) * F + co]);
+      P.tc_whabs = std::max(P.tc_whabs, (float)(a * (1.0 + 1e-6)));
+      P.tc_bhabs = std::max(P.tc_bhabs, std::fabs(hl.bias[co]));
+    }
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
-        for (int co = 0; co < F; ++co) {
-          const float w = hl.kernel[((size_t)k * F + ci) * F + co];
-          const size_t plane = (size_t)(k * tc::kChunks + ci / 4) * (2 * F) * 4;
-          const float whi = tf32_hi(w);
-          cat[plane + (size_t)co * 4 + (ci % 4)] = whi;
-          cat[plane + (size_t)(F + co) * 4 + (ci % 4)] = tf32_hi(w - whi);
-        }
+        for (int co = 0; co < F; ++co) put_weight(cat, F, k, ci, co, hl.kernel[((size_t)k * F + ci) * F + co], sw);
   }
   // last layer with the projection folded in: W'[k][ci][q] = sum_c W[k][ci][c] pm[c][q]
   const HostLayer& ll = h->layers[L - 1];
   P.tc_blast_lo = 0;
-  P.tc_blast_off = reserve((size_t)2 * K * tc::kChunks * NL * 4);
+  P.tc_blast_off = reserve((size_t)2 * K * planes * NL * 4);
   {
-    float* cat = blob.data() + P.tc_blast_off;
+    std::vector<double> folded((size_t)K * F * Q, 0.0);
+    double wmax = 0.0;
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
         for (int q = 0; q < Q; ++q) {
           double acc = 0.0;
           for (int ch = 0; ch < c.net_outputs; ++ch)
             acc += (double)ll.kernel[((size_t)k * F + ci) * c.net_outputs + ch] * pm[(size_t)ch * Q + q];
-          const float w = (float)acc;
-          const size_t plane = (size_t)(k * tc::kChunks + ci / 4) * (2 * NL) * 4;
-          const float whi = tf32_hi(w);
-          cat[plane + (size_t)q * 4 + (ci % 4)] = whi;
-          cat[plane + (size_t)(NL + q) * 4 + (ci % 4)] = tf32_hi(w - whi);
+          folded[((size_t)k * F + ci) * Q + q] = acc;
+          wmax = std::max(wmax, std::fabs(acc));
         }
+    const double sw = f16 ? pow2_scale(wmax) : 1.0;
+    P.tc_sw_last = (float)sw;
+    float* cat = blob.data() + P.tc_blast_off;
+    for (int k = 0; k < K; ++k)
+      for (int ci = 0; ci < F; ++ci)
+        for (int q = 0; q < Q; ++q) put_weight(cat, NL, k, ci, q, folded[((size_t)k * F + ci) * Q + q], sw);
     for (int q = 0; q < Q; ++q) {
       double acc = pbias[q];
       for (int ch = 0; ch < c.net_outputs; ++ch) acc += (double)ll.bias[ch] * pm[(size_t)ch * Q + q];
@@ -240,8 +284,9 @@ int finalize_tc(ddd1d_handle* h) {
   // shared-memory plan: as many row teams as fit (at most 512 / N)
   const int plane = (N + 4) * 16;
   int t = 0;
-  P.tc_t_act_hi = t; t += tc::kChunks * plane;
-  P.tc_t_act_lo = t; t += tc::kChunks * plane;
+  P.tc_t_act_hi = t; t += planes * plane;
+  P.tc_t_act_lo = t; t += planes * plane;
+  P.tc_t_umax = t; t += 16 * 4;                                     // per-warp max |u / sigma|
   P.tc_t_ust = t; t += align_up(2 * (N + 2 * kHalo + 2) * 4, 16);   // raw row + row / sigma
   P.tc_t_k = t; t += kMaxStages * N * 4;
   P.tc_t_flux = t; t += N * 4;
@@ -266,10 +311,11 @@ int finalize_tc(ddd1d_handle* h) {
   CUDA_TRY(h, cudaMalloc(&h->d_blob_tc, blob.size() * sizeof(float)));
   CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   P.blob = h->d_blob_tc;
-  CUDA_TRY(h, cudaFuncSetAttribute(tc::tc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
+  const void* kern = f16 ? (const void*)tc::tc_row_kernel<true> : (const void*)tc::tc_row_kernel<false>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
   h->tc_threads = P.tc_teams * N;            // thread <-> grid point; tile-leader warps issue the MMAs
   int occ = 0;
-  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc::tc_row_kernel, h->tc_threads, P.smem_bytes));
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, h->tc_threads, P.smem_bytes));
   if (occ < 1) {
     h->tc_why = "tensor kernel does not fit on an SM";
     if (want == DDD1D_ENGINE_TENSOR) return fail(h, DDD1D_EUNSUPPORTED, "%s", h->tc_why.c_str());
@@ -487,7 +533,8 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     const Params& T = h->Ptc;
     const int teams_needed = (W.batch + T.tc_teams - 1) / T.tc_teams;
     const int grid_tc = std::min(teams_needed, h->num_sms);
-    tc::tc_row_kernel<<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W);
+    if (T.tc_f16) tc::tc_row_kernel<true><<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W);
+    else tc::tc_row_kernel<false><<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;

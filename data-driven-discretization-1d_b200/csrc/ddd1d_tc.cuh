@@ -24,6 +24,8 @@
 // tcgen05.commit -> mbarrier; 16 warps per CTA keep 128 registers per thread (no spills).  While one team runs an epilogue on the CUDA
 // cores, the tensor pipe works on another team's tile.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ddd1d_device.cuh"
 
 namespace ddd1d {
@@ -194,36 +196,97 @@ __device__ __forceinline__ void mma_tf32_split(uint32_t tmem_d, uint32_t a_lo, u
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t instr_desc_f16(int m, int n) {   // kind::f16, fp16 x fp16 -> fp32
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Issue every MMA of one layer for one 128-position tile.  Must be called by a converged warp with
 // warp-uniform arguments; one elected lane issues.
 //   act_hi/act_lo : shared addresses of the tile's team planes (position 0 of the row)
 //   b             : shared address of the layer's [Whi | Wlo] planes, b_plane_bytes = 2*NB*16
 //   d_col         : TMEM column of the tile's accumulator block; layout
 //                   [even taps: main NB | cross NB][odd taps: main NB | cross NB]
+// F16 = false: TF32 planes, 8 chunk planes of 4 floats, K = 8 per MMA (4 ci-blocks per tap);
+// F16 = true : fp16 planes, 4 chunk planes of 8 halfs, K = 16 per MMA (2 ci-blocks per tap).
+template <bool F16>
 __device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes, uint32_t b,
                                             uint32_t b_plane_bytes, int tile, uint32_t d_col, int nb) {
+  constexpr int kPlanes = F16 ? kChunks / 2 : kChunks;
   const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1 (bits 32..47)
   const uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
   const uint32_t ah0 = (((act_hi >> 4) + (uint32_t)tile * 128u) & 0x3FFFu) | (plane16 << 16);
   const uint32_t al0 = (((act_lo >> 4) + (uint32_t)tile * 128u) & 0x3FFFu) | (plane16 << 16);
   const uint32_t b0 = ((b >> 4) & 0x3FFFu) | (bplane16 << 16);
-  const uint32_t idesc_wide = instr_desc_tf32(128, 2 * nb), idesc_narrow = instr_desc_tf32(128, nb);
+  const uint32_t idesc_wide = F16 ? instr_desc_f16(128, 2 * nb) : instr_desc_tf32(128, 2 * nb);
+  const uint32_t idesc_narrow = F16 ? instr_desc_f16(128, nb) : instr_desc_tf32(128, nb);
   if (elect_one()) {
 #pragma unroll
     for (int k = 0; k < kTaps; ++k) {
       const uint32_t d_main = d_col + (uint32_t)((k & 1) * 2 * nb);
       const uint32_t d_cross = d_main + (uint32_t)nb;
 #pragma unroll
-      for (int kb = 0; kb < kChunks / 2; ++kb) {
+      for (int kb = 0; kb < kPlanes / 2; ++kb) {
         const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
-        const uint32_t bo = (uint32_t)(k * kChunks + 2 * kb) * bplane16;
+        const uint32_t bo = (uint32_t)(k * kPlanes + 2 * kb) * bplane16;
         const uint32_t first = (k < 2 && kb == 0) ? 0u : 1u;     // first touch of the even / odd block
-        mma_tf32_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);   // hi*[Whi|Wlo] -> main | cross
-        mma_tf32_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);   // lo*Whi       -> cross
+        if (F16) {
+          mma_f16_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);    // hi*[Wh|Wl'] -> main | cross
+          mma_f16_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);    // lo'*Wh      -> cross
+        } else {
+          mma_tf32_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);   // hi*[Whi|Wlo] -> main | cross
+          mma_tf32_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);   // lo*Whi       -> cross
+        }
       }
     }
   }
   __syncwarp();
+}
+
+// ---- fp16 x 2 planes -----------------------------------------------------------------------------
+// v (already multiplied by the layer's power-of-two scale) = hi + lo' * 2^-11 with hi = fp16(v) and
+// lo' = fp16((v - hi) * 2^11): 22 significant bits like the 3xTF32 split, but 2 bytes per element, so one
+// 4 KB A read covers K = 16.  Static bounds on the activations (operator norms x the row's max |u/sigma|)
+// keep v below 2^14, far from fp16's range limits; scales are powers of two, i.e. exact.
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+}
+__device__ __forceinline__ float lo_part(float v) { return (v - __half2float(__float2half_rn(v))) * 2048.f; }
+
+__device__ __forceinline__ void store_split_f16(unsigned char* hi_plane, unsigned char* lo_plane, int x, int N,
+                                                bool edge, const float (&v)[8]) {
+  uint4 h, l;
+  h.x = pack_half2(v[0], v[1]); h.y = pack_half2(v[2], v[3]); h.z = pack_half2(v[4], v[5]); h.w = pack_half2(v[6], v[7]);
+  l.x = pack_half2(lo_part(v[0]), lo_part(v[1])); l.y = pack_half2(lo_part(v[2]), lo_part(v[3]));
+  l.z = pack_half2(lo_part(v[4]), lo_part(v[5])); l.w = pack_half2(lo_part(v[6]), lo_part(v[7]));
+  *reinterpret_cast<uint4*>(hi_plane + (size_t)(x + 2) * 16) = h;
+  *reinterpret_cast<uint4*>(lo_plane + (size_t)(x + 2) * 16) = l;
+  if (edge) {
+    if (x < 2) {
+      *reinterpret_cast<uint4*>(hi_plane + (size_t)(x + 2 + N) * 16) = h;
+      *reinterpret_cast<uint4*>(lo_plane + (size_t)(x + 2 + N) * 16) = l;
+    }
+    if (x >= N - 2) {
+      *reinterpret_cast<uint4*>(hi_plane + (size_t)(x + 2 - N) * 16) = h;
+      *reinterpret_cast<uint4*>(lo_plane + (size_t)(x + 2 - N) * 16) = l;
+    }
+  }
+}
+// largest power of two s with bound * s < 2^14 (bound > 0), capped so that tiny bounds stay finite
+__device__ __forceinline__ float scale_for(float bound) {
+  int e;
+  frexpf(fmaxf(bound, 1e-30f), &e);            // bound = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, min(14 - e, 60));
 }
 
 // store 4 consecutive channels of one position into a plane (+ its wrapped halo copy).  `edge` is
@@ -258,7 +321,9 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
 }
 // sixteen outputs = (even main + odd main) + (even cross + odd cross); two loads in flight at a time
 // keeps the register peak at 48
-__device__ __forceinline__ void tmem_sum4x16(uint32_t t_em, uint32_t t_om, uint32_t t_ec, uint32_t t_oc, float* v) {
+// cross_scale: 1 for the TF32 planes, 2^-11 for the fp16 planes (their cross terms carry a 2^11 factor)
+__device__ __forceinline__ void tmem_sum4x16(uint32_t t_em, uint32_t t_om, uint32_t t_ec, uint32_t t_oc, float* v,
+                                             float cross_scale = 1.f) {
   uint32_t a[16], b[16];
   tmem_ld16_issue(t_em, a);
   tmem_ld16_issue(t_om, b);
@@ -269,16 +334,16 @@ __device__ __forceinline__ void tmem_sum4x16(uint32_t t_em, uint32_t t_om, uint3
   tmem_ld16_issue(t_oc, b);
   tmem_wait_ld();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] += (__uint_as_float(a[i]) + __uint_as_float(b[i]));
+  for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(a[i]) + __uint_as_float(b[i]), cross_scale, v[i]);
 }
 // NB = 32: block layout [even main 32 | even cross 32 | odd main 32 | odd cross 32]
-__device__ __forceinline__ void tmem_sum32(uint32_t taddr, float (&v)[32]) {
-  tmem_sum4x16(taddr, taddr + 64, taddr + 32, taddr + 96, v);
-  tmem_sum4x16(taddr + 16, taddr + 80, taddr + 48, taddr + 112, v + 16);
+__device__ __forceinline__ void tmem_sum32(uint32_t taddr, float (&v)[32], float cross_scale = 1.f) {
+  tmem_sum4x16(taddr, taddr + 64, taddr + 32, taddr + 96, v, cross_scale);
+  tmem_sum4x16(taddr + 16, taddr + 80, taddr + 48, taddr + 112, v + 16, cross_scale);
 }
 // NB = 16: block layout [even main 16 | even cross 16 | odd main 16 | odd cross 16]
-__device__ __forceinline__ void tmem_sum16(uint32_t taddr, float (&v)[16]) {
-  tmem_sum4x16(taddr, taddr + 32, taddr + 16, taddr + 48, v);
+__device__ __forceinline__ void tmem_sum16(uint32_t taddr, float (&v)[16], float cross_scale = 1.f) {
+  tmem_sum4x16(taddr, taddr + 32, taddr + 16, taddr + 48, v, cross_scale);
 }
 
 // Last-layer epilogue for one grid point: window coefficients = TMEM accumulators + folded bias,
@@ -286,10 +351,10 @@ __device__ __forceinline__ void tmem_sum16(uint32_t taddr, float (&v)[16]) {
 template <int NLV>
 __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, uint32_t taddr,
                                               const float (&u7)[kWin],
-                                              int row, int x, float (&dv)[kMaxD]) {
+                                              int row, int x, float (&dv)[kMaxD], float cross_scale, float inv_scale) {
   float cfv[NLV];
-  if (NLV == 16) tmem_sum16(taddr, reinterpret_cast<float(&)[16]>(cfv));
-  else tmem_sum32(taddr, reinterpret_cast<float(&)[32]>(cfv));
+  if (NLV == 16) tmem_sum16(taddr, reinterpret_cast<float(&)[16]>(cfv), cross_scale);
+  else tmem_sum32(taddr, reinterpret_cast<float(&)[32]>(cfv), cross_scale);
   fence_before();
   const int N = P.N;
 #pragma unroll
@@ -299,7 +364,7 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < kWin; ++j) {
-      const float cf = cfv[d * kWin + j] + P.tc_bl[d * kWin + j];
+      const float cf = fmaf(cfv[d * kWin + j], inv_scale, P.tc_bl[d * kWin + j]);
       sum = fmaf(cf, u7[j], sum);
       if (W.op == OP_COEF) {
         const int i = j - P.wshift;
@@ -314,6 +379,7 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -363,6 +429,7 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
     unsigned char* act_lo = tb + P.tc_t_act_lo;
     float* ust = reinterpret_cast<float*>(tb + P.tc_t_ust);
     float* unr = ust + (N + 2 * kHalo + 2);              // the same row divided by sigma
+    uint32_t* umax_w = reinterpret_cast<uint32_t*>(tb + P.tc_t_umax);   // per-warp max |u/sigma| (fp16 planes)
     float* kst = reinterpret_cast<float*>(tb + P.tc_t_k);
     float* flux = reinterpret_cast<float*>(tb + P.tc_t_flux);
     float* fs = reinterpret_cast<float*>(tb + P.tc_t_fs);
@@ -407,10 +474,10 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
         } else if (layer_idx != hidden_tc_layers) {
           const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
           for (int m = 0; m < tiles; ++m)
-            issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m, d_col0 + (uint32_t)m * 128u, 32);
+            issue_layer<F16>(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m, d_col0 + (uint32_t)m * 128u, 32);
         } else {
           for (int m = 0; m < tiles; ++m)
-            issue_layer(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
+            issue_layer<F16>(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
                         2u * (uint32_t)NL * 16u, m, d_col0 + (uint32_t)m * 128u, NL);
         }
         if (elect_one()) mma_commit(done);
@@ -451,6 +518,10 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
           const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
           ust[x + kHalo] = us;
           unr[x + kHalo] = usn;
+          if (F16) {      // row maximum of |u / sigma| for the activation bounds; rides on the stage barrier
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(usn)));
+            if (lane == 0) umax_w[warp_in_team] = wmax;
+          }
           if (edge) {
             if (x < kHalo) { ust[x + kHalo + N] = us; unr[x + kHalo + N] = usn; }
             if (x >= N - kHalo) { ust[x + kHalo - N] = us; unr[x + kHalo - N] = usn; }
@@ -467,6 +538,13 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
           }
           team_sync(team, N);
           if (forced) forcing_reduce(P, fs + s * kForcingStride, x);   // visible to the team after the mbarrier rounds below
+          float s_act = 1.f, bound = 0.f;      // scale of the planes being written / bound on their values
+          if (F16) {
+            uint32_t m = 0;
+            for (int w = 0; w < team_warps; ++w) m = max(m, umax_w[w]);
+            bound = fmaf(P.tc_w1abs, __uint_as_float(m), P.tc_b1abs);   // |h1| <= |b1| + sum|W1| * max|u/sigma|
+            s_act = scale_for(bound);
+          }
           float u7[kWin];
 #pragma unroll
           for (int j = 0; j < kWin; ++j) u7[j] = ust[x + j];
@@ -476,6 +554,7 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
             float un[kTaps];
 #pragma unroll
             for (int k = 0; k < kTaps; ++k) un[k] = unr[x + k + 1];
+            float pend[8];      // fp16 planes hold 8 channels per 16-byte chunk
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
               float4 h = make_float4(P.tc_b1[4 * c4], P.tc_b1[4 * c4 + 1], P.tc_b1[4 * c4 + 2], P.tc_b1[4 * c4 + 3]);
@@ -487,8 +566,17 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
                 h.w = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 3], h.w);
               }
               // hidden activations are ReLU on this engine (other nonlinearities use the FFMA engine)
-              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
-                          fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
+              if (F16) {
+                const int o = (c4 & 1) * 4;
+                pend[o] = fmaxf(h.x, 0.f) * s_act; pend[o + 1] = fmaxf(h.y, 0.f) * s_act;
+                pend[o + 2] = fmaxf(h.z, 0.f) * s_act; pend[o + 3] = fmaxf(h.w, 0.f) * s_act;
+                if (c4 & 1)
+                  store_split_f16(act_hi + (size_t)(c4 >> 1) * plane_bytes, act_lo + (size_t)(c4 >> 1) * plane_bytes,
+                                  x, N, edge, pend);
+              } else {
+                store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
+                            fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
+              }
             }
           }
           fence_async_smem();
@@ -502,14 +590,32 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
             release_pipe();
             fence_after();
             float acc[32];
-            tmem_sum32(taddr, acc);
+            tmem_sum32(taddr, acc, F16 ? (1.f / 2048.f) : 1.f);
             fence_before();
+            // accumulators carry (activation scale x filter scale); the next planes get their own scale
+            const float inv = F16 ? 1.f / (s_act * P.tc_sw_hid) : 1.f;
+            if (F16) {
+              bound = fmaf(P.tc_whabs, bound, P.tc_bhabs);      // |h2| <= |b2| + max_co sum|W2| * max|h1|
+              s_act = scale_for(bound);
+            }
+            float pend[8];
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
               const float4 b = make_float4(P.tc_bh[4 * c4], P.tc_bh[4 * c4 + 1], P.tc_bh[4 * c4 + 2], P.tc_bh[4 * c4 + 3]);
-              store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
-                          fmaxf(acc[4 * c4] + b.x, 0.f), fmaxf(acc[4 * c4 + 1] + b.y, 0.f),
-                          fmaxf(acc[4 * c4 + 2] + b.z, 0.f), fmaxf(acc[4 * c4 + 3] + b.w, 0.f));
+              if (F16) {
+                const int o = (c4 & 1) * 4;
+                pend[o] = fmaxf(fmaf(acc[4 * c4], inv, b.x), 0.f) * s_act;
+                pend[o + 1] = fmaxf(fmaf(acc[4 * c4 + 1], inv, b.y), 0.f) * s_act;
+                pend[o + 2] = fmaxf(fmaf(acc[4 * c4 + 2], inv, b.z), 0.f) * s_act;
+                pend[o + 3] = fmaxf(fmaf(acc[4 * c4 + 3], inv, b.w), 0.f) * s_act;
+                if (c4 & 1)
+                  store_split_f16(act_hi + (size_t)(c4 >> 1) * plane_bytes, act_lo + (size_t)(c4 >> 1) * plane_bytes,
+                                  x, N, edge, pend);
+              } else {
+                store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
+                            fmaxf(acc[4 * c4] + b.x, 0.f), fmaxf(acc[4 * c4 + 1] + b.y, 0.f),
+                            fmaxf(acc[4 * c4 + 2] + b.z, 0.f), fmaxf(acc[4 * c4 + 3] + b.w, 0.f));
+              }
             }
             fence_async_smem();
             mbar_arrive(req);
@@ -522,8 +628,10 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
           release_pipe();
           fence_after();
           float dv[kMaxD];
-          if (NL == 16) last_epilogue<16>(P, W, taddr, u7, row, x, dv);
-          else last_epilogue<32>(P, W, taddr, u7, row, x, dv);
+          const float inv_last = F16 ? 1.f / (s_act * P.tc_sw_last) : 1.f;
+          const float cross_scale = F16 ? (1.f / 2048.f) : 1.f;
+          if (NL == 16) last_epilogue<16>(P, W, taddr, u7, row, x, dv, cross_scale, inv_last);
+          else last_epilogue<32>(P, W, taddr, u7, row, x, dv, cross_scale, inv_last);
           if (W.op == OP_COEF || W.op == OP_DERIV) continue;
           float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
           if (cons) {
@@ -615,7 +723,7 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
   const uint32_t tmem_base = *slot;
   if (warp == 4) {
     const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    issue_layer(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_cat), 2u * (uint32_t)nout * 16u, 0, base_u,
+    issue_layer<false>(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_cat), 2u * (uint32_t)nout * 16u, 0, base_u,
                 nout);
     if (elect_one()) mma_commit(bar);
     __syncwarp();
