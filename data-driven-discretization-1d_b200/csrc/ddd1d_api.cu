@@ -59,6 +59,7 @@ struct ddd1d_handle {
   bool tc_ok = false;
   std::string tc_why;
   float* d_blob_tc = nullptr;
+  float* d_scratch_tc = nullptr;   // tensor engine: per-CTA exchange scratch (stage rows, maxima, flux, forcing)
   int tc_threads = 0;
   // staging for the *_host entry points
   void* d_stage_in = nullptr;
@@ -110,14 +111,6 @@ double plan_cost(int cout, int N, int nwarps, int cg, int pbt) {
 }
 
 
-float tf32_hi(float v) {   // round to TF32 (10 explicit mantissa bits), as ddd1d::tc::round_tf32
-  uint32_t b;
-  memcpy(&b, &v, 4);
-  b = (b + 0x1000u) & 0xffffe000u;
-  float r;
-  memcpy(&r, &b, 4);
-  return r;
-}
 
 int engine_request(const ddd1d_handle* h) {
   int e = h->cfg.engine;
@@ -175,12 +168,10 @@ int finalize_tc(ddd1d_handle* h) {
   }
   std::vector<float> blob;
   auto reserve = [&](size_t n) { size_t off = blob.size(); blob.resize(off + n, 0.f); return (int)off; };
-  // Operand format of the tensor layers: fp16 x 2 planes (K = 16 per MMA) unless DDD1D_TC_F16=0 asks for the
-  // TF32 hi/lo planes (K = 8 per MMA).  Both carry ~22 significant bits per operand.
-  const bool f16 = !(getenv("DDD1D_TC_F16") && atoi(getenv("DDD1D_TC_F16")) == 0);
-  P.tc_f16 = f16 ? 1 : 0;
-  const int planes = f16 ? tc::kChunks / 2 : tc::kChunks;     // chunk planes per tap
-  const int cpp = f16 ? 8 : 4;                                // input channels per 16-byte chunk
+  // Operand format of the tensor layers: fp16 x 2 planes, value * scale = hi + lo' * 2^-11 (~22 significant
+  // bits per operand, K = 16 per MMA); scales are powers of two, so they are exact.
+  const int planes = tc::kChunks / 2;     // 16-byte chunk planes per tap
+  const int cpp = 8;                      // input channels per 16-byte chunk
   auto pow2_scale = [](double maxabs) {                       // largest 2^e with maxabs * 2^e < 2^14
     if (!(maxabs > 0.0)) return 1.0;
     int e;
@@ -190,17 +181,11 @@ int finalize_tc(ddd1d_handle* h) {
   // writes one filter value into a [Whi | Wlo] plane pair (rows = 2 * nb)
   auto put_weight = [&](float* cat, int nb, int k, int ci, int col, double w, double sw) {
     const size_t plane = (size_t)(k * planes + ci / cpp) * (2 * nb) * 4;      // in floats (16 B per row)
-    if (f16) {
-      __half* hp = reinterpret_cast<__half*>(cat + plane);
-      const float v = (float)(w * sw);
-      const __half hi = __float2half_rn(v);
-      hp[(size_t)col * 8 + (ci % 8)] = hi;
-      hp[(size_t)(nb + col) * 8 + (ci % 8)] = __float2half_rn((v - __half2float(hi)) * 2048.f);
-    } else {
-      const float wf = (float)w, whi = tf32_hi(wf);
-      cat[plane + (size_t)col * 4 + (ci % 4)] = whi;
-      cat[plane + (size_t)(nb + col) * 4 + (ci % 4)] = tf32_hi(wf - whi);
-    }
+    __half* hp = reinterpret_cast<__half*>(cat + plane);
+    const float v = (float)(w * sw);
+    const __half hi = __float2half_rn(v);
+    hp[(size_t)col * 8 + (ci % 8)] = hi;
+    hp[(size_t)(nb + col) * 8 + (ci % 8)] = __float2half_rn((v - __half2float(hi)) * 2048.f);
   };
   // first layer [5][32] + bias
   const HostLayer& l0 = h->layers[0];
@@ -215,7 +200,7 @@ int finalize_tc(ddd1d_handle* h) {
   P.tc_bl_off = reserve(32);
   P.tc_bhid_stride = 2 * K * planes * F * 4;   // planes [tap*planes+chunk][2F rows: Whi then Wlo][16 B]
   P.tc_w1abs = P.tc_b1abs = P.tc_whabs = P.tc_bhabs = 0.f;
-  P.tc_sw_hid = P.tc_sw_last = 1.f;
+  P.tc_inv_sw_hid = P.tc_inv_sw_last = 1.f;
   for (int co = 0; co < F; ++co) {
     double a = 0.0;
     for (int k = 0; k < K; ++k) a += std::fabs((double)l0.kernel[(size_t)k * F + co]);
@@ -230,8 +215,8 @@ int finalize_tc(ddd1d_handle* h) {
     float* cat = blob.data() + P.tc_bhid_off + (size_t)l * P.tc_bhid_stride;
     double wmax = 0.0;
     for (size_t i = 0; i < (size_t)K * F * F; ++i) wmax = std::max(wmax, std::fabs((double)hl.kernel[i]));
-    const double sw = f16 ? pow2_scale(wmax) : 1.0;
-    P.tc_sw_hid = (float)sw;
+    const double sw = pow2_scale(wmax);
+    P.tc_inv_sw_hid = (float)(1.0 / sw);
     for (int co = 0; co < F; ++co) {
       double a = 0.0;
       for (int k = 0; k < K; ++k)
@@ -259,8 +244,8 @@ int finalize_tc(ddd1d_handle* h) {
           folded[((size_t)k * F + ci) * Q + q] = acc;
           wmax = std::max(wmax, std::fabs(acc));
         }
-    const double sw = f16 ? pow2_scale(wmax) : 1.0;
-    P.tc_sw_last = (float)sw;
+    const double sw = pow2_scale(wmax);
+    P.tc_inv_sw_last = (float)(1.0 / sw);
     float* cat = blob.data() + P.tc_blast_off;
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
@@ -281,25 +266,32 @@ int finalize_tc(ddd1d_handle* h) {
   P.blob_floats = (int)blob.size();
   P.tc_nlast = NL;
   P.tc_debug = getenv("DDD1D_TC_DEBUG") ? atoi(getenv("DDD1D_TC_DEBUG")) : 0;
-  // shared-memory plan: as many row teams as fit (at most 512 / N)
+  // shared-memory plan: 512 / N row teams, each with up to two rows (slots) in flight.  A slot's shared
+  // region holds only its activation planes; what threads exchange goes through the global scratch.
   const int plane = (N + 4) * 16;
   int t = 0;
   P.tc_t_act_hi = t; t += planes * plane;
   P.tc_t_act_lo = t; t += planes * plane;
-  P.tc_t_umax = t; t += 16 * 4;                                     // per-warp max |u / sigma|
-  P.tc_t_ust = t; t += align_up(2 * (N + 2 * kHalo + 2) * 4, 16);   // raw row + row / sigma
-  P.tc_t_k = t; t += kMaxStages * N * 4;
-  P.tc_t_flux = t; t += N * 4;
-  P.tc_t_fs = t; t += align_up((kMaxStages * tc::kForcingStride + 4) * 4, 16);
   P.tc_team_stride = align_up(t, 128);
-  P.off_bar = 0;
-  P.tc_off_slot = 96;                        // TMEM base (4 B) + tensor-pipe ticket lock (8 B)
-  P.tc_off_tab = 128;                       // Tableau (200 B)
-  P.off_blob = 384;
+  {
+    int f = 0;
+    f += 2 * 2 * (N + 2 * kHalo + 2);                       // (raw row + row / sigma) x stage parity
+    P.tc_sc_umax = f; f += 2 * 16;                          // per-warp max |u / sigma| x stage parity
+    P.tc_sc_flux = f; f += N;
+    P.tc_sc_fs = f; f += kMaxStages * tc::kForcingStride + 4;   // forcing scratch + first-bad-step word
+    P.tc_sc_stride = align_up(f, 32);
+  }
+  P.off_bar = 0;                            // 1 + 2 * (teams * slots) <= 17 mbarriers
+  P.tc_off_slot = 144;                      // TMEM base address
+  P.off_blob = 256;
   P.tc_off_team0 = align_up(P.off_blob + P.blob_floats * 4, 128);
   P.tc_teams = 512 / N;
-  while (P.tc_teams > 1 && P.tc_off_team0 + P.tc_teams * P.tc_team_stride > 227 * 1024) P.tc_teams -= 1;
-  P.smem_bytes = P.tc_off_team0 + P.tc_teams * P.tc_team_stride;
+  P.tc_slots = 2;                           // TMEM: teams * slots * (N / 128) tiles * 64 columns = 512
+  if (getenv("DDD1D_TC_SLOTS")) P.tc_slots = std::max(1, std::min(2, atoi(getenv("DDD1D_TC_SLOTS"))));
+  auto plan_bytes = [&]() { return P.tc_off_team0 + P.tc_teams * P.tc_slots * P.tc_team_stride; };
+  if (plan_bytes() > 227 * 1024) P.tc_slots = 1;
+  while (P.tc_teams > 1 && plan_bytes() > 227 * 1024) P.tc_teams -= 1;
+  P.smem_bytes = plan_bytes();
   if (P.smem_bytes > 227 * 1024) {
     h->tc_why = "shared memory plan does not fit";
     if (want == DDD1D_ENGINE_TENSOR)
@@ -311,9 +303,15 @@ int finalize_tc(ddd1d_handle* h) {
   CUDA_TRY(h, cudaMalloc(&h->d_blob_tc, blob.size() * sizeof(float)));
   CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   P.blob = h->d_blob_tc;
-  const void* kern = f16 ? (const void*)tc::tc_row_kernel<true> : (const void*)tc::tc_row_kernel<false>;
+  if (h->d_scratch_tc) CUDA_TRY(h, cudaFree(h->d_scratch_tc));
+  h->d_scratch_tc = nullptr;
+  const size_t scratch_floats = (size_t)h->num_sms * P.tc_teams * P.tc_slots * P.tc_sc_stride;
+  CUDA_TRY(h, cudaMalloc(&h->d_scratch_tc, scratch_floats * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d_scratch_tc, 0, scratch_floats * sizeof(float)));
+  P.tc_scratch = h->d_scratch_tc;
+  const void* kern = (const void*)tc::tc_row_kernel;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  h->tc_threads = P.tc_teams * N;            // thread <-> grid point; tile-leader warps issue the MMAs
+  h->tc_threads = P.tc_teams * N + 32;       // thread <-> grid point, plus the warp that issues the MMAs
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, h->tc_threads, P.smem_bytes));
   if (occ < 1) {
@@ -533,8 +531,7 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     const Params& T = h->Ptc;
     const int teams_needed = (W.batch + T.tc_teams - 1) / T.tc_teams;
     const int grid_tc = std::min(teams_needed, h->num_sms);
-    if (T.tc_f16) tc::tc_row_kernel<true><<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W);
-    else tc::tc_row_kernel<false><<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W);
+    tc::tc_row_kernel<<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W, make_tableau(W.scheme));
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;
@@ -644,6 +641,7 @@ int ddd1d_destroy(ddd1d_handle* h) {
   cudaSetDevice(h->cfg.device);
   cudaFree(h->d_blob);
   cudaFree(h->d_blob_tc);
+  cudaFree(h->d_scratch_tc);
   cudaFree(h->d_fparams);
   cudaFree(h->d_fbasis);
   cudaFree(h->d_fparams64);
@@ -944,6 +942,25 @@ int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long
   if (rc) return rc;
   CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * sizeof(long long), cudaMemcpyDeviceToHost));
   CUDA_TRY(nullptr, cudaFree(d));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_overlap(int device, int mode, int reps, int iters, int blocks, long long* cycles_host) {
+  if (reps < 1 || iters < 1 || blocks < 1 || !cycles_host) return fail(nullptr, DDD1D_EINVAL, "bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  long long* d = nullptr;
+  float* sink = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * 2 * sizeof(long long)));
+  CUDA_TRY(nullptr, cudaMemset(d, 0, (size_t)blocks * 2 * sizeof(long long)));
+  CUDA_TRY(nullptr, cudaMalloc(&sink, (256 + 1024) * sizeof(float)));
+  CUDA_TRY(nullptr, cudaMemset(sink, 0, (256 + 1024) * sizeof(float)));
+  const int smem = 128 + 2 * 4 * 260 * 16 + tc::kTaps * 4 * 64 * 16 + 8192;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_overlap_kernel<<<blocks, 256, smem>>>(reps, mode, iters, d, sink);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
+  CUDA_TRY(nullptr, cudaFree(sink));
   return DDD1D_OK;
 }
 

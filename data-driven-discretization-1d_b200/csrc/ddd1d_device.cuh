@@ -67,10 +67,12 @@ struct Params {
   // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
   int tc_teams, tc_nlast, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
   int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
-  int tc_t_act_hi, tc_t_act_lo, tc_t_ust, tc_t_k, tc_t_flux, tc_t_fs, tc_t_umax;   // byte offsets inside a team region
-  int tc_f16;               // 1: fp16 x 2 activation planes (K = 16 per MMA), 0: TF32 hi/lo planes
-  float tc_w1abs, tc_b1abs, tc_whabs, tc_bhabs;   // operator-norm bounds for the fp16 plane scales
-  float tc_sw_hid, tc_sw_last;                    // power-of-two filter scales (fp16 planes)
+  int tc_t_act_hi, tc_t_act_lo;   // byte offsets of the activation planes inside a slot's shared region
+  float* tc_scratch;              // global scratch [grid][teams * slots][tc_sc_stride] floats (L1 / L2 resident)
+  int tc_sc_stride, tc_sc_umax, tc_sc_flux, tc_sc_fs;   // float offsets inside a slot's scratch
+  int tc_slots;             // rows in flight per team (their CUDA-core and tensor phases interleave)
+  float tc_w1abs, tc_b1abs, tc_whabs, tc_bhabs;   // operator-norm bounds behind the fp16 plane scales
+  float tc_inv_sw_hid, tc_inv_sw_last;            // 1 / power-of-two filter scales
   int tc_w1_off, tc_b1_off, tc_bh_off, tc_bl_off;                          // float offsets into the blob
   int tc_bhid_off, tc_bhid_stride, tc_bhid_lo, tc_blast_off, tc_blast_lo;
   // small tables read as constant-bank FFMA operands by every thread (no shared-memory traffic)
@@ -115,7 +117,7 @@ struct Tableau {
   double b[kMaxStages];
 };
 
-__device__ __forceinline__ Tableau make_tableau(int scheme) {
+__host__ __device__ __forceinline__ Tableau make_tableau(int scheme) {
   Tableau t;
 #pragma unroll
   for (int i = 0; i < kMaxStages; ++i) {

@@ -219,7 +219,9 @@ __device__ __forceinline__ void mma_f16_split(uint32_t tmem_d, uint32_t a_lo, ui
 //                   [even taps: main NB | cross NB][odd taps: main NB | cross NB]
 // F16 = false: TF32 planes, 8 chunk planes of 4 floats, K = 8 per MMA (4 ci-blocks per tap);
 // F16 = true : fp16 planes, 4 chunk planes of 8 halfs, K = 16 per MMA (2 ci-blocks per tap).
-template <bool F16>
+// EO = true : taps accumulate alternately into two D blocks [even main|cross][odd main|cross] (halves the
+//             accumulate chain; the TF32 probe uses it);  EO = false: one block [main | cross].
+template <bool F16, bool EO>
 __device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes, uint32_t b,
                                             uint32_t b_plane_bytes, int tile, uint32_t d_col, int nb) {
   constexpr int kPlanes = F16 ? kChunks / 2 : kChunks;
@@ -233,13 +235,13 @@ __device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, ui
   if (elect_one()) {
 #pragma unroll
     for (int k = 0; k < kTaps; ++k) {
-      const uint32_t d_main = d_col + (uint32_t)((k & 1) * 2 * nb);
+      const uint32_t d_main = d_col + (EO ? (uint32_t)((k & 1) * 2 * nb) : 0u);
       const uint32_t d_cross = d_main + (uint32_t)nb;
 #pragma unroll
       for (int kb = 0; kb < kPlanes / 2; ++kb) {
         const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
         const uint32_t bo = (uint32_t)(k * kPlanes + 2 * kb) * bplane16;
-        const uint32_t first = (k < 2 && kb == 0) ? 0u : 1u;     // first touch of the even / odd block
+        const uint32_t first = (k < (EO ? 2 : 1) && kb == 0) ? 0u : 1u;     // first touch of a D block
         if (F16) {
           mma_f16_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);    // hi*[Wh|Wl'] -> main | cross
           mma_f16_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);    // lo'*Wh      -> cross
@@ -258,17 +260,21 @@ __device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, ui
 // lo' = fp16((v - hi) * 2^11): 22 significant bits like the 3xTF32 split, but 2 bytes per element, so one
 // 4 KB A read covers K = 16.  Static bounds on the activations (operator norms x the row's max |u/sigma|)
 // keep v below 2^14, far from fp16's range limits; scales are powers of two, i.e. exact.
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  return (uint32_t)__half_as_ushort(__float2half_rn(a)) | ((uint32_t)__half_as_ushort(__float2half_rn(b)) << 16);
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);                  // one packed conversion
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);   // exact remainder, scaled
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ float lo_part(float v) { return (v - __half2float(__float2half_rn(v))) * 2048.f; }
 
 __device__ __forceinline__ void store_split_f16(unsigned char* hi_plane, unsigned char* lo_plane, int x, int N,
                                                 bool edge, const float (&v)[8]) {
   uint4 h, l;
-  h.x = pack_half2(v[0], v[1]); h.y = pack_half2(v[2], v[3]); h.z = pack_half2(v[4], v[5]); h.w = pack_half2(v[6], v[7]);
-  l.x = pack_half2(lo_part(v[0]), lo_part(v[1])); l.y = pack_half2(lo_part(v[2]), lo_part(v[3]));
-  l.z = pack_half2(lo_part(v[4]), lo_part(v[5])); l.w = pack_half2(lo_part(v[6]), lo_part(v[7]));
+  split_half2(v[0], v[1], h.x, l.x);
+  split_half2(v[2], v[3], h.y, l.y);
+  split_half2(v[4], v[5], h.z, l.z);
+  split_half2(v[6], v[7], h.w, l.w);
   *reinterpret_cast<uint4*>(hi_plane + (size_t)(x + 2) * 16) = h;
   *reinterpret_cast<uint4*>(lo_plane + (size_t)(x + 2) * 16) = l;
   if (edge) {
@@ -284,9 +290,13 @@ __device__ __forceinline__ void store_split_f16(unsigned char* hi_plane, unsigne
 }
 // largest power of two s with bound * s < 2^14 (bound > 0), capped so that tiny bounds stay finite
 __device__ __forceinline__ float scale_for(float bound) {
-  int e;
-  frexpf(fmaxf(bound, 1e-30f), &e);            // bound = m * 2^e, m in [0.5, 1)
-  return ldexpf(1.f, min(14 - e, 60));
+  // bound in [2^(eb-127), 2^(eb-126))  ->  s = 2^(140 - eb), i.e. bound * s in [2^13, 2^14)
+  const int eb = (int)((__float_as_uint(fmaxf(bound, 1e-30f)) >> 23) & 0xffu);
+  return __uint_as_float((uint32_t)(min(140 - eb, 60) + 127) << 23);
+}
+// 1 / s for a power of two s (exact)
+__device__ __forceinline__ float pow2_inverse(float s) {
+  return __uint_as_float((254u << 23) - __float_as_uint(s));
 }
 
 // store 4 consecutive channels of one position into a plane (+ its wrapped halo copy).  `edge` is
@@ -318,6 +328,15 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// sixteen outputs = main + cross * cross_scale
+__device__ __forceinline__ void tmem_pair16(uint32_t t_main, uint32_t t_cross, float* v, float cross_scale) {
+  uint32_t a[16], b[16];
+  tmem_ld16_issue(t_main, a);
+  tmem_ld16_issue(t_cross, b);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(b[i]), cross_scale, __uint_as_float(a[i]));
 }
 // sixteen outputs = (even main + odd main) + (even cross + odd cross); two loads in flight at a time
 // keeps the register peak at 48
@@ -353,8 +372,8 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
                                               const float (&u7)[kWin],
                                               int row, int x, float (&dv)[kMaxD], float cross_scale, float inv_scale) {
   float cfv[NLV];
-  if (NLV == 16) tmem_sum16(taddr, reinterpret_cast<float(&)[16]>(cfv), cross_scale);
-  else tmem_sum32(taddr, reinterpret_cast<float(&)[32]>(cfv), cross_scale);
+  tmem_pair16(taddr, taddr + NLV, cfv, cross_scale);                       // [main NLV | cross NLV]
+  if (NLV == 32) tmem_pair16(taddr + 16, taddr + NLV + 16, cfv + 16, cross_scale);
   fence_before();
   const int N = P.N;
 #pragma unroll
@@ -378,12 +397,34 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
 
 // ------------------------------------------------------------------------------------------------
 // The kernel
+//
+// A CTA holds R row teams of N threads (thread <-> grid point); every team keeps SLOTS rows in flight
+// and walks them round-robin through the three phases of a right-hand-side evaluation:
+//   phase 0  stage value -> first layer on the CUDA cores -> fp16 planes -> issue the hidden layer's MMAs
+//   phase 1  (per hidden layer) TMEM -> bias/ReLU -> fp16 planes -> issue the next layer's MMAs
+//   phase 2  TMEM -> coefficients -> stencil dot products -> equation -> stage derivative
+// While slot A's MMAs run on the tensor pipe the team's threads are in slot B's CUDA-core phase, so the
+// mbarrier wait at the top of phases 1 and 2 normally returns at once.
+//
+// A tcgen05.mma issue blocks the issuing thread once the tensor pipe's queue is full, i.e. for about as long
+// as the MMAs take.  A warp that both computes and issues therefore serialises its CUDA-core work with every
+// burst, and its team waits for it at the next barrier.  So the MMAs are issued by one extra warp that does
+// nothing else: it polls the slots' "planes stored" barriers and issues whichever layer is ready.
+//
+// Shared-memory LOADS stall for as long as MMAs stream their operands from shared memory (stores, shuffles,
+// tcgen05.ld, global loads and barriers do not: scripts/tc_overlap.py).  So the steady-state loop issues no
+// LDS at all: shared memory holds only what the tensor pipe reads (activation planes, filter planes);
+// everything threads exchange among themselves (stage row + halo, row maxima, flux, forcing amplitudes)
+// goes through a small per-CTA global scratch that stays in L1/L2, per-thread state that outlives a phase
+// (float64 solution, stage derivatives, bounds) sits in slot-indexed local arrays, and the Runge-Kutta
+// tableau is a kernel parameter (constant bank).
 // ------------------------------------------------------------------------------------------------
-template <bool F16>
-__global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W) {
+constexpr int kMaxSlots = 2;
+__global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
+                                                        const __grid_constant__ Tableau tab) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = P.N, R = P.tc_teams, tiles = N / 128;
+  const int N = P.N, R = P.tc_teams, SLOTS = P.tc_slots, tiles = N / 128;
   const int team_warps = N / 32;
   const bool is_alloc_warp = warp == 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + P.off_bar);
@@ -392,16 +433,13 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
   const uint32_t plane_bytes = (uint32_t)(N + 4) * 16u;
   const int NL = P.tc_nlast;                         // 16 or 32 columns for the last layer
   const int hidden_tc_layers = P.nlayers - 2;        // layers between the first and the last
+  const int TS = R * SLOTS;                          // rows in flight per CTA
 
-  Tableau* tab_s = reinterpret_cast<Tableau*>(smem_raw + P.tc_off_tab);
   if (tid == 0) {
-    *tab_s = make_tableau(W.scheme);
-    reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot + 4)[0] = 0u;
-    reinterpret_cast<uint32_t*>(smem_raw + P.tc_off_slot + 4)[1] = 0u;
     mbar_init(&bars[0], 1);
-    for (int t = 0; t < R; ++t) {
-      mbar_init(&bars[1 + t], (uint32_t)N);
-      mbar_init(&bars[1 + R + t], 1);
+    for (int t = 0; t < TS; ++t) {
+      mbar_init(&bars[1 + t], (uint32_t)N);          // "planes stored" : every thread of the team arrives
+      mbar_init(&bars[1 + TS + t], 1);               // "MMAs done"     : tcgen05.commit arrives
     }
     mbar_fence_init();
   }
@@ -411,7 +449,7 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
     mbar_expect_tx(&bars[0], bytes);
     bulk_copy_g2s(blob, P.blob, bytes, &bars[0]);
   }
-  if (is_alloc_warp) tmem_alloc(tmem_slot, 512);      // 4 tiles x 128 columns
+  if (is_alloc_warp) tmem_alloc(tmem_slot, 512);      // TS rows x tiles x 64 columns (main | cross)
   mbar_wait_guarded(&bars[0], 0);
   fence_before();
   __syncthreads();
@@ -419,232 +457,253 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_teams = gridDim.x * R;
+  const int nsteps = (W.op == OP_INTEGRATE) ? W.nsteps : 1;
+  const int nstages = (W.op == OP_INTEGRATE) ? tab.stages : 1;
+  const uint32_t smem_s = smem_u32(dyn_smem);
 
-  {
-    // ---------------- row team ----------------
-    const int team = warp / team_warps;
-    const int x = tid - team * N;                      // this thread's grid point
-    unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)team * P.tc_team_stride;
-    unsigned char* act_hi = tb + P.tc_t_act_hi;
-    unsigned char* act_lo = tb + P.tc_t_act_lo;
-    float* ust = reinterpret_cast<float*>(tb + P.tc_t_ust);
-    float* unr = ust + (N + 2 * kHalo + 2);              // the same row divided by sigma
-    uint32_t* umax_w = reinterpret_cast<uint32_t*>(tb + P.tc_t_umax);   // per-warp max |u/sigma| (fp16 planes)
-    float* kst = reinterpret_cast<float*>(tb + P.tc_t_k);
-    float* flux = reinterpret_cast<float*>(tb + P.tc_t_flux);
-    float* fs = reinterpret_cast<float*>(tb + P.tc_t_fs);
-    uint64_t* req = &bars[1 + team];
-    uint64_t* done = &bars[1 + R + team];
-    uint32_t done_parity = 0;
-    const int tile = x >> 7;
-    const int warp_in_team = __shfl_sync(0xffffffffu, warp - team * team_warps, 0);
-    const bool edge = warp_in_team == 0 || warp_in_team == team_warps - 1;
-    // The first warp of every 128-position tile also issues that tile's MMAs (asynchronous: it then
-    // waits for completion like everybody else).  All issue-side values are warp-uniform.
-    const bool issuer = warp_in_team == 0;
-    const int team_u = __shfl_sync(0xffffffffu, team, 0);
-    const uint32_t smem_s = smem_u32(dyn_smem);
+  if (warp == R * team_warps) {
+    // ---------------- issuer warp ----------------
     const uint32_t blob_s = smem_s + (uint32_t)P.off_blob;
-    const uint32_t team_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)team_u * (uint32_t)P.tc_team_stride;
-    const uint32_t act_hi_s = team_s + (uint32_t)P.tc_t_act_hi, act_lo_s = team_s + (uint32_t)P.tc_t_act_lo;
-    const uint32_t d_col0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(team_u * tiles * 128);
-    // ticket lock on the tensor pipe: one team's MMAs in flight at a time, so they run at full speed
-    // while the other teams are in their CUDA-core phases (alternation instead of lockstep)
-    volatile uint32_t* lock = reinterpret_cast<volatile uint32_t*>(smem_raw + P.tc_off_slot + 4);  // [0] next ticket, [1] now serving
-    uint32_t req_parity = 0;
-    bool holding = false;
-    auto post_layer = [&](int layer_idx) {
-      if (issuer) {
-        mbar_wait_guarded(req, req_parity);          // every thread of the team has stored its planes
-        uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(const_cast<uint32_t*>(lock), 1u);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        long long start = 0;
-        uint32_t spins = 0;
-        while (lock[1] != ticket) {
-          if ((++spins & 1023u) == 0) {
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int remaining[8], layer[8];
+    uint32_t parity[8];
+    int total = 0;
+    for (int ts = 0; ts < TS; ++ts) {
+      const int first = blockIdx.x * R + ts / SLOTS + (ts % SLOTS) * total_teams;      // this slot's first row
+      const int stride = SLOTS * total_teams;
+      const int rows = first < W.batch ? (W.batch - first + stride - 1) / stride : 0;
+      remaining[ts] = rows * nsteps * nstages * (hidden_tc_layers + 1);
+      layer[ts] = 0;
+      parity[ts] = 0;
+      total += remaining[ts];
+    }
+    long long start = 0;
+    uint32_t idle = 0;
+    while (total > 0) {
+      for (int ts = 0; ts < TS; ++ts) {
+        if (remaining[ts] == 0) continue;
+        // every thread of the slot's team has stored its planes (all lanes acquire)
+        if (!__all_sync(0xffffffffu, mbar_test(&bars[1 + ts], parity[ts]))) {
+          if ((++idle & 0xfffu) == 0) {
             const long long now = clock64();
             if (start == 0) start = now;
             else if (now - start > kSpinCycles) asm volatile("trap;");
           }
+          continue;
         }
+        idle = 0;
+        start = 0;
         fence_after();
+        const uint32_t slot_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)ts * (uint32_t)P.tc_team_stride;
+        const uint32_t act_hi_s = slot_s + (uint32_t)P.tc_t_act_hi, act_lo_s = slot_s + (uint32_t)P.tc_t_act_lo;
+        const uint32_t d_col0 = tmem_u + (uint32_t)(ts * tiles * 64);
+        const int layer_idx = layer[ts];
         if (P.tc_debug & 1) {
           // timing experiment: no MMAs
         } else if (layer_idx != hidden_tc_layers) {
           const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
           for (int m = 0; m < tiles; ++m)
-            issue_layer<F16>(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m, d_col0 + (uint32_t)m * 128u, 32);
+            issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m,
+                                     d_col0 + (uint32_t)m * 64u, 32);
         } else {
           for (int m = 0; m < tiles; ++m)
-            issue_layer<F16>(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
-                        2u * (uint32_t)NL * 16u, m, d_col0 + (uint32_t)m * 128u, NL);
+            issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
+                                     2u * (uint32_t)NL * 16u, m, d_col0 + (uint32_t)m * 64u, NL);
         }
-        if (elect_one()) mma_commit(done);
+        if (elect_one()) mma_commit(&bars[1 + TS + ts]);
         __syncwarp();
-        holding = true;
+        parity[ts] ^= 1u;
+        layer[ts] = layer_idx == hidden_tc_layers ? 0 : layer_idx + 1;
+        remaining[ts] -= 1;
+        total -= 1;
       }
-      req_parity ^= 1u;
-    };
-    // called right after a wait on `done`: the team's MMAs have completed, pass the pipe on
-    auto release_pipe = [&]() {
-      if (issuer && holding) {
-        if (lane == 0) atomicAdd(const_cast<uint32_t*>(lock + 1), 1u);
-        holding = false;
-      }
-    };
-    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((team * tiles + tile) * 128);
-    const Tableau& tab = *tab_s;
-    const bool cons = eq_conservative(P.eq);
-    const bool forced_eq = eq_forced(P.eq) && P.P > 0;
+    }
+  } else {
+  // ---------------- row teams ----------------
+  const int team = warp / team_warps;
+  const int x = tid - team * N;                      // this thread's grid point
+  const int tile = x >> 7;
+  const int warp_in_team = __shfl_sync(0xffffffffu, warp - team * team_warps, 0);
+  const bool edge = warp_in_team == 0 || warp_in_team == team_warps - 1;
+  const bool cons = eq_conservative(P.eq);
+  const bool forced_eq = eq_forced(P.eq) && P.P > 0;
+  const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
+  const float cross_scale = 1.f / 2048.f;
+  uint32_t done_parity = 0;
 
-    const int g = blockIdx.x * R + team;
-    for (int row = g; row < W.batch; row += total_teams) {
-      const int sample = W.sample_offset + row;
-      const ForcingTerm fterm = load_forcing_term(P, sample, x);
-      double y = W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
-      int first_bad = -1, save_idx = 0;
-      const int nsteps = (W.op == OP_INTEGRATE) ? W.nsteps : 1;
-      for (int step = 0; step < nsteps; ++step) {
-        const double t0 = W.t0 + (double)step * W.dt;
-        const int nstages = (W.op == OP_INTEGRATE) ? tab.stages : 1;
-        for (int s = 0; s < nstages; ++s) {
+  // ---- per-slot views -------------------------------------------------------------------------
+  struct SlotView {
+    unsigned char *act_hi, *act_lo;      // shared memory (written with STS, read by the tensor pipe)
+    float *ust, *unr, *flux, *fs;        // global scratch
+    uint32_t* umax_w;
+    uint64_t *req, *done;
+    uint32_t taddr;
+  };
+  // The stage row (raw, normalised) and its warp maxima are double-buffered on the stage parity: phase 2
+  // of stage s reads them while a faster warp may already be writing stage s+1 (phase 0).
+  uint32_t stage_par = 0;
+  auto view = [&](int sl) {
+    const int ts = team * SLOTS + sl;
+    unsigned char* tb = smem_raw + P.tc_off_team0 + (size_t)ts * P.tc_team_stride;
+    SlotView v;
+    v.act_hi = tb + P.tc_t_act_hi;
+    v.act_lo = tb + P.tc_t_act_lo;
+    float* sc = P.tc_scratch + ((size_t)blockIdx.x * TS + ts) * P.tc_sc_stride;
+    v.ust = sc + stage_par * (uint32_t)(2 * (N + 2 * kHalo + 2));
+    v.unr = v.ust + (N + 2 * kHalo + 2);             // the same row divided by sigma
+    v.umax_w = reinterpret_cast<uint32_t*>(sc + P.tc_sc_umax) + stage_par * 16u;
+    v.flux = sc + P.tc_sc_flux;
+    v.fs = sc + P.tc_sc_fs;
+    v.req = &bars[1 + ts];
+    v.done = &bars[1 + TS + ts];
+    v.taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((ts * tiles + tile) * 64);
+    return v;
+  };
+  // scale of the planes written by phase 0 / phase 1 and the bound behind it (team-uniform, recomputed)
+  auto first_bound = [&](const SlotView& v) {
+    uint32_t m = 0;
+    for (int w = 0; w < team_warps; ++w) m = max(m, v.umax_w[w]);
+    return fmaf(P.tc_w1abs, __uint_as_float(m), P.tc_b1abs);      // |h1| <= |b1| + sum|W1| * max|u/sigma|
+  };
+
+  // per-thread state that outlives a phase, indexed by slot (local memory: L1, never LDS)
+  double y_s[kMaxSlots];
+  float k_s[kMaxSlots][kMaxStages];
+  float bound_s[kMaxSlots];
+
+  const int g = blockIdx.x * R + team;
+  for (int row0 = g; row0 < W.batch; row0 += SLOTS * total_teams) {
+    int nslots = 0;
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int row = row0 + sl * total_teams;
+      if (row >= W.batch) break;
+      ++nslots;
+      const SlotView v = view(sl);
+      y_s[sl] = W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
+      if (x == 0) *reinterpret_cast<unsigned int*>(v.fs + kMaxStages * kForcingStride) = 0xffffffffu;
+    }
+    int save_idx = 0;
+    for (int step = 0; step < nsteps; ++step) {
+      const double t0 = W.t0 + (double)step * W.dt;
+      for (int s = 0; s < nstages; ++s) {
+        // ================= phase 0 =================
+#pragma unroll 1
+        for (int sl = 0; sl < nslots; ++sl) {
+          const SlotView v = view(sl);
+          const int sample = W.sample_offset + row0 + sl * total_teams;
           // ---- stage value, rounded to float32 (integrate.py:57-60,71) ----
           double accd = 0.0;
 #pragma unroll
           for (int j = 0; j < kMaxStages; ++j)
-            if (j < s && tab.a[s][j] != 0.0) accd += tab.a[s][j] * (double)kst[j * N + x];
+            if (j < s && tab.a[s][j] != 0.0) accd += tab.a[s][j] * (double)k_s[sl][j];
+          const double y = y_s[sl];
           const float us = (float)(s == 0 ? y : y + W.dt * accd);
           const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
-          ust[x + kHalo] = us;
-          unr[x + kHalo] = usn;
-          if (F16) {      // row maximum of |u / sigma| for the activation bounds; rides on the stage barrier
+          v.ust[x + kHalo] = us;
+          v.unr[x + kHalo] = usn;
+          {      // row maximum of |u / sigma| for the activation bounds; rides on the stage barrier
             const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(usn)));
-            if (lane == 0) umax_w[warp_in_team] = wmax;
+            if (lane == 0) v.umax_w[warp_in_team] = wmax;
           }
           if (edge) {
-            if (x < kHalo) { ust[x + kHalo + N] = us; unr[x + kHalo + N] = usn; }
-            if (x >= N - kHalo) { ust[x + kHalo - N] = us; unr[x + kHalo - N] = usn; }
+            if (x < kHalo) { v.ust[x + kHalo + N] = us; v.unr[x + kHalo + N] = usn; }
+            if (x >= N - kHalo) { v.ust[x + kHalo - N] = us; v.unr[x + kHalo - N] = usn; }
           }
-          const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
           if (forced && s == 0) {
             // the sincos of every stage of this step, spread over nstages * P threads
             const int sq = x / P.P, q = x - sq * P.P;
             if (sq < nstages) {
-              const ForcingTerm fq = (sq == 0) ? fterm : load_forcing_term(P, sample, q);
+              const ForcingTerm fq = load_forcing_term(P, sample, q);
               const float ts = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[sq] * W.dt : W.t0);
-              forcing_terms(P, fs + sq * kForcingStride, fq, q, ts);
+              forcing_terms(P, v.fs + sq * kForcingStride, fq, q, ts);
             }
           }
           team_sync(team, N);
-          if (forced) forcing_reduce(P, fs + s * kForcingStride, x);   // visible to the team after the mbarrier rounds below
-          float s_act = 1.f, bound = 0.f;      // scale of the planes being written / bound on their values
-          if (F16) {
-            uint32_t m = 0;
-            for (int w = 0; w < team_warps; ++w) m = max(m, umax_w[w]);
-            bound = fmaf(P.tc_w1abs, __uint_as_float(m), P.tc_b1abs);   // |h1| <= |b1| + sum|W1| * max|u/sigma|
-            s_act = scale_for(bound);
-          }
-          float u7[kWin];
-#pragma unroll
-          for (int j = 0; j < kWin; ++j) u7[j] = ust[x + j];
+          if (forced) forcing_reduce(P, v.fs + s * kForcingStride, x);   // visible after the barriers below
+          const float bound1 = first_bound(v);
+          bound_s[sl] = bound1;
+          const float s_act = scale_for(bound1);
 
           // ---- first layer 1 -> 32 on the CUDA cores, split and written as A planes ----
-          {
-            float un[kTaps];
+          float un[kTaps];
 #pragma unroll
-            for (int k = 0; k < kTaps; ++k) un[k] = unr[x + k + 1];
-            float pend[8];      // fp16 planes hold 8 channels per 16-byte chunk
+          for (int k = 0; k < kTaps; ++k) un[k] = v.unr[x + k + 1];
 #pragma unroll
-            for (int c4 = 0; c4 < kChunks; ++c4) {
-              float4 h = make_float4(P.tc_b1[4 * c4], P.tc_b1[4 * c4 + 1], P.tc_b1[4 * c4 + 2], P.tc_b1[4 * c4 + 3]);
+          for (int c8 = 0; c8 < kChunks / 2; ++c8) {
+            float h[8];
 #pragma unroll
-              for (int k = 0; k < kTaps; ++k) {      // filters are constant-bank operands of the FFMAs
-                h.x = fmaf(un[k], P.tc_w1[k * kF + 4 * c4], h.x);
-                h.y = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 1], h.y);
-                h.z = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 2], h.z);
-                h.w = fmaf(un[k], P.tc_w1[k * kF + 4 * c4 + 3], h.w);
-              }
-              // hidden activations are ReLU on this engine (other nonlinearities use the FFMA engine)
-              if (F16) {
-                const int o = (c4 & 1) * 4;
-                pend[o] = fmaxf(h.x, 0.f) * s_act; pend[o + 1] = fmaxf(h.y, 0.f) * s_act;
-                pend[o + 2] = fmaxf(h.z, 0.f) * s_act; pend[o + 3] = fmaxf(h.w, 0.f) * s_act;
-                if (c4 & 1)
-                  store_split_f16(act_hi + (size_t)(c4 >> 1) * plane_bytes, act_lo + (size_t)(c4 >> 1) * plane_bytes,
-                                  x, N, edge, pend);
-              } else {
-                store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
-                            fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
-              }
-            }
+            for (int i = 0; i < 8; ++i) h[i] = P.tc_b1[8 * c8 + i];
+#pragma unroll
+            for (int k = 0; k < kTaps; ++k)        // filters are constant-bank operands of the FFMAs
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = fmaf(un[k], P.tc_w1[k * kF + 8 * c8 + i], h[i]);
+            // hidden activations are ReLU on this engine (other nonlinearities use the FFMA engine)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = fmaxf(h[i], 0.f) * s_act;
+            store_split_f16(v.act_hi + (size_t)c8 * plane_bytes, v.act_lo + (size_t)c8 * plane_bytes, x, N, edge, h);
           }
           fence_async_smem();
-          mbar_arrive(req);
-          post_layer(0);
+          mbar_arrive(v.req);
+        }
 
-          // ---- hidden layers on the tensor pipe; epilogue rewrites the planes in place ----
-          for (int l = 0; l < hidden_tc_layers; ++l) {
-            mbar_wait_guarded(done, done_parity);
-            done_parity ^= 1u;
-            release_pipe();
+        // ================= phase 1: hidden layers on the tensor pipe =================
+        for (int l = 0; l < hidden_tc_layers; ++l) {
+#pragma unroll 1
+          for (int sl = 0; sl < nslots; ++sl) {
+            const SlotView v = view(sl);
+            mbar_wait_guarded(v.done, done_parity);
             fence_after();
             float acc[32];
-            tmem_sum32(taddr, acc, F16 ? (1.f / 2048.f) : 1.f);
+            tmem_pair16(v.taddr, v.taddr + 32, acc, cross_scale);
+            tmem_pair16(v.taddr + 16, v.taddr + 48, acc + 16, cross_scale);
             fence_before();
             // accumulators carry (activation scale x filter scale); the next planes get their own scale
-            const float inv = F16 ? 1.f / (s_act * P.tc_sw_hid) : 1.f;
-            if (F16) {
-              bound = fmaf(P.tc_whabs, bound, P.tc_bhabs);      // |h2| <= |b2| + max_co sum|W2| * max|h1|
-              s_act = scale_for(bound);
-            }
-            float pend[8];
+            const float bound1 = bound_s[sl];
+            const float inv = pow2_inverse(scale_for(bound1)) * P.tc_inv_sw_hid;
+            const float s_act = scale_for(fmaf(P.tc_whabs, bound1, P.tc_bhabs));   // |h2| <= |b2| + sum|W2| max|h1|
 #pragma unroll
-            for (int c4 = 0; c4 < kChunks; ++c4) {
-              const float4 b = make_float4(P.tc_bh[4 * c4], P.tc_bh[4 * c4 + 1], P.tc_bh[4 * c4 + 2], P.tc_bh[4 * c4 + 3]);
-              if (F16) {
-                const int o = (c4 & 1) * 4;
-                pend[o] = fmaxf(fmaf(acc[4 * c4], inv, b.x), 0.f) * s_act;
-                pend[o + 1] = fmaxf(fmaf(acc[4 * c4 + 1], inv, b.y), 0.f) * s_act;
-                pend[o + 2] = fmaxf(fmaf(acc[4 * c4 + 2], inv, b.z), 0.f) * s_act;
-                pend[o + 3] = fmaxf(fmaf(acc[4 * c4 + 3], inv, b.w), 0.f) * s_act;
-                if (c4 & 1)
-                  store_split_f16(act_hi + (size_t)(c4 >> 1) * plane_bytes, act_lo + (size_t)(c4 >> 1) * plane_bytes,
-                                  x, N, edge, pend);
-              } else {
-                store_split(act_hi + (size_t)c4 * plane_bytes, act_lo + (size_t)c4 * plane_bytes, x, N, edge,
-                            fmaxf(acc[4 * c4] + b.x, 0.f), fmaxf(acc[4 * c4 + 1] + b.y, 0.f),
-                            fmaxf(acc[4 * c4 + 2] + b.z, 0.f), fmaxf(acc[4 * c4 + 3] + b.w, 0.f));
-              }
+            for (int c8 = 0; c8 < kChunks / 2; ++c8) {
+              float h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                h[i] = fmaxf(fmaf(acc[8 * c8 + i], inv, P.tc_bh[8 * c8 + i]), 0.f) * s_act;
+              store_split_f16(v.act_hi + (size_t)c8 * plane_bytes, v.act_lo + (size_t)c8 * plane_bytes, x, N, edge, h);
             }
             fence_async_smem();
-            mbar_arrive(req);
-            post_layer(l + 1);
+            mbar_arrive(v.req);
           }
-
-          // ---- last layer: stencil coefficients (projection folded in) straight from TMEM ----
-          mbar_wait_guarded(done, done_parity);
           done_parity ^= 1u;
-          release_pipe();
+        }
+
+        // ================= phase 2: coefficients, derivatives, equation =================
+#pragma unroll 1
+        for (int sl = 0; sl < nslots; ++sl) {
+          const SlotView v = view(sl);
+          const int row = row0 + sl * total_teams;
+          float u7[kWin];
+#pragma unroll
+          for (int j = 0; j < kWin; ++j) u7[j] = v.ust[x + j];
+          const float bound1 = bound_s[sl];
+          const float s_last = hidden_tc_layers > 0 ? scale_for(fmaf(P.tc_whabs, bound1, P.tc_bhabs)) : scale_for(bound1);
+          const float inv_last = pow2_inverse(s_last) * P.tc_inv_sw_last;
+          mbar_wait_guarded(v.done, done_parity);
           fence_after();
           float dv[kMaxD];
-          const float inv_last = F16 ? 1.f / (s_act * P.tc_sw_last) : 1.f;
-          const float cross_scale = F16 ? (1.f / 2048.f) : 1.f;
-          if (NL == 16) last_epilogue<16>(P, W, taddr, u7, row, x, dv, cross_scale, inv_last);
-          else last_epilogue<32>(P, W, taddr, u7, row, x, dv, cross_scale, inv_last);
+          if (NL == 16) last_epilogue<16>(P, W, v.taddr, u7, row, x, dv, cross_scale, inv_last);
+          else last_epilogue<32>(P, W, v.taddr, u7, row, x, dv, cross_scale, inv_last);
           if (W.op == OP_COEF || W.op == OP_DERIV) continue;
           float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
           if (cons) {
-            flux[x] = r;
+            v.flux[x] = r;
             team_sync(team, N);
-            const float fwd = flux[x + 1 == N ? 0 : x + 1];
+            const float fwd = v.flux[x + 1 == N ? 0 : x + 1];
             r = -__fmul_rn(P.inv_dx, __fsub_rn(fwd, r));
           }
           if (forced) {
             float f = 0.f;
             for (int m = 0; m < P.M; ++m) {
-              f = fmaf(fs[s * kForcingStride + m], __ldg(P.fbasis + (size_t)m * N + x), f);
-              f = fmaf(fs[s * kForcingStride + P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
+              f = fmaf(v.fs[s * kForcingStride + m], __ldg(P.fbasis + (size_t)m * N + x), f);
+              f = fmaf(v.fs[s * kForcingStride + P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
             }
             r = __fadd_rn(r, f);
           }
@@ -652,32 +711,40 @@ __global__ void __launch_bounds__(512, 1) tc_row_kernel(const __grid_constant__ 
             if (W.out64) W.out64[(size_t)row * N + x] = (double)r;
             else W.out[(size_t)row * N + x] = r;
           } else {
-            kst[s * N + x] = r;
+            k_s[sl][s] = r;
           }
         }
-        if (W.op != OP_INTEGRATE) continue;
+        done_parity ^= 1u;
+        stage_par ^= 1u;
+      }
+      if (W.op != OP_INTEGRATE) continue;
+      const bool save = ((step + 1) % W.save_every) == 0;
+      for (int sl = 0; sl < nslots; ++sl) {
+        const SlotView v = view(sl);
+        const int row = row0 + sl * total_teams;
         double accd = 0.0;
 #pragma unroll
         for (int j = 0; j < kMaxStages; ++j)
-          if (j < tab.stages && tab.b[j] != 0.0) accd += tab.b[j] * (double)kst[j * N + x];
-        y = y + W.dt * accd;
-        if (first_bad < 0 && !isfinite(y)) first_bad = step;
-        if (((step + 1) % W.save_every) == 0) {
-          W.snaps[((size_t)save_idx * W.batch + row) * N + x] = (float)y;
-          ++save_idx;
-        }
+          if (j < tab.stages && tab.b[j] != 0.0) accd += tab.b[j] * (double)k_s[sl][j];
+        const double y = y_s[sl] + W.dt * accd;
+        y_s[sl] = y;
+        if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
+          atomicMin(reinterpret_cast<unsigned int*>(v.fs + kMaxStages * kForcingStride), (unsigned int)step);
+        if (save) W.snaps[((size_t)save_idx * W.batch + row) * N + x] = (float)y;
       }
-      if (W.op == OP_INTEGRATE && W.first_bad) {
-        unsigned int* slot = reinterpret_cast<unsigned int*>(fs + kMaxStages * kForcingStride);
-        if (x == 0) *slot = 0xffffffffu;
-        team_sync(team, N);
-        atomicMin(slot, first_bad < 0 ? 0xffffffffu : (unsigned int)first_bad);
-        team_sync(team, N);
-        if (x == 0) W.first_bad[row] = (*slot == 0xffffffffu) ? -1 : (int)*slot;
-        team_sync(team, N);
+      if (save) ++save_idx;
+    }
+    if (W.op == OP_INTEGRATE && W.first_bad) {
+      team_sync(team, N);
+      for (int sl = 0; sl < nslots; ++sl) {
+        const SlotView v = view(sl);
+        const unsigned int fb = *reinterpret_cast<unsigned int*>(v.fs + kMaxStages * kForcingStride);
+        if (x == 0) W.first_bad[row0 + sl * total_teams] = (fb == 0xffffffffu) ? -1 : (int)fb;
       }
     }
+    team_sync(team, N);       // the next rows reuse the slot regions
   }
+  }   // row teams
   fence_before();
   __syncthreads();
   fence_after();
@@ -723,7 +790,7 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
   const uint32_t tmem_base = *slot;
   if (warp == 4) {
     const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    issue_layer<false>(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_cat), 2u * (uint32_t)nout * 16u, 0, base_u,
+    issue_layer<false, true>(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_cat), 2u * (uint32_t)nout * 16u, 0, base_u,
                 nout);
     if (elect_one()) mma_commit(bar);
     __syncwarp();
@@ -831,6 +898,157 @@ __global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, long long* __
     __syncwarp();
     mbar_wait_guarded(bar, 0);
     if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Overlap experiment: warp 0 streams fp16 MMAs (M128 N64 K16 + M128 N32 K16 per step, operands in shared
+// memory, the production hidden-layer step) while warps 4..7 run a CUDA-core workload:
+//   work 0 nothing, 1 FFMA chain, 2 STS.128 + LDS.128, 3 packed fp16 conversions, 4 tcgen05.ld, 5 SHFL,
+//        6 LDG (L1-resident), 7 LDS.128 only, 8 STS.128 only, 9 mbarrier arrive + wait, 10 bar.sync,
+//        11 STS + fence.proxy.async, 12 tcgen05 fences, 13 plane store + fence + mbarrier round
+// mode bit 0 = run the MMAs, bits 1.. = work.  cycles[2*b] = MMA stream, cycles[2*b+1] = CUDA stream.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) tc_overlap_kernel(int reps, int mode, int iters,
+                                                            long long* __restrict__ cycles, float* __restrict__ sink) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t plane_bytes = 260u * 16u, b_plane_bytes = 64u * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned char* a_0 = smem_raw + 128;
+  unsigned char* a_1 = a_0 + 4 * plane_bytes;
+  unsigned char* b_cat = a_1 + 4 * plane_bytes;
+  unsigned char* scratch = b_cat + kTaps * 4 * b_plane_bytes;       // 4 warps x 32 lanes x 16 B x 4
+  const uint32_t init_words = (2 * 4 * plane_bytes + kTaps * 4 * b_plane_bytes + 8192) / 4;
+  for (uint32_t i = tid; i < init_words; i += blockDim.x) reinterpret_cast<uint32_t*>(a_0)[i] = 0x3c003c00u + (i & 63u);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    for (int w = 0; w < 4; ++w) mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 32) + w, 32);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  const bool run_mma = mode & 1;
+  const int work = mode >> 1;
+  if (warp == 0 && run_mma) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
+    const uint32_t a00 = ((smem_u32(a_0) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t a10 = ((smem_u32(a_1) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t b0 = ((smem_u32(b_cat) >> 4) & 0x3FFFu) | (bplane16 << 16);
+    const uint32_t id1 = instr_desc_f16(128, 64), id2 = instr_desc_f16(128, 32);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+            const uint32_t bo = (uint32_t)(k * 4 + 2 * kb) * bplane16;
+            mma_f16_split(base_u + 256u, a00 + ao, b0 + bo, desc_hi, id1, 1u);
+            mma_f16_split(base_u + 288u, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+    mbar_wait_guarded(bar, 0);
+    if (tid == 0) cycles[2 * blockIdx.x] = clock64() - t0;
+  }
+  if (warp >= 4 && work > 0) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (float)(lane + i);
+    uint4* mine = reinterpret_cast<uint4*>(scratch) + (warp - 4) * 128 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (work == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], 1.0001f, 0.5f);
+      } else if (work == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v = mine[j * 32];
+          v.x += (uint32_t)it;
+          mine[j * 32] = v;
+        }
+      } else if (work == 3) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            uint32_t hi, lo;
+            split_half2(acc[i], acc[i + 1], hi, lo);
+            acc[i] += __uint_as_float(hi & 0x3fffffu);
+            acc[i + 1] += __uint_as_float(lo & 0x3fffffu);
+          }
+      } else if (work == 4) {
+        uint32_t r[16];
+        tmem_ld16_issue(taddr + (uint32_t)((it & 7) * 16), r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(r[i]) + __uint_as_float(r[i + 8]);
+      } else if (work == 5) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], 1);
+      } else if (work == 6) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += __ldg(sink + 256 + ((it + j * 32 + lane) & 1023));
+      } else if (work == 7) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 v = mine[j * 32];
+          acc[j] += __uint_as_float(v.x & 0x3fffffu);
+        }
+      } else if (work == 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine[j * 32] = make_uint4((uint32_t)it, 0u, 0u, 0u);
+      } else if (work == 9) {
+        // mbarrier round: every lane arrives on the warp's own barrier, then waits for the phase
+        uint64_t* wb = reinterpret_cast<uint64_t*>(smem_raw + 32) + (warp - 4);
+        mbar_arrive(wb);
+        mbar_wait_guarded(wb, (uint32_t)(it & 1));
+      } else if (work == 10) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1) : "memory");     // named barrier among warps 4..7
+      } else if (work == 11) {
+        mine[0] = make_uint4((uint32_t)it, 0u, 0u, 0u);
+        fence_async_smem();                                        // generic -> async proxy fence after a store
+      } else if (work == 12) {
+        fence_before();
+        fence_after();
+      } else {
+        // plane store as the row kernel does it: 8 STS.128 into a [chunk][pos] plane + fence + mbarrier arrive
+        uint4* plane = reinterpret_cast<uint4*>(scratch);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) plane[j * 128 + (warp - 4) * 32 + lane] = make_uint4((uint32_t)it, 1u, 2u, 3u);
+        fence_async_smem();
+        uint64_t* wb = reinterpret_cast<uint64_t*>(smem_raw + 32) + (warp - 4);
+        mbar_arrive(wb);
+        mbar_wait_guarded(wb, (uint32_t)(it & 1));
+      }
+    }
+    const long long t1 = clock64();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += acc[i];
+    if (sum == 1.2345f) sink[tid] = sum;
+    if (tid == 128) cycles[2 * blockIdx.x + 1] = t1 - t0;
   }
   fence_before();
   __syncthreads();

@@ -14,6 +14,12 @@ int ddd1d_debug_tc_probe(int device, const float* x, const float* w_cat, float* 
 /* MMA issue-rate microbenchmark: `blocks` CTAs each issue reps x 20 (tap, ci-block) steps of the
  * tensor engine's MMA pattern (mode: see csrc/ddd1d_tc.cuh) and report the clocks until completion. */
 int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long* cycles_host);
+/* Tensor-pipe / CUDA-core overlap experiment: warp 0 streams reps x 10 fp16 MMA steps (hidden-layer shape)
+ * while warps 4..7 run `iters` rounds of a CUDA-core workload.  mode bit 0 = run the MMAs; mode >> 1 =
+ * workload (0 none, 1 FFMA, 2 STS.128 + LDS.128, 3 packed fp16 splits, 4 tcgen05.ld, 5 SHFL, 6 LDG,
+ * 7 LDS.128, 8 STS.128).
+ * cycles_host[2*b] = clocks of the MMA stream, cycles_host[2*b + 1] = clocks of the CUDA-core stream. */
+int ddd1d_debug_tc_overlap(int device, int mode, int reps, int iters, int blocks, long long* cycles_host);
 #ifdef __cplusplus
 }
 #endif
