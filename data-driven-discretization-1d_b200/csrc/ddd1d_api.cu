@@ -278,7 +278,7 @@ int finalize_tc(ddd1d_handle* h) {
     f += 2 * 2 * (N + 2 * kHalo + 2);                       // (raw row + row / sigma) x stage parity
     P.tc_sc_umax = f; f += 2 * 16;                          // per-warp max |u / sigma| x stage parity
     P.tc_sc_flux = f; f += N;
-    P.tc_sc_fs = f; f += kMaxStages * tc::kForcingStride + 4;   // forcing scratch + first-bad-step word
+    P.tc_sc_fs = f; f += 2 * kMaxStages * tc::kForcingStride + 4;   // forcing amplitudes x step parity + first-bad-step word
     P.tc_sc_stride = align_up(f, 32);
   }
   P.off_bar = 0;                            // 1 + 2 * (teams * slots) <= 17 mbarriers

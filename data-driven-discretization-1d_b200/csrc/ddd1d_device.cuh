@@ -503,6 +503,34 @@ __device__ __forceinline__ void forcing_reduce(const Params& P, float* fs, int j
   }
 }
 
+// Warp-wide version: lane q holds term q (terms beyond 32 in further rounds); the amplitude of mode m is the
+// warp sum of the terms with |k| == m.  Writes fs[0..M) (sine) and fs[M..2M) (cosine).
+__device__ __forceinline__ void forcing_amplitudes(const Params& P, float* fs, int sample, float t, int lane) {
+  float ps[kMaxModes], pc[kMaxModes];
+#pragma unroll
+  for (int m = 0; m < kMaxModes; ++m) ps[m] = pc[m] = 0.f;
+  for (int q = lane; q < P.P; q += 32) {
+    const ForcingTerm f = load_forcing_term(P, sample, q);
+    float sn, cs;
+    sincosf(fmaf(f.w, t, f.phi), &sn, &cs);
+    const float a_sin = f.a * sn, a_cos = (f.k < 0.f ? -f.a : f.a) * cs, ka = fabsf(f.k);
+#pragma unroll
+    for (int m = 0; m < kMaxModes; ++m)
+      if (ka == (float)(m + 1)) { ps[m] += a_sin; pc[m] += a_cos; }
+  }
+#pragma unroll
+  for (int m = 0; m < kMaxModes; ++m) {
+    if (m >= P.M) break;
+    float a = ps[m], b = pc[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { fs[m] = a; fs[P.M + m] = b; }
+  }
+}
+
 __device__ __forceinline__ float forcing_at(const Params& P, const Smem& S, int p) {
   float f = 0.f;
   for (int m = 0; m < P.M; ++m) {

@@ -131,10 +131,10 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspends up to the hint (ns)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     if (done) return;
     if ((++spins & 1023u) == 0) {
@@ -437,10 +437,8 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
-    for (int t = 0; t < TS; ++t) {
-      mbar_init(&bars[1 + t], (uint32_t)N);          // "planes stored" : every thread of the team arrives
-      mbar_init(&bars[1 + TS + t], 1);               // "MMAs done"     : tcgen05.commit arrives
-    }
+    for (int t = 0; t < TS; ++t) mbar_init(&bars[1 + t], (uint32_t)N);      // "planes stored": every thread of the team arrives
+    for (int t = 0; t < TS * tiles; ++t) mbar_init(&bars[1 + TS + t], 1);    // "tile's MMAs done": tcgen05.commit arrives
     mbar_fence_init();
   }
   __syncthreads();
@@ -480,6 +478,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     long long start = 0;
     uint32_t idle = 0;
     while (total > 0) {
+      bool any = false;
       for (int ts = 0; ts < TS; ++ts) {
         if (remaining[ts] == 0) continue;
         // every thread of the slot's team has stored its planes (all lanes acquire)
@@ -493,6 +492,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
         }
         idle = 0;
         start = 0;
+        any = true;
         fence_after();
         const uint32_t slot_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)ts * (uint32_t)P.tc_team_stride;
         const uint32_t act_hi_s = slot_s + (uint32_t)P.tc_t_act_hi, act_lo_s = slot_s + (uint32_t)P.tc_t_act_lo;
@@ -502,21 +502,31 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           // timing experiment: no MMAs
         } else if (layer_idx != hidden_tc_layers) {
           const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
-          for (int m = 0; m < tiles; ++m)
+          for (int m = 0; m < tiles; ++m) {       // one commit per tile: its threads start their epilogue early
             issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m,
                                      d_col0 + (uint32_t)m * 64u, 32);
+            if (!(P.tc_debug & 8) && elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
+            __syncwarp();
+          }
         } else {
-          for (int m = 0; m < tiles; ++m)
+          for (int m = 0; m < tiles; ++m) {
             issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
                                      2u * (uint32_t)NL * 16u, m, d_col0 + (uint32_t)m * 64u, NL);
+            if (!(P.tc_debug & 8) && elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
+            __syncwarp();
+          }
         }
-        if (elect_one()) mma_commit(&bars[1 + TS + ts]);
-        __syncwarp();
+        if (P.tc_debug & 9) {
+          for (int m = 0; m < tiles; ++m)
+            if (elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
+          __syncwarp();
+        }
         parity[ts] ^= 1u;
         layer[ts] = layer_idx == hidden_tc_layers ? 0 : layer_idx + 1;
         remaining[ts] -= 1;
         total -= 1;
       }
+      if (!any && !(P.tc_debug & 4)) __nanosleep(32);      // nothing ready: leave the issue slots to the row teams
     }
   } else {
   // ---------------- row teams ----------------
@@ -536,9 +546,16 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     unsigned char *act_hi, *act_lo;      // shared memory (written with STS, read by the tensor pipe)
     float *ust, *unr, *flux, *fs;        // global scratch
     uint32_t* umax_w;
-    uint64_t *req, *done;
+    uint64_t *req, *done, *done_nb;
     uint32_t taddr;
   };
+  // MMAs complete tile by tile.  A tile's MMAs also read two positions of each neighbouring tile (and the
+  // periodic halo copies), so the first / last warp of a tile must see the neighbouring tile's MMAs complete
+  // as well before it overwrites its planes; the inner warps only depend on their own tile.
+  const int warp_in_tile = warp_in_team & 3;
+  const int nb_tile = tiles == 1 ? -1
+                      : warp_in_tile == 0 ? (tile + tiles - 1) % tiles
+                      : warp_in_tile == 3 ? (tile + 1) % tiles : -1;
   // The stage row (raw, normalised) and its warp maxima are double-buffered on the stage parity: phase 2
   // of stage s reads them while a faster warp may already be writing stage s+1 (phase 0).
   uint32_t stage_par = 0;
@@ -555,14 +572,17 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     v.flux = sc + P.tc_sc_flux;
     v.fs = sc + P.tc_sc_fs;
     v.req = &bars[1 + ts];
-    v.done = &bars[1 + TS + ts];
+    v.done = &bars[1 + TS + ts * tiles + tile];
+    v.done_nb = nb_tile >= 0 ? &bars[1 + TS + ts * tiles + nb_tile] : nullptr;
     v.taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((ts * tiles + tile) * 64);
     return v;
   };
   // scale of the planes written by phase 0 / phase 1 and the bound behind it (team-uniform, recomputed)
+  // (the maximum is accumulated with atomics, which are performed in L2: read it past L1; the word of the
+  //  other stage parity is cleared for its next use)
   auto first_bound = [&](const SlotView& v) {
-    uint32_t m = 0;
-    for (int w = 0; w < team_warps; ++w) m = max(m, v.umax_w[w]);
+    const uint32_t m = __ldcg(v.umax_w);
+    if (x == 0) v.umax_w[stage_par ? -16 : 16] = 0u;
     return fmaf(P.tc_w1abs, __uint_as_float(m), P.tc_b1abs);      // |h1| <= |b1| + sum|W1| * max|u/sigma|
   };
 
@@ -580,8 +600,13 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
       ++nslots;
       const SlotView v = view(sl);
       y_s[sl] = W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
-      if (x == 0) *reinterpret_cast<unsigned int*>(v.fs + kMaxStages * kForcingStride) = 0xffffffffu;
+      if (x == 0) {
+        *reinterpret_cast<unsigned int*>(v.fs + 2 * kMaxStages * kForcingStride) = 0xffffffffu;
+        v.umax_w[0] = 0u;                            // both stage parities: results must not depend on history
+        v.umax_w[stage_par ? -16 : 16] = 0u;
+      }
     }
+    team_sync(team, N);
     int save_idx = 0;
     for (int step = 0; step < nsteps; ++step) {
       const double t0 = W.t0 + (double)step * W.dt;
@@ -603,23 +628,20 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           v.unr[x + kHalo] = usn;
           {      // row maximum of |u / sigma| for the activation bounds; rides on the stage barrier
             const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(usn)));
-            if (lane == 0) v.umax_w[warp_in_team] = wmax;
+            if (lane == 0) atomicMax(v.umax_w, wmax);
           }
           if (edge) {
             if (x < kHalo) { v.ust[x + kHalo + N] = us; v.unr[x + kHalo + N] = usn; }
             if (x >= N - kHalo) { v.ust[x + kHalo - N] = us; v.unr[x + kHalo - N] = usn; }
           }
-          if (forced && s == 0) {
-            // the sincos of every stage of this step, spread over nstages * P threads
-            const int sq = x / P.P, q = x - sq * P.P;
-            if (sq < nstages) {
-              const ForcingTerm fq = load_forcing_term(P, sample, q);
-              const float ts = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[sq] * W.dt : W.t0);
-              forcing_terms(P, v.fs + sq * kForcingStride, fq, q, ts);
-            }
+          if (forced && s == 0 && warp_in_team < nstages) {
+            // warp sq prepares stage sq of this step: one forcing term per lane, mode amplitudes by warp sums
+            const int sq = warp_in_team;
+            const float ts = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[sq] * W.dt : W.t0);
+            // (double-buffered on the step parity: slower warps may still be reading the previous step's)
+            forcing_amplitudes(P, v.fs + ((step & 1) * kMaxStages + sq) * kForcingStride, sample, ts, lane);
           }
           team_sync(team, N);
-          if (forced) forcing_reduce(P, v.fs + s * kForcingStride, x);   // visible after the barriers below
           const float bound1 = first_bound(v);
           bound_s[sl] = bound1;
           const float s_act = scale_for(bound1);
@@ -661,6 +683,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
             const float bound1 = bound_s[sl];
             const float inv = pow2_inverse(scale_for(bound1)) * P.tc_inv_sw_hid;
             const float s_act = scale_for(fmaf(P.tc_whabs, bound1, P.tc_bhabs));   // |h2| <= |b2| + sum|W2| max|h1|
+            if (v.done_nb) mbar_wait_guarded(v.done_nb, done_parity);
 #pragma unroll
             for (int c8 = 0; c8 < kChunks / 2; ++c8) {
               float h[8];
@@ -687,6 +710,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           const float s_last = hidden_tc_layers > 0 ? scale_for(fmaf(P.tc_whabs, bound1, P.tc_bhabs)) : scale_for(bound1);
           const float inv_last = pow2_inverse(s_last) * P.tc_inv_sw_last;
           mbar_wait_guarded(v.done, done_parity);
+          if (v.done_nb) mbar_wait_guarded(v.done_nb, done_parity);     // before the next stage rewrites the planes
           fence_after();
           float dv[kMaxD];
           if (NL == 16) last_epilogue<16>(P, W, v.taddr, u7, row, x, dv, cross_scale, inv_last);
@@ -702,8 +726,8 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           if (forced) {
             float f = 0.f;
             for (int m = 0; m < P.M; ++m) {
-              f = fmaf(v.fs[s * kForcingStride + m], __ldg(P.fbasis + (size_t)m * N + x), f);
-              f = fmaf(v.fs[s * kForcingStride + P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
+              f = fmaf(v.fs[((step & 1) * kMaxStages + s) * kForcingStride + m], __ldg(P.fbasis + (size_t)m * N + x), f);
+              f = fmaf(v.fs[((step & 1) * kMaxStages + s) * kForcingStride + P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
             }
             r = __fadd_rn(r, f);
           }
@@ -729,7 +753,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
         const double y = y_s[sl] + W.dt * accd;
         y_s[sl] = y;
         if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
-          atomicMin(reinterpret_cast<unsigned int*>(v.fs + kMaxStages * kForcingStride), (unsigned int)step);
+          atomicMin(reinterpret_cast<unsigned int*>(v.fs + 2 * kMaxStages * kForcingStride), (unsigned int)step);
         if (save) W.snaps[((size_t)save_idx * W.batch + row) * N + x] = (float)y;
       }
       if (save) ++save_idx;
@@ -738,7 +762,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
       team_sync(team, N);
       for (int sl = 0; sl < nslots; ++sl) {
         const SlotView v = view(sl);
-        const unsigned int fb = *reinterpret_cast<unsigned int*>(v.fs + kMaxStages * kForcingStride);
+        const unsigned int fb = *reinterpret_cast<unsigned int*>(v.fs + 2 * kMaxStages * kForcingStride);
         if (x == 0) W.first_bad[row0 + sl * total_teams] = (fb == 0xffffffffu) ? -1 : (int)fb;
       }
     }
