@@ -263,7 +263,7 @@ def workload_config(args, batch):
       'parallelism': 'batch-sharded x%d, no data-path collective' % args.gpus,
       'l2': 'flushed between timed steps (256 MiB write)',
       'weights': 'seeded Glorot-uniform, last layer x1e-2, zero biases (random init of the reference architecture)',
-      'arithmetic': 'float32 state I/O, float64 RK accumulation; conv stack FP32 FFMA or 3xTF32 tensor (FP32-faithful, tests/test_gpu_tensor.py)',
+      'arithmetic': 'float32 state I/O, float64 RK accumulation; conv stack FP32 FFMA, or tcgen05 kind::f16 on fp16 hi/lo planes with FP32 accumulate (FP32-faithful, tests/test_gpu_tensor.py)',
   }
 
 
@@ -388,13 +388,15 @@ def run_ours(args):
   hbm['traffic'] = traffic
   achieved_tf = fl * gps_kernel / 1e12
   if engine == 'tensor':
-    tf32_peak = peaks['bf16_tflops_sustained' if 'bf16_tflops_sustained' in peaks else 'bf16_tflops'] / 2.0
-    roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / tf32_peak, 'traffic': traffic, 'peak_kind': peak_kind,
-                'note': 'achieved = algorithmic FP32-equivalent FLOPs (%d per grid-point-step); peak = dense TF32 = '
-                        'half of the measured sustained bf16 cuBLAS rate.  The 3xTF32 split executes 3x the conv '
-                        'FLOPs on the tensor pipe, and each M128xN32xK8 MMA reads ~5 KB of shared-memory operands '
-                        'for 16 clk of math: the kernel is shared-memory-operand bound (profiles/r01)' % fl}
+    # the conv stack runs as kind::f16 MMAs (fp16 hi/lo planes, FP32 accumulate): the dense f16/bf16 rate is the peak
+    f16_peak = peaks['bf16_tflops_sustained' if 'bf16_tflops_sustained' in peaks else 'bf16_tflops']
+    roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': f16_peak, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / f16_peak, 'traffic': traffic, 'peak_kind': peak_kind,
+                'note': 'achieved = algorithmic FP32-equivalent FLOPs (%d per grid-point-step); peak = measured sustained '
+                        'dense bf16/f16 cuBLAS rate.  The FP32-faithful fp16 hi/lo split executes 3x the conv FLOPs on '
+                        'the tensor pipe (hi*Wh, hi*Wl, lo*Wh) at N padded to 32/16, and each M128xK16 MMA streams its '
+                        'A operand from shared memory: the skinny implicit GEMM is shared-memory-operand bound, not '
+                        'math bound (profiles/r01/README.md)' % fl}
   else:
     roofline = dict(hbm)
   roofline.update({'kernel': kernel_name, 'kernel_ms': kernel_ms})

@@ -59,6 +59,7 @@ struct ddd1d_handle {
   bool tc_ok = false;
   std::string tc_why;
   float* d_blob_tc = nullptr;
+  long long* d_trace_tc = nullptr; // debug event trace (DDD1D_TC_TRACE)
   float* d_scratch_tc = nullptr;   // tensor engine: per-CTA exchange scratch (stage rows, maxima, flux, forcing)
   int tc_threads = 0;
   // staging for the *_host entry points
@@ -185,7 +186,7 @@ int finalize_tc(ddd1d_handle* h) {
     const float v = (float)(w * sw);
     const __half hi = __float2half_rn(v);
     hp[(size_t)col * 8 + (ci % 8)] = hi;
-    hp[(size_t)(nb + col) * 8 + (ci % 8)] = __float2half_rn((v - __half2float(hi)) * 2048.f);
+    hp[(size_t)(nb + col) * 8 + (ci % 8)] = __float2half_rn((v - __half2float(hi)) * tc::kLoScale);
   };
   // first layer [5][32] + bias
   const HostLayer& l0 = h->layers[0];
@@ -276,9 +277,9 @@ int finalize_tc(ddd1d_handle* h) {
   {
     int f = 0;
     f += 2 * 2 * (N + 2 * kHalo + 2);                       // (raw row + row / sigma) x stage parity
-    P.tc_sc_umax = f; f += 2 * 16;                          // per-warp max |u / sigma| x stage parity
+    P.tc_sc_umax = f; f += 16;                              // row maximum of |u / sigma| (calibration only)
     P.tc_sc_flux = f; f += N;
-    P.tc_sc_fs = f; f += 2 * kMaxStages * tc::kForcingStride + 4;   // forcing amplitudes x step parity + first-bad-step word
+    P.tc_sc_fs = f; f += tc::kFsWords + 4;                  // forcing amplitude sets + first-bad-step word
     P.tc_sc_stride = align_up(f, 32);
   }
   P.off_bar = 0;                            // 1 + 2 * (teams * slots) <= 17 mbarriers
@@ -309,6 +310,11 @@ int finalize_tc(ddd1d_handle* h) {
   CUDA_TRY(h, cudaMalloc(&h->d_scratch_tc, scratch_floats * sizeof(float)));
   CUDA_TRY(h, cudaMemset(h->d_scratch_tc, 0, scratch_floats * sizeof(float)));
   P.tc_scratch = h->d_scratch_tc;
+  P.tc_trace = nullptr;
+  if (getenv("DDD1D_TC_TRACE")) {       // debug: [8 streams][kTraceCap] (tag << 48 | clock) records of CTA 0
+    if (!h->d_trace_tc) CUDA_TRY(h, cudaMalloc(&h->d_trace_tc, sizeof(long long) * 8 * tc::kTraceCap));
+    P.tc_trace = h->d_trace_tc;
+  }
   const void* kern = (const void*)tc::tc_row_kernel;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
   h->tc_threads = P.tc_teams * N + 32;       // thread <-> grid point, plus the warp that issues the MMAs
@@ -531,8 +537,18 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     const Params& T = h->Ptc;
     const int teams_needed = (W.batch + T.tc_teams - 1) / T.tc_teams;
     const int grid_tc = std::min(teams_needed, h->num_sms);
+    if (T.tc_trace) CUDA_TRY(h, cudaMemsetAsync(T.tc_trace, 0, sizeof(long long) * 8 * tc::kTraceCap, st));
     tc::tc_row_kernel<<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W, make_tableau(W.scheme));
     CUDA_TRY(h, cudaGetLastError());
+    if (T.tc_trace) {                    // debug only: synchronous dump of the last launch's trace
+      std::vector<long long> host((size_t)8 * tc::kTraceCap);
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      CUDA_TRY(h, cudaMemcpy(host.data(), T.tc_trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(getenv("DDD1D_TC_TRACE"), "wb")) {
+        fwrite(host.data(), sizeof(long long), host.size(), f);
+        fclose(f);
+      }
+    }
     h->launches += 1;
     return DDD1D_OK;
   }
@@ -570,12 +586,12 @@ int ensure_stage(ddd1d_handle* h, void** buf, size_t* have, size_t need) {
 }  // namespace
 
 namespace {
-template <int KIND, int N1, int N2, int BROWS, int ALT>
+template <int KIND, int N1, int N2, int BROWS, int ALT, int DOFF2 = 128>
 int run_rate(int reps, int blocks, long long* d) {
   const int smem = 128 + 2 * tc::kChunks * 516 * 16 + tc::kTaps * tc::kChunks * BROWS * 16;
-  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT>,
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT, DOFF2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT><<<blocks, 128, smem>>>(reps, d);
+  tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT, DOFF2><<<blocks, 128, smem>>>(reps, d);
   CUDA_TRY(nullptr, cudaGetLastError());
   return DDD1D_OK;
 }
@@ -642,6 +658,7 @@ int ddd1d_destroy(ddd1d_handle* h) {
   cudaFree(h->d_blob);
   cudaFree(h->d_blob_tc);
   cudaFree(h->d_scratch_tc);
+  cudaFree(h->d_trace_tc);
   cudaFree(h->d_fparams);
   cudaFree(h->d_fbasis);
   cudaFree(h->d_fparams64);
@@ -937,6 +954,10 @@ int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long
     case 11: rc = run_rate<1, 96, 0, 96, 1>(reps, blocks, d); break;
     case 12: rc = run_rate<1, 96, 64, 96, 1>(reps, blocks, d); break;  // bf16x3 first two of a step
     case 13: rc = run_rate<1, 128, 0, 128, 1>(reps, blocks, d); break;
+    case 14: rc = run_rate<1, 64, 32, 64, 0, 128>(reps, blocks, d); break;  // f16 hidden step, separate accumulators
+    case 15: rc = run_rate<1, 64, 32, 64, 0, 32>(reps, blocks, d); break;   // f16 hidden step, production D overlap
+    case 16: rc = run_rate<1, 32, 16, 32, 0, 16>(reps, blocks, d); break;   // f16 last step, production D overlap
+    case 17: rc = run_rate<1, 96, 0, 96, 0>(reps, blocks, d); break;        // one MMA per step, N = 96
     default: return fail(nullptr, DDD1D_EINVAL, "unknown variant");
   }
   if (rc) return rc;

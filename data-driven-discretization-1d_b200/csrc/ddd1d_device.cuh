@@ -68,6 +68,7 @@ struct Params {
   int tc_teams, tc_nlast, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
   int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
   int tc_t_act_hi, tc_t_act_lo;   // byte offsets of the activation planes inside a slot's shared region
+  long long* tc_trace;            // debug: clock64 event trace of CTA 0 (DDD1D_TC_TRACE=<file>), else null
   float* tc_scratch;              // global scratch [grid][teams * slots][tc_sc_stride] floats (L1 / L2 resident)
   int tc_sc_stride, tc_sc_umax, tc_sc_flux, tc_sc_fs;   // float offsets inside a slot's scratch
   int tc_slots;             // rows in flight per team (their CUDA-core and tensor phases interleave)

@@ -34,7 +34,10 @@ namespace tc {
 constexpr int kF = 32;             // hidden width this path is built for
 constexpr int kTaps = 5;
 constexpr int kChunks = kF / 4;    // 16-byte chunks along ci
-constexpr int kForcingStride = 2 * kMaxModes + 3 * kMaxForcing;   // floats of forcing scratch per RK stage
+constexpr int kFsStride = 2 * kMaxModes;     // forcing mode amplitudes per RK stage (sine | cosine)
+constexpr int kFsBuffers = 3;                // amplitude sets in rotation: written one step ahead of their use
+constexpr int kFsWords = kFsBuffers * kMaxStages * kFsStride;     // + 1 word: first non-finite step of the row
+constexpr int kTraceCap = 8192;     // debug trace records per stream
 constexpr long long kSpinCycles = 4000000000ll;   // ~2 s at 1.9 GHz: a protocol bug traps instead of hanging
 
 // ---- descriptors -------------------------------------------------------------------------------
@@ -144,11 +147,32 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity
     }
   }
 }
+// debug event trace: (tag << 48 | clock64) records, one stream per traced thread (null = off)
+#ifdef DDD1D_TRACE
+__device__ __forceinline__ void trace_ev(long long* base, int& n, int tag) {
+  if (base && n < kTraceCap) base[n++] = ((long long)tag << 48) | (clock64() & 0xffffffffffffll);
+}
+#else
+#define trace_ev(base, n, tag) ((void)0)
+#endif
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void team_sync(int team, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(threads) : "memory");
+}
+// the same barrier carrying a vote: true iff `ok` holds on every thread of the team
+__device__ __forceinline__ bool team_sync_all(int team, int threads, bool ok) {
+  uint32_t all;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "barrier.cta.red.and.pred q, %1, %2, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t}"
+      : "=r"(all)
+      : "r"(team + 1), "r"(threads), "r"((uint32_t)ok)
+      : "memory");
+  return all != 0;
 }
 
 // x = hi + lo with hi = x rounded to TF32 (round-half-up on the magnitude) and lo = the exact
@@ -256,14 +280,19 @@ __device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, ui
 }
 
 // ---- fp16 x 2 planes -----------------------------------------------------------------------------
-// v (already multiplied by the layer's power-of-two scale) = hi + lo' * 2^-11 with hi = fp16(v) and
-// lo' = fp16((v - hi) * 2^11): 22 significant bits like the 3xTF32 split, but 2 bytes per element, so one
-// 4 KB A read covers K = 16.  Static bounds on the activations (operator norms x the row's max |u/sigma|)
-// keep v below 2^14, far from fp16's range limits; scales are powers of two, i.e. exact.
+// v (already multiplied by the layer's power-of-two scale) = hi + lo with hi = fp16(v) and
+// lo = fp16(v - hi): 22 significant bits like the 3xTF32 split, but 2 bytes per element, so one 4 KB A read
+// covers K = 16.  Static bounds on the activations (operator norms x a verified bound on the row's
+// max |u/sigma|) put the largest v in [2^12, 2^14), far from fp16's range limits; scales are powers of two,
+// i.e. exact.  lo is at most half an ulp of hi; where it falls into fp16's subnormal range (|v| < 2^-3) its
+// absolute error 2^-25 is 2^-37 of the row's bound.  kLoScale = 2048 would keep lo normal everywhere at the
+// price of two more multiplies per pair (the filters' lo rows carry the same factor: ddd1d_api.cu).
+constexpr float kLoScale = 1.f;
 __device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);                  // one packed conversion
   const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a - f.x) * 2048.f, (b - f.y) * 2048.f);   // exact remainder, scaled
+  const __half2 l = kLoScale == 1.f ? __floats2half2_rn(a - f.x, b - f.y)     // exact remainder
+                                    : __floats2half2_rn((a - f.x) * kLoScale, (b - f.y) * kLoScale);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -461,72 +490,74 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
 
   if (warp == R * team_warps) {
     // ---------------- issuer warp ----------------
+    // The tensor pipe's queue is only a few MMAs deep, so the pipe drains (and pays its ~1000 clk start-up
+    // latency again) unless the next layer's first MMA is queued within ~150 clk of the previous layer's last.
+    // Hence the polling is lean: lane l owns slot l's bookkeeping in registers and polls its "planes stored"
+    // barrier, one ballot finds the ready slots, and the oldest-served-first rotation picks one.
     const uint32_t blob_s = smem_s + (uint32_t)P.off_blob;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int remaining[8], layer[8];
-    uint32_t parity[8];
-    int total = 0;
-    for (int ts = 0; ts < TS; ++ts) {
-      const int first = blockIdx.x * R + ts / SLOTS + (ts % SLOTS) * total_teams;      // this slot's first row
+    int my_remaining = 0, my_layer = 0;
+    uint32_t my_parity = 0;
+    if (lane < TS) {
+      const int first = blockIdx.x * R + lane / SLOTS + (lane % SLOTS) * total_teams;      // this slot's first row
       const int stride = SLOTS * total_teams;
       const int rows = first < W.batch ? (W.batch - first + stride - 1) / stride : 0;
-      remaining[ts] = rows * nsteps * nstages * (hidden_tc_layers + 1);
-      layer[ts] = 0;
-      parity[ts] = 0;
-      total += remaining[ts];
+      my_remaining = rows * nsteps * nstages * (hidden_tc_layers + 1);
     }
+    const uint32_t b_hid_s = blob_s + (uint32_t)P.tc_bhid_off * 4u, b_last_s = blob_s + (uint32_t)P.tc_blast_off * 4u;
+    const uint32_t team0_s = smem_s + (uint32_t)P.tc_off_team0;
     long long start = 0;
     uint32_t idle = 0;
-    while (total > 0) {
-      bool any = false;
-      for (int ts = 0; ts < TS; ++ts) {
-        if (remaining[ts] == 0) continue;
-        // every thread of the slot's team has stored its planes (all lanes acquire)
-        if (!__all_sync(0xffffffffu, mbar_test(&bars[1 + ts], parity[ts]))) {
-          if ((++idle & 0xfffu) == 0) {
-            const long long now = clock64();
-            if (start == 0) start = now;
-            else if (now - start > kSpinCycles) asm volatile("trap;");
-          }
-          continue;
+    int next = 0;                                     // rotation: the slot after the one served last goes first
+#ifdef DDD1D_TRACE
+    long long* const tr = (P.tc_trace && blockIdx.x == 0 && lane == 0) ? P.tc_trace + 4 * kTraceCap : nullptr;
+    int trn = 0;
+#endif
+    while (true) {
+      const bool ready = my_remaining > 0 && mbar_test(&bars[1 + lane], my_parity);    // (acquire)
+      const uint32_t mask = __ballot_sync(0xffffffffu, ready);
+      if (mask == 0u) {
+        if (__ballot_sync(0xffffffffu, my_remaining > 0) == 0u) break;
+        if ((++idle & 0xfffu) == 0) {
+          const long long now = clock64();
+          if (start == 0) start = now;
+          else if (now - start > kSpinCycles) asm volatile("trap;");
         }
-        idle = 0;
-        start = 0;
-        any = true;
-        fence_after();
-        const uint32_t slot_s = smem_s + (uint32_t)P.tc_off_team0 + (uint32_t)ts * (uint32_t)P.tc_team_stride;
-        const uint32_t act_hi_s = slot_s + (uint32_t)P.tc_t_act_hi, act_lo_s = slot_s + (uint32_t)P.tc_t_act_lo;
-        const uint32_t d_col0 = tmem_u + (uint32_t)(ts * tiles * 64);
-        const int layer_idx = layer[ts];
-        if (P.tc_debug & 1) {
-          // timing experiment: no MMAs
-        } else if (layer_idx != hidden_tc_layers) {
-          const uint32_t off = (uint32_t)(P.tc_bhid_off + layer_idx * P.tc_bhid_stride) * 4u;
-          for (int m = 0; m < tiles; ++m) {       // one commit per tile: its threads start their epilogue early
-            issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, blob_s + off, 2u * 32u * 16u, m,
-                                     d_col0 + (uint32_t)m * 64u, 32);
-            if (!(P.tc_debug & 8) && elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
-            __syncwarp();
-          }
-        } else {
-          for (int m = 0; m < tiles; ++m) {
-            issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, blob_s + (uint32_t)P.tc_blast_off * 4u,
-                                     2u * (uint32_t)NL * 16u, m, d_col0 + (uint32_t)m * 64u, NL);
-            if (!(P.tc_debug & 8) && elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
-            __syncwarp();
-          }
-        }
-        if (P.tc_debug & 9) {
-          for (int m = 0; m < tiles; ++m)
-            if (elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
+        if (P.tc_debug & 4) __nanosleep(32);
+        continue;
+      }
+      idle = 0;
+      start = 0;
+      const uint32_t rot = (mask >> next) | (mask << ((32 - next) & 31));       // bit i = slot (next + i) % 32
+      const int ts = (next + __ffs((int)rot) - 1) & 31;
+      next = ts + 1 == TS ? 0 : ts + 1;
+      const int layer_idx = __shfl_sync(0xffffffffu, my_layer, ts);
+      trace_ev(tr, trn, ts * 16 + 1);
+      fence_after();
+      const uint32_t slot_s = team0_s + (uint32_t)ts * (uint32_t)P.tc_team_stride;
+      const uint32_t act_hi_s = slot_s + (uint32_t)P.tc_t_act_hi, act_lo_s = slot_s + (uint32_t)P.tc_t_act_lo;
+      const uint32_t d_col0 = tmem_u + (uint32_t)(ts * tiles * 64);
+      const bool last = layer_idx == hidden_tc_layers;
+      if (!(P.tc_debug & 1)) {          // (bit 0: timing experiment without MMAs)
+        const uint32_t b_s = last ? b_last_s : b_hid_s + (uint32_t)(layer_idx * P.tc_bhid_stride) * 4u;
+        const int nb = last ? NL : 32;
+        for (int m = 0; m < tiles; ++m) {       // one commit per tile: its threads start their epilogue early
+          issue_layer<true, false>(act_hi_s, act_lo_s, plane_bytes, b_s, 2u * (uint32_t)nb * 16u, m,
+                                   d_col0 + (uint32_t)m * 64u, nb);
+          if (elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
           __syncwarp();
         }
-        parity[ts] ^= 1u;
-        layer[ts] = layer_idx == hidden_tc_layers ? 0 : layer_idx + 1;
-        remaining[ts] -= 1;
-        total -= 1;
+      } else {
+        for (int m = 0; m < tiles; ++m)
+          if (elect_one()) mma_commit(&bars[1 + TS + ts * tiles + m]);
+        __syncwarp();
       }
-      if (!any && !(P.tc_debug & 4)) __nanosleep(32);      // nothing ready: leave the issue slots to the row teams
+      trace_ev(tr, trn, ts * 16 + 2);
+      if (lane == ts) {
+        my_parity ^= 1u;
+        my_layer = last ? 0 : layer_idx + 1;
+        my_remaining -= 1;
+      }
     }
   } else {
   // ---------------- row teams ----------------
@@ -538,8 +569,13 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
   const bool cons = eq_conservative(P.eq);
   const bool forced_eq = eq_forced(P.eq) && P.P > 0;
   const bool forced = forced_eq && (W.op == OP_RHS || W.op == OP_INTEGRATE);
-  const float cross_scale = 1.f / 2048.f;
+  const float cross_scale = 1.f / kLoScale;
   uint32_t done_parity = 0;
+#ifdef DDD1D_TRACE
+  long long* const tr = (P.tc_trace && blockIdx.x == 0 && (x == 0 || x == N - 1))
+                            ? P.tc_trace + (team + (x == 0 ? 0 : 2)) * kTraceCap : nullptr;
+  int trn = 0;
+#endif
 
   // ---- per-slot views -------------------------------------------------------------------------
   struct SlotView {
@@ -568,7 +604,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     float* sc = P.tc_scratch + ((size_t)blockIdx.x * TS + ts) * P.tc_sc_stride;
     v.ust = sc + stage_par * (uint32_t)(2 * (N + 2 * kHalo + 2));
     v.unr = v.ust + (N + 2 * kHalo + 2);             // the same row divided by sigma
-    v.umax_w = reinterpret_cast<uint32_t*>(sc + P.tc_sc_umax) + stage_par * 16u;
+    v.umax_w = reinterpret_cast<uint32_t*>(sc + P.tc_sc_umax);
     v.flux = sc + P.tc_sc_flux;
     v.fs = sc + P.tc_sc_fs;
     v.req = &bars[1 + ts];
@@ -577,19 +613,26 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     v.taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((ts * tiles + tile) * 64);
     return v;
   };
-  // scale of the planes written by phase 0 / phase 1 and the bound behind it (team-uniform, recomputed)
-  // (the maximum is accumulated with atomics, which are performed in L2: read it past L1; the word of the
-  //  other stage parity is cleared for its next use)
-  auto first_bound = [&](const SlotView& v) {
-    const uint32_t m = __ldcg(v.umax_w);
-    if (x == 0) v.umax_w[stage_par ? -16 : 16] = 0u;
-    return fmaf(P.tc_w1abs, __uint_as_float(m), P.tc_b1abs);      // |h1| <= |b1| + sum|W1| * max|u/sigma|
+  // The fp16 plane scales rest on a bound `umax_s` on the row's max |u / sigma|.  It is fixed when a row
+  // starts (twice the row's maximum) and every stage only VERIFIES it, as a vote carried by the barrier the
+  // stage needs anyway; the slow path -- row maximum by atomics performed in L2, read past L1 -- runs for a
+  // row's first stage and again if a row ever outgrows its bound.  (Reading the maximum every stage put an
+  // L2 round trip on the critical path of every right-hand side.)
+  auto recalibrate = [&](const SlotView& v, float usn) {
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(usn)));
+    if (lane == 0) atomicMax(v.umax_w, wmax);
+    team_sync(team, N);
+    const float m = __uint_as_float(__ldcg(v.umax_w));
+    team_sync(team, N);
+    if (x == 0) *v.umax_w = 0u;                       // next use is at least one barrier away
+    return 2.f * m;
   };
 
   // per-thread state that outlives a phase, indexed by slot (local memory: L1, never LDS)
   double y_s[kMaxSlots];
   float k_s[kMaxSlots][kMaxStages];
   float bound_s[kMaxSlots];
+  float umax_s[kMaxSlots];
 
   const int g = blockIdx.x * R + team;
   for (int row0 = g; row0 < W.batch; row0 += SLOTS * total_teams) {
@@ -601,10 +644,10 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
       const SlotView v = view(sl);
       y_s[sl] = W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
       if (x == 0) {
-        *reinterpret_cast<unsigned int*>(v.fs + 2 * kMaxStages * kForcingStride) = 0xffffffffu;
-        v.umax_w[0] = 0u;                            // both stage parities: results must not depend on history
-        v.umax_w[stage_par ? -16 : 16] = 0u;
+        *reinterpret_cast<unsigned int*>(v.fs + kFsWords) = 0xffffffffu;
+        *v.umax_w = 0u;
       }
+      umax_s[sl] = -1.f;                             // no bound yet: the first stage calibrates
     }
     team_sync(team, N);
     int save_idx = 0;
@@ -615,6 +658,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
 #pragma unroll 1
         for (int sl = 0; sl < nslots; ++sl) {
           const SlotView v = view(sl);
+          trace_ev(tr, trn, sl * 16 + 1);
           const int sample = W.sample_offset + row0 + sl * total_teams;
           // ---- stage value, rounded to float32 (integrate.py:57-60,71) ----
           double accd = 0.0;
@@ -626,24 +670,29 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
           v.ust[x + kHalo] = us;
           v.unr[x + kHalo] = usn;
-          {      // row maximum of |u / sigma| for the activation bounds; rides on the stage barrier
-            const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(usn)));
-            if (lane == 0) atomicMax(v.umax_w, wmax);
-          }
           if (edge) {
             if (x < kHalo) { v.ust[x + kHalo + N] = us; v.unr[x + kHalo + N] = usn; }
             if (x >= N - kHalo) { v.ust[x + kHalo - N] = us; v.unr[x + kHalo - N] = usn; }
           }
-          if (forced && s == 0 && warp_in_team < nstages) {
-            // warp sq prepares stage sq of this step: one forcing term per lane, mode amplitudes by warp sums
+          if (forced && s == 0 && step == 0 && warp_in_team < nstages) {
+            // the first step's amplitudes; later steps get theirs one step ahead, after the planes are stored
             const int sq = warp_in_team;
             const float ts = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[sq] * W.dt : W.t0);
-            // (double-buffered on the step parity: slower warps may still be reading the previous step's)
-            forcing_amplitudes(P, v.fs + ((step & 1) * kMaxStages + sq) * kForcingStride, sample, ts, lane);
+            forcing_amplitudes(P, v.fs + sq * kFsStride, sample, ts, lane);
           }
-          team_sync(team, N);
-          const float bound1 = first_bound(v);
+          trace_ev(tr, trn, sl * 16 + 12);
+          float umax = umax_s[sl];
+          bool keep = team_sync_all(team, N, fabsf(usn) <= umax);    // team-uniform; NaN rows fail every stage
+          if (keep && s == 0 && (step & 15) == 15)                   // now and then: has the row decayed far below
+            keep = !team_sync_all(team, N, fabsf(usn) < umax * (1.f / 256.f));   // its bound (lo planes would thin out)?
+          if (!keep) {
+            umax = recalibrate(v, usn);
+            umax_s[sl] = umax;
+          }
+          trace_ev(tr, trn, sl * 16 + 2);
+          const float bound1 = fmaf(P.tc_w1abs, umax, P.tc_b1abs);   // |h1| <= |b1| + sum|W1| * max|u/sigma|
           bound_s[sl] = bound1;
+          trace_ev(tr, trn, sl * 16 + 13);
           const float s_act = scale_for(bound1);
 
           // ---- first layer 1 -> 32 on the CUDA cores, split and written as A planes ----
@@ -666,6 +715,16 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           }
           fence_async_smem();
           mbar_arrive(v.req);
+          trace_ev(tr, trn, sl * 16 + 3);
+          if (forced && s == 0 && W.op == OP_INTEGRATE && step + 1 < nsteps && warp_in_team < nstages) {
+            // Forcing amplitudes of the NEXT step, off the critical path (the MMAs just requested are running).
+            // Warp sq prepares stage sq: one forcing term per lane, mode amplitudes by warp sums.  Three sets
+            // rotate: set (step + 1) % 3 was last read in step - 2, and every warp that gets here has passed a
+            // barrier of step `step`, which no warp reaches before it has finished step - 1.
+            const int sq = warp_in_team;
+            const float ts = (float)(W.t0 + (double)(step + 1) * W.dt + tab.c[sq] * W.dt);
+            forcing_amplitudes(P, v.fs + (((step + 1) % kFsBuffers) * kMaxStages + sq) * kFsStride, sample, ts, lane);
+          }
         }
 
         // ================= phase 1: hidden layers on the tensor pipe =================
@@ -673,7 +732,9 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
 #pragma unroll 1
           for (int sl = 0; sl < nslots; ++sl) {
             const SlotView v = view(sl);
+            trace_ev(tr, trn, sl * 16 + 4);
             mbar_wait_guarded(v.done, done_parity);
+            trace_ev(tr, trn, sl * 16 + 5);
             fence_after();
             float acc[32];
             tmem_pair16(v.taddr, v.taddr + 32, acc, cross_scale);
@@ -684,6 +745,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
             const float inv = pow2_inverse(scale_for(bound1)) * P.tc_inv_sw_hid;
             const float s_act = scale_for(fmaf(P.tc_whabs, bound1, P.tc_bhabs));   // |h2| <= |b2| + sum|W2| max|h1|
             if (v.done_nb) mbar_wait_guarded(v.done_nb, done_parity);
+            trace_ev(tr, trn, sl * 16 + 6);
 #pragma unroll
             for (int c8 = 0; c8 < kChunks / 2; ++c8) {
               float h[8];
@@ -694,6 +756,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
             }
             fence_async_smem();
             mbar_arrive(v.req);
+            trace_ev(tr, trn, sl * 16 + 7);
           }
           done_parity ^= 1u;
         }
@@ -709,13 +772,17 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           const float bound1 = bound_s[sl];
           const float s_last = hidden_tc_layers > 0 ? scale_for(fmaf(P.tc_whabs, bound1, P.tc_bhabs)) : scale_for(bound1);
           const float inv_last = pow2_inverse(s_last) * P.tc_inv_sw_last;
+          trace_ev(tr, trn, sl * 16 + 8);
           mbar_wait_guarded(v.done, done_parity);
+          trace_ev(tr, trn, sl * 16 + 9);
           if (v.done_nb) mbar_wait_guarded(v.done_nb, done_parity);     // before the next stage rewrites the planes
+          trace_ev(tr, trn, sl * 16 + 10);
           fence_after();
           float dv[kMaxD];
           if (NL == 16) last_epilogue<16>(P, W, v.taddr, u7, row, x, dv, cross_scale, inv_last);
           else last_epilogue<32>(P, W, v.taddr, u7, row, x, dv, cross_scale, inv_last);
           if (W.op == OP_COEF || W.op == OP_DERIV) continue;
+          trace_ev(tr, trn, sl * 16 + 14);
           float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
           if (cons) {
             v.flux[x] = r;
@@ -724,11 +791,16 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
             r = -__fmul_rn(P.inv_dx, __fsub_rn(fwd, r));
           }
           if (forced) {
+            // all loads issued together (unrolled, predicated): one L1 latency instead of 2M in a chain
+            const float* amp = v.fs + ((step % kFsBuffers) * kMaxStages + s) * kFsStride;
+            const float* basis = P.fbasis + x;
             float f = 0.f;
-            for (int m = 0; m < P.M; ++m) {
-              f = fmaf(v.fs[((step & 1) * kMaxStages + s) * kForcingStride + m], __ldg(P.fbasis + (size_t)m * N + x), f);
-              f = fmaf(v.fs[((step & 1) * kMaxStages + s) * kForcingStride + P.M + m], __ldg(P.fbasis + (size_t)(P.M + m) * N + x), f);
-            }
+#pragma unroll
+            for (int m = 0; m < kMaxModes; ++m)
+              if (m < P.M) {
+                f = fmaf(amp[m], __ldg(basis + (size_t)m * N), f);
+                f = fmaf(amp[P.M + m], __ldg(basis + (size_t)(P.M + m) * N), f);
+              }
             r = __fadd_rn(r, f);
           }
           if (W.op == OP_RHS) {
@@ -737,6 +809,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
           } else {
             k_s[sl][s] = r;
           }
+          trace_ev(tr, trn, sl * 16 + 11);
         }
         done_parity ^= 1u;
         stage_par ^= 1u;
@@ -753,7 +826,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
         const double y = y_s[sl] + W.dt * accd;
         y_s[sl] = y;
         if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
-          atomicMin(reinterpret_cast<unsigned int*>(v.fs + 2 * kMaxStages * kForcingStride), (unsigned int)step);
+          atomicMin(reinterpret_cast<unsigned int*>(v.fs + kFsWords), (unsigned int)step);
         if (save) W.snaps[((size_t)save_idx * W.batch + row) * N + x] = (float)y;
       }
       if (save) ++save_idx;
@@ -762,7 +835,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
       team_sync(team, N);
       for (int sl = 0; sl < nslots; ++sl) {
         const SlotView v = view(sl);
-        const unsigned int fb = *reinterpret_cast<unsigned int*>(v.fs + 2 * kMaxStages * kForcingStride);
+        const unsigned int fb = *reinterpret_cast<unsigned int*>(v.fs + kFsWords);
         if (x == 0) W.first_bad[row0 + sl * total_teams] = (fb == 0xffffffffu) ? -1 : (int)fb;
       }
     }
@@ -862,7 +935,7 @@ __device__ __forceinline__ void mma_bf16_split(uint32_t tmem_d, uint32_t a_lo, u
       : "memory");
 }
 
-template <int KIND, int N1, int N2, int BROWS, int ALT>
+template <int KIND, int N1, int N2, int BROWS, int ALT, int DOFF2 = 128>
 __global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, long long* __restrict__ cycles) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -910,8 +983,8 @@ __global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, long long* __
               else mma_tf32_split(base_u + dsel, a00 + ao, b0 + bo, desc_hi, id1, 1u);
             }
             if (N2) {
-              if (KIND) mma_bf16_split(base_u + dsel + 128u, a10 + ao, b0 + bo, desc_hi, id2, 1u);
-              else mma_tf32_split(base_u + dsel + 128u, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+              if (KIND) mma_bf16_split(base_u + dsel + (uint32_t)DOFF2, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+              else mma_tf32_split(base_u + dsel + (uint32_t)DOFF2, a10 + ao, b0 + bo, desc_hi, id2, 1u);
             }
           }
         }

@@ -7,10 +7,13 @@ from ddd1d_b200 import _lib
 lib = _lib.load()
 VARIANTS = ['tf32 N=16', 'tf32 N=32', 'tf32 N=64', 'tf32 N=128', 'tf32 N=32 of a 64-row B plane', 'tf32 N=32 single accumulator',
             'tf32 64+32 (hidden layer step)', 'tf32 32+16 (last layer step)', 'tf32 32+32',
-            'bf16 N=32 (K=16)', 'bf16 N=64', 'bf16 N=96', 'bf16 96+64', 'bf16 N=128']
+            'bf16 N=32 (K=16)', 'bf16 N=64', 'bf16 N=96', 'bf16 96+64', 'bf16 N=128',
+            'f16 64+32 separate D', 'f16 64+32 D overlap (production hidden)', 'f16 32+16 D overlap (production last)', 'f16 N=96 one D']
 for blocks in (1, 148):
   for v, name in enumerate(VARIANTS):
-    out = np.zeros(blocks, np.int64)
-    reps = 100
-    _lib.check(lib.ddd1d_debug_tc_rate(0, v, reps, blocks, _lib.host_ptr(out)))
-    print('blocks %3d  %-34s %7.1f clk/step' % (blocks, name, out.mean() / (reps * 20)))
+    line = 'blocks %3d  %-40s' % (blocks, name)
+    for reps in (100, 1):       # reps = 1: one 20-step job from a cold pipe (fill + drain latency included)
+      out = np.zeros(blocks, np.int64)
+      _lib.check(lib.ddd1d_debug_tc_rate(0, v, reps, blocks, _lib.host_ptr(out)))
+      line += '  reps %3d: %7.1f clk/step' % (reps, out.mean() / (reps * 20))
+    print(line)
