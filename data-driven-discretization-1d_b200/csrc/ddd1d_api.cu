@@ -317,7 +317,7 @@ int finalize_tc(ddd1d_handle* h) {
   }
   const void* kern = (const void*)tc::tc_row_kernel;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  h->tc_threads = P.tc_teams * N + 32;       // thread <-> grid point, plus the warp that issues the MMAs
+  h->tc_threads = P.tc_teams * N + 32 * tc::kIssuers;       // thread <-> grid point, plus the warps that issue the MMAs
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, h->tc_threads, P.smem_bytes));
   if (occ < 1) {

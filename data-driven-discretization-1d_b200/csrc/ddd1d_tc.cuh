@@ -449,7 +449,13 @@ __device__ __forceinline__ void last_epilogue(const Params& P, const Work& W, ui
 // tableau is a kernel parameter (constant bank).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 2;
-__global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
+// MMA issuer warps.  One warp's instruction stream (descriptor arithmetic, uniform-register moves, the
+// tcgen05.mma itself) sustains one MMA per ~62 clk, the tensor pipe takes one per ~42 clk at these shapes: the
+// single issuer, not the pipe, bounded the MMA stream (measured with the teams switched off: 10.5 ms for the
+// C2 launch against 7.1 ms of MMA time).  Two issuers on different scheduler partitions each serve half of
+// the slots; their MMAs interleave in the pipe, every tcgen05.commit tracks its own warp's MMAs.
+constexpr int kIssuers = 2;
+__global__ void __launch_bounds__(512 + 32 * kIssuers, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
                                                         const __grid_constant__ Tableau tab) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
   const int nstages = (W.op == OP_INTEGRATE) ? tab.stages : 1;
   const uint32_t smem_s = smem_u32(dyn_smem);
 
-  if (warp == R * team_warps) {
+  if (warp >= R * team_warps) {
     // ---------------- issuer warp ----------------
     // The tensor pipe's queue is only a few MMAs deep, so the pipe drains (and pays its ~1000 clk start-up
     // latency again) unless the next layer's first MMA is queued within ~150 clk of the previous layer's last.
@@ -498,7 +504,9 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int my_remaining = 0, my_layer = 0;
     uint32_t my_parity = 0;
-    if (lane < TS) {
+    const int issuer = warp - R * team_warps;          // serves slots [issuer * TS / kIssuers, (issuer + 1) * TS / kIssuers)
+    const int served = TS >= kIssuers ? (P.tc_debug & 2 ? (issuer == 0 ? TS : 0) : TS / kIssuers) : (issuer == 0 ? TS : 0);
+    if (lane >= issuer * served && lane < (issuer + 1) * served && lane < TS) {
       const int first = blockIdx.x * R + lane / SLOTS + (lane % SLOTS) * total_teams;      // this slot's first row
       const int stride = SLOTS * total_teams;
       const int rows = first < W.batch ? (W.batch - first + stride - 1) / stride : 0;
@@ -514,7 +522,8 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
     int trn = 0;
 #endif
     while (true) {
-      const bool ready = my_remaining > 0 && mbar_test(&bars[1 + lane], my_parity);    // (acquire)
+      // (debug bit 6: the MMA stream alone -- every request counts as made, the teams sit the launch out)
+      const bool ready = my_remaining > 0 && ((P.tc_debug & 64) || mbar_test(&bars[1 + lane], my_parity));    // (acquire)
       const uint32_t mask = __ballot_sync(0xffffffffu, ready);
       if (mask == 0u) {
         if (__ballot_sync(0xffffffffu, my_remaining > 0) == 0u) break;
@@ -635,7 +644,7 @@ __global__ void __launch_bounds__(544, 1) tc_row_kernel(const __grid_constant__ 
   float umax_s[kMaxSlots];
 
   const int g = blockIdx.x * R + team;
-  for (int row0 = g; row0 < W.batch; row0 += SLOTS * total_teams) {
+  for (int row0 = g; row0 < W.batch && !(P.tc_debug & 64); row0 += SLOTS * total_teams) {
     int nslots = 0;
     for (int sl = 0; sl < SLOTS; ++sl) {
       const int row = row0 + sl * total_teams;

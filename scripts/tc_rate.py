@@ -17,3 +17,15 @@ for blocks in (1, 148):
       _lib.check(lib.ddd1d_debug_tc_rate(0, v, reps, blocks, _lib.host_ptr(out)))
       line += '  reps %3d: %7.1f clk/step' % (reps, out.mean() / (reps * 20))
     print(line)
+
+# cost of tcgen05.commit inside an MMA stream (production commits once per tile = every 10 MMA pairs)
+for v, name in ((15, 'no commit'), (18, 'commit every 10 steps'), (19, 'commit every 5 steps'), (20, 'commit every step')):
+  out = np.zeros(1, np.int64)
+  _lib.check(lib.ddd1d_debug_tc_rate(0, v, 100, 1, _lib.host_ptr(out)))
+  print('f16 64+32 (hidden step), %-24s %7.1f clk/step' % (name, out.mean() / (100 * 20)))
+
+# does the operand DATA change the rate?  (values near 1 | random bit patterns incl. NaN/Inf/subnormals | zeros)
+for kind, name in ((0, 'values near 1'), (1, 'random bits'), (2, 'zeros')):
+  out = np.zeros(148, np.int64)
+  _lib.check(lib.ddd1d_debug_tc_rate(0, 15, 100 | (kind << 16), 148, _lib.host_ptr(out)))
+  print('f16 64+32 (hidden step), data = %-16s %7.1f clk/step' % (name, out.mean() / (100 * 20)))
