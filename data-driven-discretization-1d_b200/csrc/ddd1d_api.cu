@@ -317,7 +317,10 @@ int finalize_tc(ddd1d_handle* h) {
   }
   const void* kern = (const void*)tc::tc_row_kernel;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  h->tc_threads = P.tc_teams * N + 32 * tc::kIssuers;       // thread <-> grid point, plus the warps that issue the MMAs
+  P.tc_issuers = N == 128 ? 4 : 2;
+  if (getenv("DDD1D_TC_ISSUERS")) P.tc_issuers = std::max(1, std::min(tc::kMaxIssuers, atoi(getenv("DDD1D_TC_ISSUERS"))));
+  P.tc_issuers = std::min(P.tc_issuers, P.tc_teams * P.tc_slots);
+  h->tc_threads = P.tc_teams * N + 32 * P.tc_issuers;       // thread <-> grid point, plus the warps that issue the MMAs
   int occ = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, h->tc_threads, P.smem_bytes));
   if (occ < 1) {

@@ -71,6 +71,7 @@ struct Params {
   long long* tc_trace;            // debug: clock64 event trace of CTA 0 (DDD1D_TC_TRACE=<file>), else null
   float* tc_scratch;              // global scratch [grid][teams * slots][tc_sc_stride] floats (L1 / L2 resident)
   int tc_sc_stride, tc_sc_umax, tc_sc_flux, tc_sc_fs;   // float offsets inside a slot's scratch
+  int tc_issuers;           // warps that issue the MMAs
   int tc_slots;             // rows in flight per team (their CUDA-core and tensor phases interleave)
   float tc_w1abs, tc_b1abs, tc_whabs, tc_bhabs;   // operator-norm bounds behind the fp16 plane scales
   float tc_inv_sw_hid, tc_inv_sw_last;            // 1 / power-of-two filter scales

@@ -454,8 +454,8 @@ constexpr int kMaxSlots = 2;
 // single issuer, not the pipe, bounded the MMA stream (measured with the teams switched off: 10.5 ms for the
 // C2 launch against 7.1 ms of MMA time).  Two issuers on different scheduler partitions each serve half of
 // the slots; their MMAs interleave in the pipe, every tcgen05.commit tracks its own warp's MMAs.
-constexpr int kIssuers = 2;
-__global__ void __launch_bounds__(512 + 32 * kIssuers, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
+constexpr int kMaxIssuers = 4;     // P.tc_issuers of them are launched (2 by default, 4 for the many short layers of N = 128)
+__global__ void __launch_bounds__(512 + 32 * kMaxIssuers, 1) tc_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
                                                         const __grid_constant__ Tableau tab) {
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -504,8 +504,8 @@ __global__ void __launch_bounds__(512 + 32 * kIssuers, 1) tc_row_kernel(const __
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int my_remaining = 0, my_layer = 0;
     uint32_t my_parity = 0;
-    const int issuer = warp - R * team_warps;          // serves slots [issuer * TS / kIssuers, (issuer + 1) * TS / kIssuers)
-    const int served = TS >= kIssuers ? (P.tc_debug & 2 ? (issuer == 0 ? TS : 0) : TS / kIssuers) : (issuer == 0 ? TS : 0);
+    const int issuer = warp - R * team_warps;          // serves `served` consecutive slots
+    const int served = (TS + P.tc_issuers - 1) / P.tc_issuers;
     if (lane >= issuer * served && lane < (issuer + 1) * served && lane < TS) {
       const int first = blockIdx.x * R + lane / SLOTS + (lane % SLOTS) * total_teams;      // this slot's first row
       const int stride = SLOTS * total_teams;
