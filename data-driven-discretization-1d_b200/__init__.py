@@ -13,11 +13,12 @@ from . import duckarray
 from . import polynomials
 from . import equations
 from . import training
+from . import checkpoint
 from . import runtime
 from . import model
 from . import weno
 from . import integrate
 from . import distributed
 
-__all__ = ['duckarray', 'polynomials', 'equations', 'training', 'runtime', 'model', 'weno',
+__all__ = ['duckarray', 'polynomials', 'equations', 'training', 'checkpoint', 'runtime', 'model', 'weno',
            'integrate', 'distributed']

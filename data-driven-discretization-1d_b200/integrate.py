@@ -18,6 +18,7 @@ from . import duckarray
 from . import equations as equations_lib
 from . import model
 from . import runtime
+from . import training
 
 _DEFAULT_TIMES = np.linspace(0, 10, num=201)
 
@@ -86,9 +87,9 @@ def _load_weights(source):
         out.append((f['kernel%d' % i], f['bias%d' % i]))
         i += 1
     return out
-  raise NotImplementedError(
-      'reading TensorFlow-1 Saver checkpoints (%r) is not built yet; pass the conv weights as '
-      '[(kernel, bias), ...] or a .npz with kernel0, bias0, ...' % (source,))
+  # a checkpoint directory (or prefix) written by tf.train.Saver (integrate.py:66-68)
+  from . import checkpoint
+  return checkpoint.load_conv_weights(source)
 
 
 class SavedModelDifferentiator(Differentiator):
@@ -291,7 +292,7 @@ def integrate_exact_baseline_and_model(checkpoint_dir, hparams=None, random_seed
   """Exact fine-grid run, then baseline and learned model on the coarse grid from the
   same resampled initial condition (integrate.py:342-396)."""
   if hparams is None:
-    raise NotImplementedError('hparams.pbtxt loading is not built yet; pass hparams')
+    hparams = training.load_hparams(checkpoint_dir)        # integrate.py:349-350
   fine, coarse = equations_lib.from_hparams(hparams, random_seed=random_seed)
   exact = integrate_exact(fine, times, warmup, integrate_method=integrate_method,
                           filter_interval=exact_filter_interval)
@@ -317,7 +318,7 @@ def integrate_model_from_warm_start(checkpoint_dir, y0, hparams=None, random_see
                                     times=_DEFAULT_TIMES, warmup=0, integrate_method='RK23'):
   """integrate.py:399-427."""
   if hparams is None:
-    raise NotImplementedError('hparams.pbtxt loading is not built yet; pass hparams')
+    hparams = training.load_hparams(checkpoint_dir)        # integrate.py:406-407
   _, coarse = equations_lib.from_hparams(hparams, random_seed=random_seed)
   solution, num_evals = odeint(y0, SavedModelDifferentiator(checkpoint_dir, coarse, hparams),
                                warmup + times, method=integrate_method)

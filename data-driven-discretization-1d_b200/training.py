@@ -51,3 +51,28 @@ def create_hparams(equation, **kwargs):
   hparams = HParams(equation=equation, **copy.deepcopy(_DEFAULTS))
   hparams.override_from_dict(kwargs)
   return hparams
+
+
+def checkpoint_dir_to_path(checkpoint_dir):
+  """training.py:523-524."""
+  from . import checkpoint
+  return checkpoint.checkpoint_dir_to_path(checkpoint_dir)
+
+
+def load_hparams(checkpoint_dir):
+  """Hyper-parameters saved next to a checkpoint as `hparams.pbtxt` (training.py:639-647);
+  anything the file does not mention takes its create_hparams default."""
+  import os
+  from . import checkpoint
+  with open(os.path.join(checkpoint_dir, 'hparams.pbtxt'), 'r') as f:
+    values = checkpoint.parse_hparams_pbtxt(f.read())
+  return create_hparams(**values)
+
+
+def save_hparams(checkpoint_dir, hparams):
+  """Write `hparams.pbtxt` the way training_loop does (training.py:590-592)."""
+  import os
+  from . import checkpoint
+  os.makedirs(checkpoint_dir, exist_ok=True)
+  with open(os.path.join(checkpoint_dir, 'hparams.pbtxt'), 'w') as f:
+    f.write(checkpoint.format_hparams_pbtxt(hparams.values()))

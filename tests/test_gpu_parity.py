@@ -562,3 +562,34 @@ def test_model_targets_against_reference_fixture(golden):
         model.predict_coefficients(u, hp, w)
       d = integrate.SavedModelDifferentiator(w, G.product_equation(kind, variant, 32, seed=5), hp)
       assert rel_err(d(0.61, u[0].astype(np.float64)), g[key + '/differentiator']) < FLUX_TOL, key
+
+
+# ---------------------------------------------------------------------------------
+# checkpoint directory ingestion (model.ckpt.* + hparams.pbtxt), SURVEY 8f rank 1
+# ---------------------------------------------------------------------------------
+def test_checkpoint_directory_drives_the_reference_surface(golden, tmp_path):
+  """SavedModelDifferentiator(checkpoint_dir, ...) and the hparams=None wrappers read the
+  TF-1 bundle + hparams.pbtxt and give exactly what explicit weights give (integrate.py:48-71,
+  342-427); the fixture value is the reference's own graph output."""
+  from ddd1d_b200 import checkpoint, integrate, training
+  g = golden('learned')
+  kind, variant, n = 'burgers', 'plain', 32
+  key = 'default/%s/%s/%d' % (kind, variant, n)
+  hp = G.product_hparams(kind, variant, n)
+  w = weights_from(g, key)
+  d = str(tmp_path / 'model_dir')
+  checkpoint.save_conv_weights(d, w)
+  training.save_hparams(d, hp)
+  eq = G.product_equation(kind, variant, n, seed=7)
+  u = g[key + '/u']
+  from_dir = integrate.SavedModelDifferentiator(training.checkpoint_dir_to_path(d), eq, training.load_hparams(d))
+  got = from_dir(float(g[key + '/t']), u[0].astype(np.float64))
+  assert rel_err(got, g[key + '/differentiator']) < RHS_TOL
+  explicit = integrate.SavedModelDifferentiator(w, eq, hp)
+  np.testing.assert_array_equal(got, explicit(float(g[key + '/t']), u[0].astype(np.float64)))
+  # hparams=None: read from the directory (integrate.py:406-407)
+  times = np.linspace(0, 0.1, 3)
+  y0 = u[0].astype(np.float64)
+  a = integrate.integrate_model_from_warm_start(d, y0, times=times)
+  b = integrate.integrate_model_from_warm_start(w, y0, hparams=hp, times=times)
+  np.testing.assert_array_equal(np.asarray(a['y'].data), np.asarray(b['y'].data))
