@@ -104,6 +104,31 @@ class RowSolver(object):
     self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
     self.mode = mode
     self.stencil_size = 0
+    self.constant_coefficients = None
+    constant_windows = None
+    if mode == _lib.MODE_LEARNED and hparams.num_layers == 0:
+      # model.py:496-502: no net at all -- one learned vector through the polynomial-accuracy layers, i.e.
+      # constant stencils.  They are formed here exactly as the float32 graph forms them (float32 tables,
+      # one rounding per op, polynomials.py:275-277) and run on the fixed-stencil kernel.
+      if not hparams.polynomial_accuracy_order:
+        raise NotImplementedError                            # model.py:461-462
+      if getattr(hparams, 'model_target', 'coefficients') != 'coefficients':
+        raise NotImplementedError('num_layers=0 with model_target={!r}'.format(hparams.model_target))
+      layers0 = accuracy_layers(eq, hparams)
+      vector = np.asarray(weights[0] if isinstance(weights, (list, tuple)) else weights, dtype=np.float32).ravel()
+      if vector.size != sum(l.input_size for l in layers0):
+        raise ValueError('coefficients vector has {} entries, the model needs {}'.format(
+            vector.size, sum(l.input_size for l in layers0)))
+      rows, start = [], 0
+      for l in layers0:
+        z = vector[start:start + l.input_size]
+        start += l.input_size
+        product = (z.astype(np.float64) @ l.nullspace.astype(np.float32).astype(np.float64)).astype(np.float32)
+        rows.append(l.bias.astype(np.float32) + product)
+      self.constant_coefficients = np.stack(rows)            # [derivative, grid point] float32
+      self.stencil_size = self.constant_coefficients.shape[1]
+      constant_windows = np.ascontiguousarray(_lib.to_window(self.constant_coefficients.astype(np.float64)))
+      mode = self.mode = _lib.MODE_STENCIL
 
     cfg = _lib.Config()
     cfg.struct_bytes = ctypes.sizeof(_lib.Config)
@@ -120,8 +145,6 @@ class RowSolver(object):
     cfg.engine = _lib.ENGINES[engine]
     layers = None
     if mode == _lib.MODE_LEARNED:
-      if hparams.num_layers == 0:
-        raise NotImplementedError('num_layers=0 (a constant learned stencil) is not built')
       if hparams.nonlinearity not in _lib.ACTIVATIONS:
         raise KeyError(hparams.nonlinearity)
       shapes = expected_layer_shapes(eq, hparams)
@@ -166,7 +189,8 @@ class RowSolver(object):
         self._check(self._lib.ddd1d_set_stencils(self._handle, _lib.host_ptr(bias)))
         self._check(self._lib.ddd1d_set_projection(self._handle, _lib.host_ptr(basis), _lib.host_ptr(sizes)))
     else:
-      windows = np.ascontiguousarray(baseline_windows(eq, accuracy_order))
+      windows = (constant_windows if constant_windows is not None
+                 else np.ascontiguousarray(baseline_windows(eq, accuracy_order)))
       self._check(self._lib.ddd1d_set_stencils(self._handle, _lib.host_ptr(windows)))
 
     self.forced = bool(forcing and eq.FORCED)
@@ -241,6 +265,9 @@ class RowSolver(object):
   def coefficients(self, u):
     torch = _torch()
     rows = self._rows(u)
+    if self.constant_coefficients is not None:               # num_layers = 0: tf.tile of one vector
+      const = torch.as_tensor(self.constant_coefficients, device=self.device)
+      return const.expand(rows.shape + const.shape).contiguous()
     out = torch.empty(rows.shape + (self.num_derivatives, self.stencil_size), device=self.device,
                       dtype=torch.float32)
     self._check(self._lib.ddd1d_coefficients(self._handle, rows.data_ptr(), out.data_ptr(), rows.shape[0],
@@ -332,7 +359,7 @@ def learned_solver(equations, hparams, weights, **kwargs):
 def weights_fingerprint(hparams, weights):
   import hashlib
   h = hashlib.sha1(json.dumps(hparams.values(), sort_keys=True, default=str).encode())
-  for kernel, bias in weights:
-    h.update(np.ascontiguousarray(kernel, dtype=np.float32).tobytes())
-    h.update(np.ascontiguousarray(bias, dtype=np.float32).tobytes())
+  for item in weights:
+    for array in (item if isinstance(item, (list, tuple)) else (item,)):   # (kernel, bias) | num_layers=0 vector
+      h.update(np.ascontiguousarray(array, dtype=np.float32).tobytes())
   return h.hexdigest()

@@ -181,7 +181,8 @@ def build():
   tf.identity = lambda x, name=None: Tensor(x)
 
   tf.shape = lambda x: Tensor(np.array(_a(x).shape, dtype=np.int32))
-  tf.tile = lambda x, multiples: Tensor(np.tile(_a(x), tuple(int(m) for m in _a(multiples))))
+  tf.tile = lambda x, multiples: Tensor(np.tile(_a(x), tuple(
+      int(np.asarray(_a(m))) for m in (multiples if isinstance(multiples, (list, tuple)) else _a(multiples)))))
   tf.concat = lambda values, axis, name=None: Tensor(np.concatenate([_a(v) for v in values], axis=axis))
   tf.stack = lambda values, axis=0: Tensor(np.stack([_a(v) for v in values], axis=axis))
   tf.squeeze = lambda x, axis=None: Tensor(np.squeeze(_a(x), axis=axis))

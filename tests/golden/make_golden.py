@@ -408,10 +408,35 @@ def golden_layers():
   return len(out)
 
 
+def golden_layers0():
+  """hparams.num_layers = 0: one learned constant vector through the polynomial-accuracy layers
+  (model.py:496-502), reference code on the shim."""
+  out = {}
+  rs = np.random.RandomState(2024)
+  for kind, variant in (('burgers', 'plain'), ('burgers', 'conservative'), ('kdv', 'godunov'), ('ks', 'plain')):
+    n = 32
+    hp = make_hparams(kind, variant, n, num_layers=0)
+    eq = equation_class(kind, variant)(n, random_seed=11)
+    grid = polynomials.regular_grid(eq.GRID_OFFSET, 0, hp.coefficient_grid_min_size, eq.grid.solution_dx)
+    method = (polynomials.Method.FINITE_VOLUMES if eq.CONSERVATIVE else polynomials.Method.FINITE_DIFFERENCES)
+    size = sum(polynomials.PolynomialAccuracyLayer(grid, method, o, hp.polynomial_accuracy_order).input_size
+               for o in eq.DERIVATIVE_ORDERS)
+    vec = (0.1 * rs.randn(size)).astype(np.float32)
+    u = (0.6 * rs.randn(2, n)).astype(np.float32)
+    key = '%s/%s' % (kind, variant)
+    out[key + '/vector'] = vec
+    out[key + '/u'] = u
+    S.STORE.named['coefficients'] = vec
+    out[key + '/coefficients'] = model.predict_coefficients(tf.Tensor(u), hp).a
+    out[key + '/time_derivative'] = model.predict_time_derivative(tf.Tensor(u), hp).a
+  np.savez_compressed(os.path.join(HERE, 'layers0.npz'), **out)
+  return len(out)
+
+
 if __name__ == '__main__':
   only = sys.argv[1:]
   for fn in (golden_tables, golden_learned, golden_targets, golden_baseline, golden_pointwise,
-             golden_trajectories, golden_layers):
+             golden_trajectories, golden_layers, golden_layers0):
     if only and fn.__name__ not in only:
       continue
     print(fn.__name__, fn())

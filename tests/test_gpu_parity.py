@@ -593,3 +593,17 @@ def test_checkpoint_directory_drives_the_reference_surface(golden, tmp_path):
   a = integrate.integrate_model_from_warm_start(d, y0, times=times)
   b = integrate.integrate_model_from_warm_start(w, y0, hparams=hp, times=times)
   np.testing.assert_array_equal(np.asarray(a['y'].data), np.asarray(b['y'].data))
+
+
+@pytest.mark.parametrize('kind,variant', [('burgers', 'plain'), ('burgers', 'conservative'),
+                                          ('kdv', 'godunov'), ('ks', 'plain')])
+def test_num_layers_zero_against_reference_fixture(golden, kind, variant):
+  """hparams.num_layers = 0 (model.py:496-502): constant learned stencils; fixture = reference graph."""
+  from ddd1d_b200 import model
+  g = golden('layers0')
+  key = '%s/%s' % (kind, variant)
+  hp = G.product_hparams(kind, variant, 32, num_layers=0)
+  w = [g[key + '/vector']]
+  u = g[key + '/u']
+  assert rel_err(cpu(model.predict_coefficients(u, hp, w)), g[key + '/coefficients']) < RHS_TOL
+  assert rel_err(cpu(model.predict_time_derivative(u, hp, w)), g[key + '/time_derivative']) < RHS_TOL

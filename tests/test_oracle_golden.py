@@ -217,3 +217,17 @@ def test_model_targets(golden):
         assert rel_err(O.multilayer_conv1d(u, eq, net, w), g[key + '/space_derivatives']) < F32_TOL
       d = O.ModelDifferentiator(eq, net, w)
       assert rel_err(d(0.61, u[0].astype(np.float64)), g[key + '/differentiator']) < 1e-5, key
+
+
+@pytest.mark.parametrize('kind,variant', [('burgers', 'plain'), ('burgers', 'conservative'),
+                                          ('kdv', 'godunov'), ('ks', 'plain')])
+def test_num_layers_zero(golden, kind, variant):
+  """hparams.num_layers = 0 (model.py:496-502): a learned constant vector instead of a net."""
+  g = golden('layers0')
+  key = '%s/%s' % (kind, variant)
+  eq = O.EquationSpec(kind, variant, num_points=32, random_seed=11)
+  net = O.NetSpec(num_layers=0)
+  w = [g[key + '/vector']]
+  u = g[key + '/u']
+  assert rel_err(O.predict_coefficients(u, eq, net, w), g[key + '/coefficients']) < F32_TOL
+  assert rel_err(O.predict_time_derivative(u, eq, net, w), g[key + '/time_derivative']) < F32_TOL
