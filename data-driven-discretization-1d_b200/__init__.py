@@ -19,6 +19,7 @@ from . import model
 from . import weno
 from . import integrate
 from . import distributed
+from . import evaluation
 
 __all__ = ['duckarray', 'polynomials', 'equations', 'training', 'checkpoint', 'runtime', 'model', 'weno',
-           'integrate', 'distributed']
+           'integrate', 'distributed', 'evaluation']

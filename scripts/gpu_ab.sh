@@ -1,0 +1,23 @@
+#!/bin/bash
+# A/B of library variants built into data-driven-discretization-1d_b200/variants/ (same box, same run)
+cd "$(dirname "$0")/.."
+PKG=data-driven-discretization-1d_b200
+mkdir -p gpurun_out
+timeout -k 10 900 python -m pytest tests -m gpu -q -x --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+cp $PKG/libddd1d.so /tmp/libddd1d_keep.so
+for rep in 1 2; do
+for v in "$@"; do
+  cp $PKG/variants/libddd1d_$v.so $PKG/libddd1d.so
+  if [ $rep = 1 ]; then
+    timeout -k 10 300 python -m pytest tests/test_gpu_tensor.py -q -x --timeout 200 -p no:cacheprovider 2>&1 | tail -1
+  fi
+  for w in c2 c3 c4; do
+    timeout -k 10 200 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > gpurun_out/ab_${v}_$w.json 2> gpurun_out/ab_${v}_$w.err
+    python -c "
+import json; d=json.loads(open('gpurun_out/ab_${v}_$w.json').read().strip().splitlines()[-1]); print('$v', '$w', '%.3f ms'%d['ms_per_step'], '%.3e'%d['value'])"
+  done
+done
+done
+cp /tmp/libddd1d_keep.so $PKG/libddd1d.so

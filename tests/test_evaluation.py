@@ -1,0 +1,68 @@
+"""Evaluation metrics (analysis.py, scripts/run_evaluation.py:189-210) as torch reductions: the
+reference's own KATs (analysis_test.py:31-42) plus NumPy restatements of the xarray expressions."""
+import numpy as np
+import pytest
+
+from ddd1d_b200 import evaluation as E
+
+
+@pytest.mark.parametrize('data,expected', [
+    (np.arange(100) < 65, 6.5),
+    (np.ones(100), 9.9),
+    (np.zeros(100), 0),
+    (np.concatenate([np.ones(10), np.zeros(1), np.ones(9), np.zeros(80)]), 1),
+])
+def test_calculate_survival_reference_kats(data, expected):
+  assert E.calculate_survival(data, np.arange(100) / 10).item() == expected
+
+
+def test_calculate_survival_batched():
+  good = np.stack([np.arange(100) < 65, np.ones(100, bool), np.zeros(100, bool)])
+  np.testing.assert_array_equal(E.calculate_survival(good, np.arange(100) / 10), [6.5, 9.9, 0.0])
+
+
+def test_unify_and_mae():
+  rs = np.random.RandomState(0)
+  samples, times, n, factor = 3, 11, 16, 4
+  exact_high = rs.randn(samples, times, n * factor)
+  model = rs.randn(samples, times, n)
+  t = np.linspace(0, 1, times)
+  exact_low = E.unify_x_coords(exact_high, factor).numpy()
+  np.testing.assert_allclose(exact_low, exact_high.reshape(samples, times, n, factor).mean(-1), rtol=1e-12)
+  stop = [0.35, 1.0, 5.0]
+  mae = E.calculate_mae(model, exact_low, t, stop)
+  assert mae.shape == (3, samples)
+  for i, tm in enumerate(stop):
+    sel = t <= tm                                        # xarray label slice is inclusive
+    np.testing.assert_allclose(mae[i], np.abs(model - exact_low)[:, sel].mean(axis=(1, 2)), rtol=1e-12)
+  model[1, 3, 2] = np.nan                                # skipna=False: NaN poisons every slice containing it
+  mae = E.calculate_mae(model, exact_low, t, stop)
+  assert np.isnan(mae[:, 1]).tolist() == [True, True, True] and not np.isnan(mae[:, 0]).any()
+
+
+def test_mostly_good_survival_matches_numpy():
+  rs = np.random.RandomState(1)
+  samples, times, n, factor = 4, 21, 8, 2
+  t = np.arange(times) * 0.5
+  exact_high = rs.randn(samples, times, n * factor)
+  exact_low = exact_high.reshape(samples, times, n, factor).mean(-1)
+  model = exact_low + 0.02 * t[None, :, None] * rs.randn(samples, times, n)      # error grows in time
+  q = 0.8
+  got = E.mostly_good_survival(model, exact_high, t, quantile=q)
+  max_error = np.quantile(np.abs(exact_high), 1 - q)
+  good = (np.abs(model - exact_low) <= max_error).mean(-1) >= q
+  want = np.where(good.all(1), t.max(), t[np.argmin(good, axis=1)])
+  np.testing.assert_array_equal(got, want)
+  assert (got < t.max()).any() and (got > 0).any()       # the case is not degenerate
+
+
+def test_results_round_trip(tmp_path):
+  res = {'y': np.random.RandomState(2).randn(2, 3, 8), 'time': np.array([10.0, 10.5, 11.0]),
+         'x': np.arange(8) * 0.1, 'num_evals': np.array([100, 103]), 'sample': np.array([0, 1])}
+  path = str(tmp_path / 'results.npz')
+  E.write_results(path, res)
+  back = E.read_results(path)
+  for k in res:
+    np.testing.assert_array_equal(back[k], res[k])
+  with pytest.raises(ValueError):
+    E.write_results(path, dict(res, y=res['y'][0]))

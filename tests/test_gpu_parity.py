@@ -607,3 +607,32 @@ def test_num_layers_zero_against_reference_fixture(golden, kind, variant):
   u = g[key + '/u']
   assert rel_err(cpu(model.predict_coefficients(u, hp, w)), g[key + '/coefficients']) < RHS_TOL
   assert rel_err(cpu(model.predict_time_derivative(u, hp, w)), g[key + '/time_derivative']) < RHS_TOL
+
+
+def test_run_integrate_batch_matches_per_sample_scipy(golden, tmp_path):
+  """evaluation.run_integrate_batch (all seeds in one device launch) vs the reference's per-seed
+  execution model (scripts/run_evaluation.py:152-174: SavedModelDifferentiator + SciPy odeint)."""
+  from ddd1d_b200 import checkpoint, evaluation, integrate, training
+  from ddd1d_b200 import equations as equations_lib
+  g = golden('learned')
+  kind, variant, n = 'burgers', 'plain', 32
+  key = 'default/%s/%s/%d' % (kind, variant, n)
+  hp = G.product_hparams(kind, variant, n)
+  w = weights_from(g, key)
+  d = str(tmp_path / 'model_dir')
+  checkpoint.save_conv_weights(d, w)
+  training.save_hparams(d, hp)
+  y0 = G.smooth_rows(3, n, seed=12).astype(np.float64)
+  times = np.linspace(0, 0.5, 6)
+  res = evaluation.run_integrate_batch(d, None, y0, times, warmup=1.0)
+  assert res['y'].shape == (3, 6, n) and list(res['sample']) == [0, 1, 2]
+  np.testing.assert_allclose(res['time'], 1.0 + times)
+  for seed in range(3):
+    _, coarse = equations_lib.from_hparams(hp, random_seed=seed)
+    diff = integrate.SavedModelDifferentiator(training.checkpoint_dir_to_path(d), coarse, hp)
+    want, nfev = integrate.odeint(y0[seed], diff, 1.0 + times)
+    assert int(res['num_evals'][seed]) == nfev
+    assert np.abs(res['y'][seed] - want).max() < 5e-5
+  path = str(tmp_path / 'results.npz')
+  evaluation.write_results(path, res)
+  np.testing.assert_array_equal(evaluation.read_results(path)['y'], res['y'])
