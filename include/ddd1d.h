@@ -84,7 +84,7 @@ enum {
 /* conv-stack engine (learned mode).  AUTO picks the tcgen05 kernel when the net is
  * the shape it is built for (kernel_size 5, filter_size 32, relu, 2 or 3 layers, N in
  * {128, 256, 512}) and the FP32-FFMA kernel otherwise; both satisfy the same
- * float32 tolerances (the tensor path uses the 3xTF32 split). */
+ * float32 tolerances (the tensor path splits every operand into fp16 hi + lo, 22 bits, FP32 accumulate). */
 enum { DDD1D_ENGINE_AUTO = 0, DDD1D_ENGINE_FFMA = 1, DDD1D_ENGINE_TENSOR = 2 };
 
 /* arithmetic of the WENO reconstruction: float32 (TF path, model.py:81-87) or
