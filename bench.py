@@ -394,9 +394,10 @@ def run_ours(args):
                 'frac': achieved_tf / f16_peak, 'traffic': traffic, 'peak_kind': peak_kind,
                 'note': 'achieved = algorithmic FP32-equivalent FLOPs (%d per grid-point-step); peak = measured sustained '
                         'dense bf16/f16 cuBLAS rate.  The FP32-faithful fp16 hi/lo split executes 3x the conv FLOPs on '
-                        'the tensor pipe (hi*Wh, hi*Wl, lo*Wh) at N padded to 32/16, and each M128xK16 MMA streams its '
-                        'A operand from shared memory: the skinny implicit GEMM is shared-memory-operand bound, not '
-                        'math bound (profiles/r01/README.md)' % fl}
+                        'the tensor pipe (hi*Wh, hi*Wl, lo*Wh) at N padded to 32/16 and every MMA streams its operands '
+                        'from shared memory (88 clk per K16 step for 48 clk of math), so the MMA stream alone needs 7.7 ms '
+                        'of the launch; the CUDA-core side (stage values, first layer, splits, epilogues) alone needs 9.8 ms '
+                        'and the two overlap by about half (profiles/r01/README.md)' % fl}
   else:
     roofline = dict(hbm)
   roofline.update({'kernel': kernel_name, 'kernel_ms': kernel_ms})
@@ -419,7 +420,7 @@ def run_ours(args):
       'launch': shape, 'wall_s': wall, 'final_gather_ms': gather_ms,
   }
   if not args.no_cpu:
-    samples = 8
+    samples = 160                             # ~10-15 s of single-core work (the bounded sample of the batch)
     rk_cpu = rk
     _cpu_one_sample((args.workload, 0, 2))     # imports, first-call costs
     rate, elapsed, nfev = cpu_reference_rate(args.workload, rk_cpu, samples, 1)
