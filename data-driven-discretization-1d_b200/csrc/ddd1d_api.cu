@@ -17,6 +17,7 @@
 #include "../../include/ddd1d_debug.h"
 #include "ddd1d_device.cuh"
 #include "ddd1d_tc.cuh"
+#include "ddd1d_warp.cuh"
 
 using namespace ddd1d;
 
@@ -524,6 +525,20 @@ int finalize(ddd1d_handle* h) {
   return DDD1D_OK;
 }
 
+constexpr int kWarpRowsPerBlock = 8;      // warps (= rows in flight) per CTA of warp_row_kernel
+
+// The warp-per-row kernel takes the fused fixed-step integration of the modes without a conv net when a row
+// is exactly 1, 2, 4 or 8 points per lane.  DDD1D_NO_WARP_ROWS=1 keeps the CTA-per-row kernel (A/B, tests).
+bool use_warp_rows(const ddd1d_handle* h, int op) {
+  const ddd1d_config& c = h->cfg;
+  if (op != OP_INTEGRATE || c.mode == DDD1D_MODE_LEARNED) return false;
+  if (c.mode == DDD1D_MODE_WENO && c.weno_real != DDD1D_REAL_F32) return false;
+  const int n = c.num_points;
+  if (n % 32 != 0 || (n != 32 && n != 64 && n != 128 && n != 256)) return false;
+  if (h->P.P > 32) return false;            // one forcing term per lane
+  return getenv("DDD1D_NO_WARP_ROWS") == nullptr;
+}
+
 int launch(ddd1d_handle* h, Work& W, void* stream) {
   int rc = finalize(h);
   if (rc) return rc;
@@ -552,6 +567,22 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
         fclose(f);
       }
     }
+    h->launches += 1;
+    return DDD1D_OK;
+  }
+  if (use_warp_rows(h, W.op)) {
+    // one warp per row, everything in registers (ddd1d_warp.cuh): the fixed-step integrator of the
+    // fixed-stencil / float32 WENO modes for rows of 32 * {1, 2, 4, 8} points
+    const int blocks = std::min((W.batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * 8);
+    const Tableau tab = make_tableau(W.scheme);
+    const bool weno = c.mode == DDD1D_MODE_WENO;
+    switch (c.num_points / 32) {
+      case 1: weno ? warp_row_kernel<1, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<1, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
+      case 2: weno ? warp_row_kernel<2, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<2, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
+      case 4: weno ? warp_row_kernel<4, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<4, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
+      default: weno ? warp_row_kernel<8, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<8, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
+    }
+    CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;
   }
@@ -1017,6 +1048,12 @@ int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* bl
     if (grid) *grid = std::min((batch + h->Ptc.tc_teams - 1) / h->Ptc.tc_teams, h->num_sms);
     if (block) *block = h->tc_threads;
     if (shared_bytes) *shared_bytes = h->Ptc.smem_bytes;
+    return DDD1D_OK;
+  }
+  if (use_warp_rows(h, OP_INTEGRATE)) {     // (the shape of ddd1d_integrate launches)
+    if (grid) *grid = std::min((batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * 8);
+    if (block) *block = 256;
+    if (shared_bytes) *shared_bytes = 0;
     return DDD1D_OK;
   }
   if (grid) *grid = std::min(batch, h->num_sms * h->blocks_per_sm);

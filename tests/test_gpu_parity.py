@@ -636,3 +636,43 @@ def test_run_integrate_batch_matches_per_sample_scipy(golden, tmp_path):
   path = str(tmp_path / 'results.npz')
   evaluation.write_results(path, res)
   np.testing.assert_array_equal(evaluation.read_results(path)['y'], res['y'])
+
+
+# ---------------------------------------------------------------------------------
+# warp-per-row integrator of the modes without a net (csrc/ddd1d_warp.cuh)
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', (32, 64, 128, 256))
+@pytest.mark.parametrize('mode', ('fd', 'weno'))
+def test_warp_row_kernel_against_oracle(n, mode):
+  kinds = (('burgers', 1e-3), ('kdv', 2.5e-5), ('ks', 1e-5))
+  for kind, dt in kinds:
+    for variant in (('godunov',) if mode == 'weno' else VARIANTS):
+      _fixed_step_case(kind, variant, n, 3, 24, dt, mode, tol=2e-4 if mode == 'weno' else TRAJ_TOL)
+
+
+@pytest.mark.parametrize('scheme', ('rk3', 'midpoint', 'euler', 'rk4'))
+def test_warp_row_kernel_equals_block_kernel(monkeypatch, scheme):
+  """Same arithmetic, different thread mapping: the warp-per-row kernel and the CTA-per-row kernel agree to
+  rounding on every equation variant, with forcing, snapshots, odd batch sizes and divergence reporting."""
+  from ddd1d_b200 import integrate
+  for kind, variant, mode, dt in (('burgers', 'plain', 'fd', 1e-3), ('burgers', 'conservative', 'fd', 1e-3),
+                                  ('burgers', 'godunov', 'weno', 1e-3), ('ks', 'godunov', 'fd', 1e-5),
+                                  ('kdv', 'conservative', 'fd', 2.5e-5)):
+    n, batch = 64, 37
+    eqs = [G.product_equation(kind, variant, n, seed=s) for s in range(batch)]
+    solver = integrate.BatchIntegrator.weno(eqs) if mode == 'weno' else integrate.BatchIntegrator.baseline(eqs, 3)
+    u0 = G.smooth_rows(batch, n, seed=4)
+    if kind == 'burgers' and variant == 'plain':
+      u0[5] *= 1e20                                     # this row blows up: divergence is data
+    monkeypatch.delenv('DDD1D_NO_WARP_ROWS', raising=False)
+    assert solver.solver.launch_shape(batch)['block'] == 256
+    a, bad_a = solver.integrate(u0, 0.3, dt, 30, 10, scheme, return_first_bad=True)
+    monkeypatch.setenv('DDD1D_NO_WARP_ROWS', '1')
+    b, bad_b = solver.integrate(u0, 0.3, dt, 30, 10, scheme, return_first_bad=True)
+    monkeypatch.delenv('DDD1D_NO_WARP_ROWS', raising=False)
+    a, b = cpu(a), cpu(b)
+    np.testing.assert_array_equal(cpu(bad_a), cpu(bad_b))
+    ok = np.isfinite(b).all(axis=(0, 2))
+    assert ok.sum() >= batch - 1
+    assert rel_err(a[:, ok], b[:, ok]) < 2e-6, (kind, variant, mode, scheme)
+    np.testing.assert_array_equal(np.isfinite(a), np.isfinite(b))
