@@ -576,12 +576,21 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     const int blocks = std::min((W.batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * 8);
     const Tableau tab = make_tableau(W.scheme);
     const bool weno = c.mode == DDD1D_MODE_WENO;
+    const bool few = P.M <= 4;                 // forcing modes (the reference's k_max = 3)
+#define DDD1D_WARP_LAUNCH(PPL)                                                                        \
+  do {                                                                                                \
+    if (weno && few) warp_row_kernel<PPL, true, 4><<<blocks, 256, 0, st>>>(P, W, tab);              \
+    else if (weno) warp_row_kernel<PPL, true, kMaxModes><<<blocks, 256, 0, st>>>(P, W, tab);        \
+    else if (few) warp_row_kernel<PPL, false, 4><<<blocks, 256, 0, st>>>(P, W, tab);                \
+    else warp_row_kernel<PPL, false, kMaxModes><<<blocks, 256, 0, st>>>(P, W, tab);                 \
+  } while (0)
     switch (c.num_points / 32) {
-      case 1: weno ? warp_row_kernel<1, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<1, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
-      case 2: weno ? warp_row_kernel<2, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<2, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
-      case 4: weno ? warp_row_kernel<4, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<4, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
-      default: weno ? warp_row_kernel<8, true><<<blocks, 256, 0, st>>>(P, W, tab) : warp_row_kernel<8, false><<<blocks, 256, 0, st>>>(P, W, tab); break;
+      case 1: DDD1D_WARP_LAUNCH(1); break;
+      case 2: DDD1D_WARP_LAUNCH(2); break;
+      case 4: DDD1D_WARP_LAUNCH(4); break;
+      default: DDD1D_WARP_LAUNCH(8); break;
     }
+#undef DDD1D_WARP_LAUNCH
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;

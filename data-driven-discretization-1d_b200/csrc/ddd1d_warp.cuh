@@ -21,7 +21,8 @@
 
 namespace ddd1d {
 
-template <int PPL, bool WENO>
+// MM: compile-time bound on the number of forcing modes (4 covers the reference's k_max = 3)
+template <int PPL, bool WENO, int MM>
 __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
                                                        const __grid_constant__ Tableau tab) {
   const int lane = threadIdx.x & 31;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
           e[kHalo + PPL - 1 + h] = __shfl_sync(0xffffffffu, e[kHalo + ir], (lane + dr) & 31);
         }
         // ---- forcing amplitudes of this stage (equations.py:214-219) ----
-        float amp[2 * kMaxModes];
+        float amp[2 * MM];
         if (forced) {
           const float ts = (float)(t + tab.c[s] * W.dt);
           float sn, cs;
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
           const float a_cos = on ? (fterm.k < 0.f ? -fterm.a : fterm.a) * cs : 0.f;
           const float ka = fabsf(fterm.k);
 #pragma unroll
-          for (int m = 0; m < kMaxModes; ++m) {
-            amp[m] = amp[kMaxModes + m] = 0.f;
+          for (int m = 0; m < MM; ++m) {
+            amp[m] = amp[MM + m] = 0.f;
             if (m >= P.M) continue;
             float a = ka == (float)(m + 1) ? a_sin : 0.f, b = ka == (float)(m + 1) ? a_cos : 0.f;
 #pragma unroll
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
               b += __shfl_xor_sync(0xffffffffu, b, o);
             }
             amp[m] = a;
-            amp[kMaxModes + m] = b;
+            amp[MM + m] = b;
           }
         }
         // ---- derivatives, equation of motion ----
@@ -108,9 +109,11 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
 #pragma unroll
           for (int d = 0; d < kMaxD; ++d) {
             float acc = 0.f;                 // einsum('bxdi,bxi->bxd') with constant rows (model.py:536-548)
+            if (d < P.D && !(WENO && d < 2)) {      // (warp-uniform; WENO overwrites channels 0 and 1 below)
 #pragma unroll
-            for (int j = 0; j < kWin; ++j) acc = fmaf(cf[d][j], e[i + j], acc);
-            dv[d] = d < P.D ? acc : 0.f;
+              for (int j = 0; j < kWin; ++j) acc = fmaf(cf[d][j], e[i + j], acc);
+            }
+            dv[d] = acc;
           }
           if (WENO) {                        // u_minus / u_plus replaced by WENO5 (integrate.py:134-138)
             float um, up;
@@ -135,10 +138,10 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
             const float* basis = P.fbasis + lane * PPL + i;
             float f = 0.f;
 #pragma unroll
-            for (int m = 0; m < kMaxModes; ++m)
+            for (int m = 0; m < MM; ++m)
               if (m < P.M) {
                 f = fmaf(amp[m], __ldg(basis + (size_t)m * N), f);
-                f = fmaf(amp[kMaxModes + m], __ldg(basis + (size_t)(P.M + m) * N), f);
+                f = fmaf(amp[MM + m], __ldg(basis + (size_t)(P.M + m) * N), f);
               }
             r[i] = __fadd_rn(r[i], f);
           }
