@@ -269,9 +269,11 @@ def _build_block(items, restart_interval=16):
   return bytes(buf)
 
 
-def write_checkpoint(prefix, tensors):
+def write_checkpoint(prefix, tensors, entries_per_block=None):
   """Write {name: ndarray} as a single-shard V2 checkpoint (uncompressed index).  Used
-  by the tests and to hand weights trained elsewhere to code that expects `model.ckpt`."""
+  by the tests and to hand weights trained elsewhere to code that expects `model.ckpt`.
+  `entries_per_block` splits the index into several data blocks (TensorFlow starts a new
+  block every 256 KiB of entries; the tests use it to exercise the two-level lookup)."""
   data, items = bytearray(), []
   header = _field(1, 0, 1) + _field(3, 2, _field(1, 0, 1))        # num_shards = 1, version.producer = 1
   items.append((b'', header))
@@ -294,9 +296,14 @@ def write_checkpoint(prefix, tensors):
     out.extend(struct.pack('<I', mask_crc(crc32c(block + b'\x00'))))
     return _write_varint(offset) + _write_varint(len(block))
 
-  data_handle = emit(_build_block(items))
+  step = entries_per_block or len(items)
+  index_items = []
+  for start in range(0, len(items), step):
+    chunk = items[start:start + step]
+    # index key: any string >= the block's last key and < the next block's first key
+    index_items.append((chunk[-1][0] + b'\x00', emit(_build_block(chunk))))
   meta_handle = emit(_build_block([]))
-  index_handle = emit(_build_block([(items[-1][0] + b'\x00', data_handle)], restart_interval=1))
+  index_handle = emit(_build_block(index_items, restart_interval=1))
   footer = meta_handle + index_handle
   footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', _TABLE_MAGIC)
   out.extend(footer)

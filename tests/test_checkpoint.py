@@ -67,6 +67,20 @@ def test_checkpoint_ignores_optimizer_slots_and_orders_layers(tmp_path):
     np.testing.assert_array_equal(b0, b1)
 
 
+def test_checkpoint_with_several_index_blocks(tmp_path):
+  w = _weights(3, outputs=11)
+  tensors = {}
+  for i, (k, b) in enumerate(w):
+    scope = 'predict_coefficients/conv1d' + ('_%d' % i if i else '')
+    tensors[scope + '/kernel'], tensors[scope + '/bias'] = k, b
+  prefix = str(tmp_path / 'model.ckpt')
+  C.write_checkpoint(prefix, tensors, entries_per_block=2)        # header + 6 tensors -> 4 data blocks
+  got = C.conv_weights(C.read_checkpoint(prefix))
+  for (k0, b0), (k1, b1) in zip(w, got):
+    np.testing.assert_array_equal(k0, k1)
+    np.testing.assert_array_equal(b0, b1)
+
+
 def test_checkpoint_detects_corruption(tmp_path):
   d = str(tmp_path / 'ckpt')
   C.save_conv_weights(d, _weights(2))
