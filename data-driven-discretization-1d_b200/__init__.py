@@ -13,6 +13,8 @@ from . import duckarray
 from . import polynomials
 from . import equations
 from . import training
+from . import layers
+from . import analysis
 from . import checkpoint
 from . import runtime
 from . import model

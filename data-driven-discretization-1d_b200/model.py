@@ -179,3 +179,90 @@ def predict_time_evolution(inputs, hparams, weights=None):
   assert_consistent_solution(equation, inputs)
   snaps = solver.integrate(inputs, 0.0, equation.time_step, hparams.num_time_steps, 1, 'midpoint')
   return snaps.permute(1, 2, 0)
+
+
+# ---------------------------------------------------------------------------------
+# direct-prediction variants and the stacked-result helpers (model.py:162-290, 551-615, 664-696)
+# ---------------------------------------------------------------------------------
+def _with_target(hparams, target):
+  import copy
+  hp = copy.deepcopy(hparams)
+  hp.model_target = target
+  return hp
+
+
+def predict_space_derivatives_directly(inputs, hparams, weights=None, reuse=None):
+  """model.py:571-576: the net's channels are the space derivatives, [batch, x, derivative]."""
+  return predict_space_derivatives(inputs, _with_target(hparams, 'space_derivatives'), weights, reuse)
+
+
+def predict_time_derivative_directly(inputs, hparams, weights=None, reuse=None):
+  """model.py:603-606: the net's single channel is dy/dt, [batch, x]."""
+  return predict_time_derivative(inputs, _with_target(hparams, 'time_derivative'), weights, reuse)
+
+
+def predict_flux_directly(inputs, hparams, weights=None, reuse=None):
+  """model.py:609-615: staggered_first_derivative of the net's single channel (no minus sign)."""
+  return predict_time_derivative(inputs, _with_target(hparams, 'flux'), weights, reuse)
+
+
+def result_stack(space_derivatives, time_derivative, integrated_solution=None):
+  """[..., derivative] + [...] (+ [..., time]) -> [..., derivative + 1 (+ time)] (model.py:186-205)."""
+  import torch
+  tensors = [torch.as_tensor(space_derivatives), torch.as_tensor(time_derivative)[..., None]]
+  if integrated_solution is not None:
+    tensors.append(torch.as_tensor(integrated_solution))
+  return torch.cat(tensors, dim=-1)
+
+
+def result_unstack(tensor, equation):
+  """Inverse of result_stack (model.py:208-234)."""
+  d = len(equation.DERIVATIVE_ORDERS)
+  integrated = tensor[..., d + 1:] if tensor.shape[-1] > d + 1 else None
+  return tensor[..., :d], tensor[..., d], integrated
+
+
+def baseline_time_evolution(inputs, num_time_steps, equation):
+  """Midpoint-rule evolution with first-order-accurate standard stencils, all steps in one
+  fused launch, [batch, x] -> [batch, x, num_time_steps] (model.py:162-183)."""
+  assert_consistent_solution(equation, inputs)
+  grid = equation.grid
+  tag = (type(equation).__name__, grid.solution_num_points, grid.period, getattr(equation, 'eta', None))
+  solver = _cached(('fd', 1) + tag, lambda: runtime.stencil_solver(equation, 1, forcing=False))
+  snaps = solver.integrate(inputs, 0.0, equation.time_step, num_time_steps, 1, 'midpoint')
+  return snaps.permute(1, 2, 0)
+
+
+def baseline_result(inputs, equation, num_time_steps=0, accuracy_order=None):
+  """Space derivatives, time derivative and (optionally) the evolved solution of the baseline
+  model, stacked on the last axis (model.py:245-275)."""
+  if accuracy_order is None:
+    equation = equation.to_exact()
+  elif type(equation) in equations_lib.FLUX_EQUATION_TYPES:
+    # (as in the reference, model.py:264-265: the registry is keyed by NAME, so this membership test on a
+    #  class never holds and Godunov equations keep their own derivative set)
+    equation = equation.to_conservative()
+  space_derivatives = baseline_space_derivatives(inputs, equation, accuracy_order=accuracy_order)
+  import torch
+  rows = torch.as_tensor(inputs, device=space_derivatives.device).to(space_derivatives.dtype)
+  time_derivative = apply_space_derivatives(space_derivatives, rows, equation)
+  integrated = baseline_time_evolution(inputs, num_time_steps, equation) if num_time_steps else None
+  return result_stack(space_derivatives, time_derivative, integrated)
+
+
+def predict_result(inputs, hparams, weights=None):
+  """The learned model's counterpart of baseline_result (model.py:664-696)."""
+  import torch
+  _, equation = equations_lib.from_hparams(hparams)
+  if hparams.model_target in ('flux', 'time_derivative'):
+    if hparams.space_derivatives_weight:
+      raise ValueError('space derivatives are not predicted by model {}'.format(hparams.model_target))
+    time_derivative = predict_time_derivative(inputs, hparams, weights)
+    space_derivatives = torch.zeros(tuple(time_derivative.shape) + (len(equation.DERIVATIVE_ORDERS),),
+                                    device=time_derivative.device, dtype=time_derivative.dtype)
+  else:
+    space_derivatives = predict_space_derivatives(inputs, hparams, weights)
+    rows = torch.as_tensor(inputs, device=space_derivatives.device).to(space_derivatives.dtype)
+    time_derivative = apply_space_derivatives(space_derivatives, rows, equation)
+  integrated = predict_time_evolution(inputs, hparams, weights) if hparams.num_time_steps else None
+  return result_stack(space_derivatives, time_derivative, integrated)

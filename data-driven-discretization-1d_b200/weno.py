@@ -44,3 +44,70 @@ def reconstruct_right(u):
 def reconstruct_both(u):
   """(left, right) from one kernel launch."""
   return _reconstruct(u)
+
+
+# ---------------------------------------------------------------------------------
+# The intermediate quantities of weno.py as tensor expressions (the fused kernels compute them in registers
+# and never materialise them; these are for inspection and for callers of the reference's helper names).
+# NumPy in -> NumPy out, torch in -> torch out (on the tensor's device).
+# ---------------------------------------------------------------------------------
+def _as_torch(u):
+  import torch
+  if isinstance(u, torch.Tensor):
+    return u, False
+  return torch.as_tensor(np.asarray(u)), True
+
+
+def _back(x, was_numpy):
+  return x.cpu().numpy() if was_numpy else x
+
+
+def _indicators(u):
+  import torch
+  m2, m1, p1, p2 = (torch.roll(u, s, dims=-1) for s in (2, 1, -1, -2))
+  return torch.stack([
+      1 / 4 * (m2 - 4 * m1 + 3 * u) ** 2 + 13 / 12 * (m2 - 2 * m1 + u) ** 2,
+      1 / 4 * (m1 - p1) ** 2 + 13 / 12 * (m1 - 2 * u + p1) ** 2,
+      1 / 4 * (3 * u - 4 * p1 + p2) ** 2 + 13 / 12 * (u - 2 * p1 + p2) ** 2,
+  ], dim=-2)
+
+
+def _omega(u, optimal_linear_weights, epsilon, p):
+  import torch
+  d = torch.as_tensor(np.asarray(optimal_linear_weights, dtype=np.float64), device=u.device).to(u.dtype)
+  alpha = d[:, None] / (epsilon + _indicators(u)) ** p
+  return alpha / alpha.sum(dim=-2, keepdim=True)
+
+
+def calculate_smoothness_indicators(u):
+  """weno.py:43-57: [..., x] -> [..., 3, x]."""
+  x, was_numpy = _as_torch(u)
+  return _back(_indicators(x), was_numpy)
+
+
+def calculate_omega(u, optimal_linear_weights=OPTIMAL_SMOOTH_WEIGHTS, epsilon=1e-6, p=2):
+  """weno.py:60-73: nonlinear weights of the three sub-stencils, [..., 3, x]."""
+  x, was_numpy = _as_torch(u)
+  return _back(_omega(x, optimal_linear_weights, epsilon, p), was_numpy)
+
+
+def left_coefficients(u):
+  """weno.py:76-89: the five linear coefficients of the left-biased reconstruction, [..., x, 5]."""
+  import torch
+  x, was_numpy = _as_torch(u)
+  w = _omega(x, OPTIMAL_SMOOTH_WEIGHTS, 1e-6, 2)
+  w0, w1, w2 = w[..., 0, :], w[..., 1, :], w[..., 2, :]
+  out = torch.stack([w0 / 3, -(7 * w0 + w1) / 6, (11 * w0 + 5 * w1 + 2 * w2) / 6, (2 * w1 + 5 * w2) / 6, -w2 / 6],
+                    dim=-1)
+  return _back(out, was_numpy)
+
+
+def right_coefficients(u):
+  """weno.py:100-115 (reversed optimal weights, omega rolled by -1), [..., x, 5]."""
+  import torch
+  x, was_numpy = _as_torch(u)
+  w = torch.roll(_omega(x, OPTIMAL_SMOOTH_WEIGHTS[::-1], 1e-6, 2), -1, dims=-1)
+  w2, w1, w0 = w[..., 0, :], w[..., 1, :], w[..., 2, :]
+  out = torch.stack([-w2 / 6, (5 * w2 + 2 * w1) / 6, (2 * w2 + 5 * w1 + 11 * w0) / 6, -(w1 + 7 * w0) / 6, w0 / 3],
+                    dim=-1)
+  return _back(out, was_numpy)

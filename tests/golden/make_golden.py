@@ -433,10 +433,34 @@ def golden_layers0():
   return len(out)
 
 
+def golden_weno_parts():
+  """The intermediate quantities of weno.py (smoothness indicators, omega, linear coefficients) and the
+  index tables of layers.pad_periodic, from the reference's own NumPy / shim code."""
+  out = {}
+  rs = np.random.RandomState(77)
+  u = rs.randn(3, 24)
+  u[1] = np.where(np.arange(24) < 12, 1.0, -0.5)            # a discontinuity
+  out['u'] = u
+  out['indicators'] = weno.calculate_smoothness_indicators(u)
+  out['omega'] = weno.calculate_omega(u)
+  out['omega_reversed'] = weno.calculate_omega(u, weno.OPTIMAL_SMOOTH_WEIGHTS[::-1])
+  out['left_coefficients'] = weno.left_coefficients(u)
+  out['right_coefficients'] = weno.right_coefficients(u)
+  out['left'] = weno.reconstruct_left(u)
+  out['right'] = weno.reconstruct_right(u)
+  x = np.arange(2 * 5 * 3, dtype=np.float32).reshape(2, 5, 3)
+  out['pad/x'] = x
+  for padding in (0, 1, 2, 3, 4, 6, 11, 13):
+    for center in (False, True):
+      out['pad/%d/%d' % (padding, int(center))] = layers.pad_periodic(tf.Tensor(x), padding, center=center).a
+  np.savez_compressed(os.path.join(HERE, 'weno_parts.npz'), **out)
+  return len(out)
+
+
 if __name__ == '__main__':
   only = sys.argv[1:]
   for fn in (golden_tables, golden_learned, golden_targets, golden_baseline, golden_pointwise,
-             golden_trajectories, golden_layers, golden_layers0):
+             golden_trajectories, golden_layers, golden_layers0, golden_weno_parts):
     if only and fn.__name__ not in only:
       continue
     print(fn.__name__, fn())

@@ -676,3 +676,56 @@ def test_warp_row_kernel_equals_block_kernel(monkeypatch, scheme):
     assert ok.sum() >= batch - 1
     assert rel_err(a[:, ok], b[:, ok]) < 2e-6, (kind, variant, mode, scheme)
     np.testing.assert_array_equal(np.isfinite(a), np.isfinite(b))
+
+
+# ---------------------------------------------------------------------------------
+# stand-alone helpers and stacked results (layers.py:95-100, model.py:162-275, 551-615, 664-696)
+# ---------------------------------------------------------------------------------
+def test_nn_conv1d_periodic_and_result_helpers(golden):
+  import torch
+  from ddd1d_b200 import layers, model
+  g = golden('layers')
+  x = np.arange(5.0, dtype=np.float32)[None, :, None]
+  for name, filt in (('identity3', [0., 1., 0.]), ('shift2', [0., 1.]), ('avg2', [.5, .5]),
+                     ('k4', [1., 2., 3., 4.]), ('k5', [1., 2., 3., 4., 5.])):
+    f = np.array(filt, dtype=np.float32)[:, None, None]
+    got = cpu(layers.nn_conv1d_periodic(x, f, center=True))[0, :, 0]
+    np.testing.assert_allclose(got, g['conv/' + name], rtol=1e-6, atol=1e-6)
+    # center=False: the window starts at the output point (layers.py:70-83)
+    uncentred = cpu(layers.nn_conv1d_periodic(x, f, center=False))[0, :, 0]
+    want = sum(filt[i] * np.roll(x[0, :, 0], -i) for i in range(len(filt)))
+    np.testing.assert_allclose(uncentred, want, rtol=1e-6, atol=1e-6)
+
+  # baseline_result = [space derivatives | time derivative | midpoint evolution] (model.py:245-275)
+  gb = golden('baseline')
+  eq = G.product_equation('burgers', 'plain', 32, seed=11)
+  u = gb['burgers/plain/32/u']
+  res = model.baseline_result(u, eq, num_time_steps=3, accuracy_order=1)
+  sd, td, sol = model.result_unstack(res, eq)
+  assert tuple(res.shape) == u.shape + (2 + 1 + 3,)
+  assert rel_err(cpu(sd), gb['burgers/plain/32/acc1/space_derivatives']) < RHS_TOL
+  assert rel_err(cpu(td), gb['burgers/plain/32/acc1/time_derivative']) < RHS_TOL
+  oeq = G.oracle_equation('burgers', 'plain', 32, seed=11)
+  def rhs(t, y):                                          # no forcing inside the training unroll (model.py:177-181)
+    y32 = np.asarray(y, dtype=np.float32)
+    return O.apply_space_derivatives(O.baseline_space_derivatives(y32, oeq, 1), y32, oeq).astype(np.float32)
+  want = O.fixed_step_integrate(rhs, u, 0.0, oeq.time_step, 3, 1, scheme='midpoint')
+  assert rel_err(cpu(sol), np.transpose(want, (1, 2, 0))) < TRAJ_TOL
+
+  # the direct model targets through their own entry points (model.py:571-615) and predict_result
+  gt = golden('targets')
+  for target, fn in (('space_derivatives', model.predict_space_derivatives_directly),
+                     ('time_derivative', model.predict_time_derivative_directly),
+                     ('flux', model.predict_flux_directly)):
+    key = '%s/burgers/plain' % target
+    hp = G.product_hparams('burgers', 'plain', 32)              # model_target left at 'coefficients'
+    w = weights_from(gt, key)
+    want_key = key + ('/space_derivatives' if target == 'space_derivatives' else '/time_derivative')
+    assert rel_err(cpu(fn(gt[key + '/u'], hp, w)), gt[want_key]) < RHS_TOL
+  key = 'space_derivatives/burgers/plain'
+  hp = G.product_hparams('burgers', 'plain', 32, model_target='space_derivatives')
+  res = model.predict_result(gt[key + '/u'], hp, weights_from(gt, key))
+  sd, td, sol = model.result_unstack(res, eq)
+  assert sol is None
+  assert rel_err(cpu(sd), gt[key + '/space_derivatives']) < RHS_TOL
+  assert rel_err(cpu(td), gt[key + '/time_derivative']) < RHS_TOL
