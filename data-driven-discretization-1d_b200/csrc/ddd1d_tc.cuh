@@ -1,28 +1,27 @@
 // Tensor-core (tcgen05 / TMEM) version of the learned-coefficient row kernel, sm_100a.
 //
 // The conv stack is 96 % of the FLOPs and is an implicit GEMM per 128-position tile:
-//   hidden layer : D[128 x 32] += sum_{tap k, ci-block} A_k[128 x 8] * B_k[8 x 32]   (K = 5*32)
-//   last layer   : D[128 x NL] += ...                                                 (NL = 16 | 32)
-// A = activations kept in shared memory as K-major "chunk planes" [ci/4][position][4 floats]
-// (no swizzle), so the tap shift k is just +16 B on the descriptor start address and the periodic
-// halo is two extra positions per plane.  B = filters pre-packed on the host in the same canonical
-// layout.  FP32 fidelity on a TF32 pipe comes from the 3xTF32 split: x = hi + lo (both rounded to
-// TF32) and hi*Whi + lo*Whi + hi*Wlo accumulated in FP32 in TMEM (the dropped lo*Wlo term is 2^-22
-// relative).  B holds [Whi | Wlo] side by side, so one MMA of width 2*NB produces hi*Whi (the "main"
-// columns) and hi*Wlo (the "cross" columns) and a second one of width NB adds lo*Whi to the cross
-// columns: two instructions per (tap, ci-block) instead of three.  The tensor core truncates when it
-// adds into an accumulator (measured: error grows linearly with the number of accumulate steps, see
-// profiles/r01/tc_precision.txt), so the large main terms get their own columns, split once more
-// into even and odd taps (12 + 8 steps), and the epilogue adds the four partial sums in FP32.  The polynomial-accuracy projection is folded into the last layer's filters on
-// the host (W3' = W3 . nullspace, window form), so the last epilogue reads stencil coefficients
-// straight out of TMEM.
+//   hidden layer : D[128 x 32] += sum_{tap k, ci-block} A_k[128 x 16] * B_k[16 x 32]   (K = 5*32)
+//   last layer   : D[128 x NL] += ...                                                   (NL = 16 | 32)
+// A = activations kept in shared memory as K-major "chunk planes" [ci/8][position][8 halfs] (no swizzle), so
+// the tap shift k is just +16 B on the descriptor start address and the periodic halo is two extra positions
+// per plane.  B = filters pre-packed on the host in the same canonical layout.  FP32 fidelity on an fp16 pipe
+// comes from a two-term split: x * s = hi + lo (both fp16, s a power of two from a verified bound on the
+// row) and hi*Wh + lo*Wh + hi*Wl accumulated in FP32 in TMEM (the dropped lo*Wl term is 2^-22 relative).
+// B holds [Wh | Wl] side by side, so one MMA of width 2*NB produces hi*Wh (the "main" columns) and hi*Wl (the
+// "cross" columns) and a second one of width NB adds lo*Wh to the cross columns: two instructions per
+// (tap, ci-block) instead of three.  The tensor core truncates when it adds into an accumulator (measured,
+// profiles/r01/tc_precision.txt), so the small cross terms keep their own columns and the epilogue adds
+// main + cross in FP32.  The polynomial-accuracy projection is folded into the last layer's filters on the
+// host (W3' = W3 . nullspace, window form), so the last epilogue reads stencil coefficients straight out of
+// TMEM.  (issue_layer<false, ...> is the TF32 / 3xTF32 form of the same scheme; the probe kernel and the
+// precision microbenchmark use it.)
 //
-// Warp roles (one CTA per SM, persistent): R "row teams" of N threads (thread <-> grid point; the
-// team's warps are 4-aligned so each warp reads its own TMEM lane quadrant) run the whole
-// Runge-Kutta program of their row.  The first warp of each 128-position tile issues that tile's
-// tcgen05.mma once the team's planes are complete and signals completion with
-// tcgen05.commit -> mbarrier; 16 warps per CTA keep 128 registers per thread (no spills).  While one team runs an epilogue on the CUDA
-// cores, the tensor pipe works on another team's tile.
+// Warp roles (one CTA per SM, persistent): R "row teams" of N threads (thread <-> grid point; the team's
+// warps are 4-aligned so each warp reads its own TMEM lane quadrant) run the whole Runge-Kutta program of two
+// rows each ("slots"), and P.tc_issuers further warps do nothing but issue tcgen05.mma for the slots they
+// serve and signal completion with tcgen05.commit -> mbarrier.  While one row's MMAs run, its team works on
+// its other row.  See the comment above tc_row_kernel and DESIGN.md section 4.1 for what bounds the kernel.
 #pragma once
 #include <cuda_fp16.h>
 
