@@ -556,6 +556,7 @@ __device__ __forceinline__ void point_derivatives(const Params& P, const Smem& S
   for (int d = 0; d < kMaxD; ++d) {
     dv[d] = 0.f;
     if (d >= P.D) continue;
+    if (MODE == MODE_WENO && d < 2) continue;      // u_minus / u_plus come from WENO5 below, not from stencils
     float cf[kWin];
     if (MODE == MODE_LEARNED && P.projection >= PROJ_DERIVS) {
       // model_target='space_derivatives': the net's channels ARE the derivatives (model.py:571-576)
