@@ -17,8 +17,10 @@ the two published on-disk formats:
   bytes_value | bool_value | int64_list{value..} | float_list | bytes_list | bool_list } }`.
 
 PARITY UNPINNED: the reference ships no checkpoint file and TensorFlow cannot run here,
-so the reader is pinned only against the writer below (same format description) and the
-CRCs it verifies; the first real `model.ckpt` should be read with `verify=True`.
+so the table reader is pinned only against the writer below (same format description), the
+format's CRC-32C (RFC 3720 vectors) and magic; the protobuf wire encoding of the entries and
+the hparams text format ARE cross-checked against the protobuf runtime (tests/test_checkpoint.py).
+The first real `model.ckpt` should be read with `verify=True`.
 
 Variables of the coefficient model live under scope `predict_coefficients/`
 (model.py:442) with tf.layers naming: `conv1d/kernel [k, in, out]`, `conv1d/bias`,

@@ -187,3 +187,107 @@ def test_hparams_round_trip(tmp_path):
       np.testing.assert_allclose(np.asarray(b[key], float), np.asarray(a[key], float), rtol=1e-6, equal_nan=True)
     else:
       assert a[key] == b[key], key
+
+
+# ---------------------------------------------------------------------------------
+# independent cross-checks with the protobuf runtime (installed; TensorFlow's .proto files are not, so the
+# two message types are declared here from their published definitions)
+# ---------------------------------------------------------------------------------
+def _proto_classes():
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  F = descriptor_pb2.FieldDescriptorProto
+  fd = descriptor_pb2.FileDescriptorProto(name='ddd1d_test_hparam.proto', package='ddd1d_test', syntax='proto3')
+  hp = fd.message_type.add(name='HParamDef')
+  for name, ftype in (('BytesList', F.TYPE_BYTES), ('FloatList', F.TYPE_FLOAT), ('Int64List', F.TYPE_INT64),
+                      ('BoolList', F.TYPE_BOOL)):
+    m = hp.nested_type.add(name=name)
+    m.field.add(name='value', number=1, type=ftype, label=F.LABEL_REPEATED)
+  pt = hp.nested_type.add(name='ParamType')
+  pt.oneof_decl.add(name='kind')
+  for name, number, ftype, tname in (('int64_value', 1, F.TYPE_INT64, None), ('float_value', 2, F.TYPE_FLOAT, None),
+                                     ('bytes_value', 3, F.TYPE_BYTES, None), ('bool_value', 7, F.TYPE_BOOL, None),
+                                     ('int64_list', 4, F.TYPE_MESSAGE, 'Int64List'),
+                                     ('float_list', 5, F.TYPE_MESSAGE, 'FloatList'),
+                                     ('bytes_list', 6, F.TYPE_MESSAGE, 'BytesList'),
+                                     ('bool_list', 8, F.TYPE_MESSAGE, 'BoolList')):
+    f = pt.field.add(name=name, number=number, type=ftype, label=F.LABEL_OPTIONAL, oneof_index=0)
+    if tname:
+      f.type_name = '.ddd1d_test.HParamDef.' + tname
+  entry = hp.nested_type.add(name='HparamEntry')
+  entry.options.map_entry = True
+  entry.field.add(name='key', number=1, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+  entry.field.add(name='value', number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL,
+                  type_name='.ddd1d_test.HParamDef.ParamType')
+  hp.field.add(name='hparam', number=1, type=F.TYPE_MESSAGE, label=F.LABEL_REPEATED,
+               type_name='.ddd1d_test.HParamDef.HparamEntry')
+  # BundleEntryProto / TensorShapeProto (tensor_bundle.proto, tensor_shape.proto)
+  shape = fd.message_type.add(name='TensorShapeProto')
+  dim = shape.nested_type.add(name='Dim')
+  dim.field.add(name='size', number=1, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+  dim.field.add(name='name', number=2, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+  shape.field.add(name='dim', number=2, type=F.TYPE_MESSAGE, label=F.LABEL_REPEATED,
+                  type_name='.ddd1d_test.TensorShapeProto.Dim')
+  be = fd.message_type.add(name='BundleEntryProto')
+  be.field.add(name='dtype', number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+  be.field.add(name='shape', number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL,
+               type_name='.ddd1d_test.TensorShapeProto')
+  be.field.add(name='shard_id', number=3, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+  be.field.add(name='offset', number=4, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+  be.field.add(name='size', number=5, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+  be.field.add(name='crc32c', number=6, type=F.TYPE_FIXED32, label=F.LABEL_OPTIONAL)
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fd)
+  get = getattr(message_factory, 'GetMessageClass', None)
+  if get is None:
+    factory = message_factory.MessageFactory(pool)
+    get = factory.GetPrototype
+  return (get(pool.FindMessageTypeByName('ddd1d_test.HParamDef')),
+          get(pool.FindMessageTypeByName('ddd1d_test.BundleEntryProto')))
+
+
+def test_hparams_text_against_protobuf_text_format():
+  """`str(hparams.to_proto())` is protobuf's text_format of an HParamDef: parse what the protobuf runtime
+  prints, and let the protobuf runtime parse what we print."""
+  pytest.importorskip('google.protobuf')
+  from google.protobuf import text_format
+  HParamDef, _ = _proto_classes()
+  msg = HParamDef()
+  msg.hparam['equation'].bytes_value = b'ks'
+  msg.hparam['equation_kwargs'].bytes_value = b'{"num_points": 512, "period": 64.0}'
+  msg.hparam['conservative'].bool_value = True
+  msg.hparam['num_layers'].int64_value = 3
+  msg.hparam['polynomial_accuracy_scale'].float_value = 0.25
+  msg.hparam['noise_probability'].float_value = 1e-3
+  msg.hparam['learning_rates'].float_list.value.extend([1e-3, 1e-4])
+  msg.hparam['learning_stops'].int64_list.value.extend([20000, 40000])
+  msg.hparam['error_scale'].float_list.value.extend([float('nan')])
+  values = C.parse_hparams_pbtxt(text_format.MessageToString(msg))
+  assert values['equation'] == 'ks' and values['equation_kwargs'] == '{"num_points": 512, "period": 64.0}'
+  assert values['conservative'] is True and values['num_layers'] == 3
+  assert values['polynomial_accuracy_scale'] == 0.25
+  assert values['noise_probability'] == pytest.approx(1e-3, rel=1e-6)
+  assert values['learning_rates'] == pytest.approx([1e-3, 1e-4], rel=1e-6)
+  assert values['learning_stops'] == [20000, 40000] and np.isnan(values['error_scale'][0])
+  # and the other direction
+  hp = ddd.training.create_hparams('kdv', conservative=False, error_scale=[1.5, 2.0], num_layers=2)
+  parsed = text_format.Parse(C.format_hparams_pbtxt(hp.values()), HParamDef())
+  assert parsed.hparam['equation'].bytes_value == b'kdv' and parsed.hparam['num_layers'].int64_value == 2
+  assert list(parsed.hparam['error_scale'].float_list.value) == [1.5, 2.0]
+  assert parsed.hparam['conservative'].bool_value is False
+  assert len(parsed.hparam) == len(hp.values())
+
+
+def test_bundle_entry_wire_format_against_protobuf():
+  pytest.importorskip('google.protobuf')
+  _, BundleEntryProto = _proto_classes()
+  array = np.zeros((5, 32, 9), np.float32)
+  ours = C._encode_entry(array, offset=4096, crc=0x12345678)
+  msg = BundleEntryProto()
+  msg.ParseFromString(ours)
+  assert msg.dtype == 1 and [d.size for d in msg.shape.dim] == [5, 32, 9]
+  assert msg.offset == 4096 and msg.size == array.nbytes and msg.crc32c == 0x12345678
+  # and an entry serialised by the protobuf runtime parses with our reader
+  msg.shard_id = 0
+  msg.offset = 1 << 33
+  back = C._parse_entry(msg.SerializeToString())
+  assert back['shape'] == (5, 32, 9) and back['offset'] == 1 << 33 and back['crc32c'] == 0x12345678
