@@ -69,7 +69,7 @@ class ClockSampler(object):
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '100'],
+           '--format=csv,noheader,nounits', '-lms', '25'],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       threading.Thread(target=self._read, daemon=True).start()
     except OSError:
