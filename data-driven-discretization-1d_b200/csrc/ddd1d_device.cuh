@@ -65,7 +65,9 @@ struct Params {
   int smem_bytes;
   int use_bulk_copy;
   // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
-  int tc_teams, tc_nlast, tc_debug;      // tc_debug bit 0: skip the MMAs (timing experiments only)
+  // tc_debug (env DDD1D_TC_DEBUG): TIMING EXPERIMENTS ONLY, results are meaningless when set --
+  // bit 0 no MMAs (CUDA-core side alone), bit 2 issuers sleep when idle, bit 6 MMA stream alone (teams sit out)
+  int tc_teams, tc_nlast, tc_debug;
   int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
   int tc_t_act_hi, tc_t_act_lo;   // byte offsets of the activation planes inside a slot's shared region
   long long* tc_trace;            // debug: clock64 event trace of CTA 0 (DDD1D_TC_TRACE=<file>), else null
