@@ -291,3 +291,32 @@ def test_bundle_entry_wire_format_against_protobuf():
   msg.offset = 1 << 33
   back = C._parse_entry(msg.SerializeToString())
   assert back['shape'] == (5, 32, 9) and back['offset'] == 1 << 33 and back['crc32c'] == 0x12345678
+
+
+def test_checkpoint_round_trip_property(tmp_path):
+  """Random variable sets (names with shared prefixes, ranks 0-3, four dtypes, several index blocks)."""
+  hypothesis = pytest.importorskip('hypothesis')
+  from hypothesis import strategies as st
+
+  names = st.lists(st.text(alphabet='abc/_0123', min_size=1, max_size=24), min_size=1, max_size=12, unique=True)
+  counter = [0]
+
+  @hypothesis.settings(max_examples=25, deadline=None)
+  @hypothesis.given(names=names, seed=st.integers(0, 2**16), per_block=st.integers(1, 5))
+  def check(names, seed, per_block):
+    rs = np.random.RandomState(seed)
+    tensors = {}
+    for name in names:
+      shape = tuple(rs.randint(1, 5, size=rs.randint(0, 4)))
+      dtype = [np.float32, np.float64, np.int32, np.int64][rs.randint(4)]
+      tensors[name] = (rs.randn(*shape) * 100).astype(dtype)
+    counter[0] += 1
+    prefix = str(tmp_path / ('ckpt%d' % counter[0]))
+    C.write_checkpoint(prefix, tensors, entries_per_block=per_block)
+    back = C.read_checkpoint(prefix)
+    assert set(back) == set(tensors)
+    for name in tensors:
+      assert back[name].dtype == tensors[name].dtype and back[name].shape == tensors[name].shape
+      np.testing.assert_array_equal(back[name], tensors[name])
+
+  check()
