@@ -280,7 +280,7 @@ def write_checkpoint(prefix, tensors, entries_per_block=None):
   header = _field(1, 0, 1) + _field(3, 2, _field(1, 0, 1))        # num_shards = 1, version.producer = 1
   items.append((b'', header))
   for name in sorted(tensors):
-    array = np.ascontiguousarray(tensors[name])
+    array = np.asarray(tensors[name], order='C')         # (ascontiguousarray would turn scalars into shape (1,))
     if array.dtype not in _DTYPE_CODES:
       raise ValueError('unsupported dtype %s for %r' % (array.dtype, name))
     raw = array.astype(array.dtype.newbyteorder('<'), copy=False).tobytes()

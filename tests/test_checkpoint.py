@@ -309,7 +309,7 @@ def test_checkpoint_round_trip_property(tmp_path):
     for name in names:
       shape = tuple(rs.randint(1, 5, size=rs.randint(0, 4)))
       dtype = [np.float32, np.float64, np.int32, np.int64][rs.randint(4)]
-      tensors[name] = (rs.randn(*shape) * 100).astype(dtype)
+      tensors[name] = np.asarray(rs.randn(*shape) * 100).astype(dtype)
     counter[0] += 1
     prefix = str(tmp_path / ('ckpt%d' % counter[0]))
     C.write_checkpoint(prefix, tensors, entries_per_block=per_block)
