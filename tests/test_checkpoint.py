@@ -320,3 +320,49 @@ def test_checkpoint_round_trip_property(tmp_path):
       np.testing.assert_array_equal(back[name], tensors[name])
 
   check()
+
+
+def test_hparams_text_round_trip_property():
+  hypothesis = pytest.importorskip('hypothesis')
+  from hypothesis import strategies as st
+  from google.protobuf import text_format
+  HParamDef, _ = _proto_classes()
+  f32 = st.floats(width=32, allow_nan=False, allow_infinity=False)
+  text = st.text(max_size=20)
+  scalar = st.one_of(st.booleans(), st.integers(-2**62, 2**62), f32, text)
+  value = st.one_of(scalar, st.lists(st.booleans(), min_size=1, max_size=4), st.lists(st.integers(-2**40, 2**40), min_size=1, max_size=4),
+                    st.lists(f32, min_size=1, max_size=4), st.lists(text, min_size=1, max_size=3))
+  keys = st.text(alphabet='abcdefghijklmnopqrstuvwxyz_0123456789', min_size=1, max_size=16)
+
+  @hypothesis.settings(max_examples=60, deadline=None)
+  @hypothesis.given(values=st.dictionaries(keys, value, min_size=1, max_size=8))
+  def check(values):
+    written = C.format_hparams_pbtxt(values)
+    back = C.parse_hparams_pbtxt(written)
+    assert set(back) == set(values)
+    for k, v in values.items():
+      if isinstance(v, list):
+        assert len(back[k]) == len(v)
+        for a, b in zip(back[k], v):
+          assert a == b and type(a) is type(b)
+      else:
+        assert back[k] == v and type(back[k]) is type(v), (k, v, back[k])
+    # the protobuf runtime reads the same text
+    msg = text_format.Parse(written, HParamDef())
+    assert set(msg.hparam) == set(values)
+    for k, v in values.items():
+      if isinstance(v, str):
+        assert msg.hparam[k].bytes_value.decode('utf-8') == v
+      elif isinstance(v, bool):
+        assert msg.hparam[k].bool_value is v
+      elif isinstance(v, int):
+        assert msg.hparam[k].int64_value == v
+      elif isinstance(v, float):
+        assert msg.hparam[k].float_value == v
+    # ... and we read what the protobuf runtime prints
+    again = C.parse_hparams_pbtxt(text_format.MessageToString(msg))
+    for k, v in values.items():
+      if isinstance(v, (str, bool, int)) and not isinstance(v, list):
+        assert again[k] == v
+
+  check()
