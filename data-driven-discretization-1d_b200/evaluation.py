@@ -133,8 +133,10 @@ def mostly_good_survival(y_model, y_exact_high, times, quantile=0.8):
   model = _t(y_model)
   exact = _t(y_exact_high).to(model.device)
   flat = exact.abs().to(torch.float64).flatten()
-  # xarray/np.quantile: linear interpolation between order statistics, NaNs propagate
-  if torch.isnan(flat).any():
+  # DataArray.quantile: np.nanpercentile semantics -- NaNs are skipped, linear interpolation between order
+  # statistics
+  flat = flat[~torch.isnan(flat)]
+  if flat.numel() == 0:
     max_error = float('nan')
   else:
     srt = torch.sort(flat).values

@@ -54,6 +54,14 @@ def test_mostly_good_survival_matches_numpy():
   want = np.where(good.all(1), t.max(), t[np.argmin(good, axis=1)])
   np.testing.assert_array_equal(got, want)
   assert (got < t.max()).any() and (got > 0).any()       # the case is not degenerate
+  # NaNs in the exact solution are skipped by the quantile (DataArray.quantile = nanpercentile)
+  holed = exact_high.copy()
+  holed[0, -1, :3] = np.nan
+  got = E.mostly_good_survival(model, holed, t, quantile=q)
+  max_error = np.nanquantile(np.abs(holed), 1 - q)
+  low = holed.reshape(samples, times, n, factor).mean(-1)
+  good = (np.abs(model - low) <= max_error).mean(-1) >= q
+  np.testing.assert_array_equal(got, np.where(good.all(1), t.max(), t[np.argmin(good, axis=1)]))
 
 
 def test_results_round_trip(tmp_path):
