@@ -18,6 +18,54 @@ class HParams(object):
       setattr(self, name, value)
     return self
 
+  def set_hparam(self, name, value):
+    """tf.contrib.training.HParams.set_hparam: the name must exist, the value is cast to the
+    type of the current value (scripts/run_evaluation.py:131-132 overrides equation_kwargs this way)."""
+    if name not in self.__dict__:
+      raise KeyError('Hyperparameter {!r} does not exist'.format(name))
+    current = self.__dict__[name]
+    if isinstance(current, list):
+      if not isinstance(value, (list, tuple)):
+        raise ValueError('Must pass a list for multi-valued parameter: {}'.format(name))
+      kind = type(current[0]) if current else float
+      value = [self._cast(kind, v, name) for v in value]
+    else:
+      if isinstance(value, (list, tuple)):
+        raise ValueError('Must not pass a list for single-valued parameter: {}'.format(name))
+      value = self._cast(type(current), value, name)
+    setattr(self, name, value)
+
+  @staticmethod
+  def _cast(kind, value, name):
+    if kind is bool:
+      if isinstance(value, str):
+        if value.lower() in ('true', '1'):
+          return True
+        if value.lower() in ('false', '0'):
+          return False
+        raise ValueError('Could not parse {!r} as a bool for {}'.format(value, name))
+      return bool(value)
+    if kind is int and isinstance(value, float) and value != int(value):
+      raise ValueError('Could not cast {!r} to int for {}'.format(value, name))
+    return kind(value)
+
+  def parse(self, text):
+    """`name=value,name=[v1,v2],...` as accepted by the --hparams flag (scripts/run_training.py:47-51,73)."""
+    import re
+    pos, text = 0, text.strip()
+    pattern = re.compile(r'\s*([A-Za-z_][A-Za-z0-9_]*)\s*=\s*(\[[^\]]*\]|[^,\[]*)\s*(?:,|$)')
+    while pos < len(text):
+      m = pattern.match(text, pos)
+      if not m:
+        raise ValueError('Malformed hyperparameter value: {}'.format(text[pos:]))
+      pos = m.end()
+      name, raw = m.group(1), m.group(2).strip()
+      if raw.startswith('['):
+        self.set_hparam(name, [v.strip() for v in raw[1:-1].split(',') if v.strip()])
+      else:
+        self.set_hparam(name, raw)
+    return self
+
   def values(self):
     return copy.deepcopy(self.__dict__)
 

@@ -132,3 +132,22 @@ def test_no_oracle_import_in_product():
     if name.endswith('.py'):
       text = open(os.path.join(pkg, name)).read()
       assert 'oracle' not in text, name
+
+
+def test_hparams_set_and_parse():
+  """tf.contrib.training.HParams surface used by the scripts: set_hparam / parse with type casting."""
+  hp = training.create_hparams('burgers')
+  hp.set_hparam('equation_kwargs', '{"num_points": 128}')
+  hp.set_hparam('num_layers', 4.0)
+  assert hp.equation_kwargs == '{"num_points": 128}' and hp.num_layers == 4 and isinstance(hp.num_layers, int)
+  hp.parse('conservative=false, filter_size=16,nonlinearity=tanh,learning_rates=[0.01,0.001],resample_factor=8')
+  assert hp.conservative is False and hp.filter_size == 16 and hp.nonlinearity == 'tanh'
+  assert hp.learning_rates == [0.01, 0.001] and hp.resample_factor == 8
+  with pytest.raises(KeyError):
+    hp.set_hparam('nope', 1)
+  with pytest.raises(ValueError):
+    hp.set_hparam('num_layers', 2.5)
+  with pytest.raises(ValueError):
+    hp.set_hparam('learning_rates', 0.1)
+  with pytest.raises(ValueError):
+    hp.parse('filter_size')
