@@ -9,7 +9,7 @@ the two published on-disk formats:
 
 * checkpoint V2 "tensor bundle" (tensorflow/core/util/tensor_bundle): `<prefix>.index`
   is a LevelDB-format table (tensorflow/core/lib/io/table: prefix-compressed blocks,
-  restart array, 1-byte compression tag + masked CRC-32C trailer, 48-byte footer with
+  restart array, 1-byte compression tag (none | snappy, both read) + masked CRC-32C trailer, 48-byte footer with
   magic 0xdb4775248b80fb57) mapping "" -> BundleHeaderProto and every variable name ->
   BundleEntryProto {dtype, shape, shard_id, offset, size, crc32c};
   `<prefix>.data-00000-of-00001` holds the raw little-endian tensor bytes;
@@ -166,6 +166,46 @@ def _encode_entry(array, offset, crc):
 # ---------------------------------------------------------------------------------
 # LevelDB-format table
 # ---------------------------------------------------------------------------------
+def snappy_decompress(data):
+  """Raw Snappy block (format_description.txt of google/snappy): varint uncompressed length, then
+  literals (tag & 3 == 0) and back-references with 1-, 2- or 4-byte offsets.  tf.train.Saver writes its
+  index uncompressed (tensor_bundle.cc sets kNoCompression), but the table format allows type-1 blocks."""
+  total, pos = _read_varint(data, 0)
+  out = bytearray()
+  while pos < len(data):
+    tag = data[pos]
+    pos += 1
+    kind = tag & 3
+    if kind == 0:
+      length = (tag >> 2) + 1
+      if length > 60:                       # 61..64: the length follows in 1..4 little-endian bytes
+        extra = length - 60
+        length = int.from_bytes(data[pos:pos + extra], 'little') + 1
+        pos += extra
+      out += data[pos:pos + length]
+      pos += length
+      continue
+    if kind == 1:
+      length = ((tag >> 2) & 7) + 4
+      offset = ((tag >> 5) << 8) | data[pos]
+      pos += 1
+    elif kind == 2:
+      length = (tag >> 2) + 1
+      offset = int.from_bytes(data[pos:pos + 2], 'little')
+      pos += 2
+    else:
+      length = (tag >> 2) + 1
+      offset = int.from_bytes(data[pos:pos + 4], 'little')
+      pos += 4
+    if offset == 0 or offset > len(out):
+      raise ValueError('corrupt snappy block')
+    for _ in range(length):                 # byte by byte: references may overlap their own output
+      out.append(out[-offset])
+  if len(out) != total:
+    raise ValueError('corrupt snappy block: {} bytes, header says {}'.format(len(out), total))
+  return bytes(out)
+
+
 def _read_block(data, offset, size, verify):
   block = data[offset:offset + size]
   kind = data[offset + size]
@@ -175,8 +215,7 @@ def _read_block(data, offset, size, verify):
     if stored != actual:
       raise ValueError('checkpoint index block at %d fails its CRC-32C' % offset)
   if kind == 1:
-    raise NotImplementedError('snappy-compressed checkpoint index blocks are not supported '
-                              '(tf.train.Saver writes them uncompressed)')
+    return snappy_decompress(block)
   if kind != 0:
     raise ValueError('unknown block compression tag %d' % kind)
   return block

@@ -95,6 +95,65 @@ def test_checkpoint_detects_corruption(tmp_path):
     C.read_index(path)
 
 
+def test_snappy_decompress_hand_assembled_blocks(tmp_path):
+  # format_description.txt: literal 'a' + overlapping copy (offset 1, length 9)
+  assert C.snappy_decompress(bytes([10, 0x00, ord('a'), ((9 - 4) << 2) | 1, 1])) == b'a' * 10
+  # literal 'abcd', 2-byte-offset copy (offset 4, length 8), long literal with a 1-byte length
+  long_literal = bytes(range(70))
+  stream = bytes([4 + 8 + 70]) + bytes([(4 - 1) << 2]) + b'abcd' + bytes([((8 - 1) << 2) | 2, 4, 0]) + \
+      bytes([60 << 2, 70 - 1]) + long_literal
+  assert C.snappy_decompress(stream) == b'abcdabcdabcd' + long_literal
+  with pytest.raises(ValueError):
+    C.snappy_decompress(bytes([3, ((4 - 4) << 2) | 1, 9]))          # reference before the start
+  # an index whose data block is stored as a (literal-only) snappy block reads like the plain one
+  d = str(tmp_path / 'ckpt')
+  w = _weights(5)
+  C.save_conv_weights(d, w)
+  path = os.path.join(d, 'model.ckpt.index')
+  raw = open(path, 'rb').read()
+  header, entries = C.read_index(path)
+  footer = raw[-48:]
+  pos = 0
+  _, pos = C._read_varint(footer, pos)
+  _, pos = C._read_varint(footer, pos)
+  index_offset, pos = C._read_varint(footer, pos)
+  index_size, pos = C._read_varint(footer, pos)
+  (_, handle), = C._block_entries(raw[index_offset:index_offset + index_size])
+  block_offset, p = C._read_varint(handle, 0)
+  block_size, p = C._read_varint(handle, p)
+  assert block_offset == 0
+  block = raw[:block_size]
+
+  def literal_only(data):
+    out = bytearray(C._write_varint(len(data)))
+    for i in range(0, len(data), 60):
+      chunk = data[i:i + 60]
+      out.append((len(chunk) - 1) << 2)
+      out += chunk
+    return bytes(out)
+
+  packed = literal_only(block)
+  rebuilt = bytearray()
+
+  def emit(payload, kind):
+    offset = len(rebuilt)
+    rebuilt.extend(payload)
+    rebuilt.append(kind)
+    rebuilt.extend(struct.pack('<I', C.mask_crc(C.crc32c(payload + bytes([kind])))))
+    return C._write_varint(offset) + C._write_varint(len(payload))
+
+  data_handle = emit(packed, 1)
+  meta_handle = emit(C._build_block([]), 0)
+  index_handle = emit(C._build_block([(b'\xff', data_handle)], restart_interval=1), 0)
+  foot = meta_handle + index_handle
+  rebuilt.extend(foot + b'\x00' * (40 - len(foot)) + struct.pack('<Q', 0xdb4775248b80fb57))
+  open(path, 'wb').write(bytes(rebuilt))
+  got = C.load_conv_weights(d)
+  for (k0, b0), (k1, b1) in zip(w, got):
+    np.testing.assert_array_equal(k0, k1)
+    np.testing.assert_array_equal(b0, b1)
+
+
 def test_block_prefix_compression():
   # keys sharing prefixes, restart interval 2: the reader must rebuild keys from (shared, unshared)
   items = [(b'predict_coefficients/conv1d/bias', b'A'), (b'predict_coefficients/conv1d/kernel', b'BB'),
