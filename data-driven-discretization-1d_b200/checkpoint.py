@@ -488,6 +488,13 @@ def parse_hparams_pbtxt(text):
   return out
 
 
+def _c_escape(data):
+  """protobuf text_format's CEscape (as_utf8=False): printable ASCII as is, the usual C escapes,
+  everything else as three-digit octal."""
+  table = {9: '\\t', 10: '\\n', 13: '\\r', 34: '\\"', 39: "\\'", 92: '\\\\'}
+  return ''.join(table.get(b) or (chr(b) if 32 <= b < 127 else '\\%03o' % b) for b in data)
+
+
 def format_hparams_pbtxt(values):
   """{name: value} -> the text `str(HParams.to_proto())` produces (map entries sorted by key)."""
   def kind_of(v):
@@ -505,7 +512,7 @@ def format_hparams_pbtxt(values):
     if kind == 'bool':
       return 'true' if v else 'false'
     if kind == 'bytes':
-      return '"%s"' % v.replace('\\', '\\\\').replace('"', '\\"')
+      return '"%s"' % _c_escape(v.encode('utf-8'))
     if kind == 'float':
       return repr(float(np.float32(v))) if np.isfinite(v) else str(v)
     return str(v)
