@@ -360,7 +360,7 @@ def test_checkpoint_round_trip_property(tmp_path):
   names = st.lists(st.text(alphabet='abc/_0123', min_size=1, max_size=24), min_size=1, max_size=12, unique=True)
   counter = [0]
 
-  @hypothesis.settings(max_examples=25, deadline=None)
+  @hypothesis.settings(max_examples=25, deadline=None, derandomize=True, database=None)
   @hypothesis.given(names=names, seed=st.integers(0, 2**16), per_block=st.integers(1, 5))
   def check(names, seed, per_block):
     rs = np.random.RandomState(seed)
@@ -393,7 +393,7 @@ def test_hparams_text_round_trip_property():
                     st.lists(f32, min_size=1, max_size=4), st.lists(text, min_size=1, max_size=3))
   keys = st.text(alphabet='abcdefghijklmnopqrstuvwxyz_0123456789', min_size=1, max_size=16)
 
-  @hypothesis.settings(max_examples=60, deadline=None)
+  @hypothesis.settings(max_examples=60, deadline=None, derandomize=True, database=None)
   @hypothesis.given(values=st.dictionaries(keys, value, min_size=1, max_size=8))
   def check(values):
     written = C.format_hparams_pbtxt(values)
