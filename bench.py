@@ -327,7 +327,7 @@ def quick_rate(workload, steps=4, rk=None, engine='auto', batch=None):
   wl = workloads()
   kind, variant, n, default_batch, dt, mode = wl.WORKLOADS[workload]
   batch = batch or default_batch
-  rk = rk or {'c5': 10, 'c1b': 200}.get(workload, 50)
+  rk = rk or {'c5': 10}.get(workload, 50)        # c1b: 4 x 50 = config 1's 200 steps (T = 2)
   integrator, dt, n = build_case(workload, batch, engine=engine)
   solver = integrator.solver
   dev = torch.device('cuda', torch.cuda.current_device())
