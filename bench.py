@@ -342,7 +342,7 @@ def quick_rate(workload, steps=4, rk=None, engine='auto', batch=None):
   eng = solver.engine() if mode == 'learned' else None
   res = {'value': gps, 'unit': 'grid-point-steps/s', 'batch': batch, 'num_points': n, 'rk_steps_per_launch': rk,
          'kernel_ms': kernel_ms, 'engine': eng, 'hbm_frac': 8.0 * gps / 1e9 / peaks['hbm_gbs']}
-  if eng == 'tensor':
+  if eng and eng.startswith('tensor'):
     res['tensor_frac_burst'] = flops_per_gps(kind, mode) * gps / 1e12 / peaks['bf16_tflops']
   else:
     res['fp32_frac_nominal'] = flops_per_gps(kind, mode) * gps / 1e12 / FP32_PEAK_TFLOPS
@@ -459,7 +459,7 @@ def run_ours(args):
   fl = flops_per_gps(kind, mode)
   shape = solver.launch_shape(batch)
   engine = solver.engine() if mode == 'learned' else 'ffma'
-  kernel_name = 'ddd1d::tc::tc_row_kernel' if engine == 'tensor' else 'ddd1d::row_kernel<%s>' % mode
+  kernel_name = 'ddd1d::tc::tc_row_kernel' if engine.startswith('tensor') else 'ddd1d::row_kernel<%s>' % mode
   traffic = None
   tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
   if os.path.exists(tpath):
@@ -472,7 +472,7 @@ def run_ours(args):
          'algorithmic_bytes_per_launch': 8.0 * batch * n * rk,
          'note': 'rows stay on chip for all RK steps of a launch, so HBM is idle by design; the binding resource is on-chip'}
   achieved_tf = fl * gps_kernel / 1e12
-  if engine == 'tensor':
+  if engine.startswith('tensor'):
     burst = peaks['bf16_tflops']
     sustained = peaks.get('bf16_tflops_sustained', burst)
     roofline = {'bound': 'tensor', 'achieved': achieved_tf, 'peak': burst, 'unit': 'TFLOP/s',
@@ -556,7 +556,7 @@ def main():
   ap.add_argument('--batch', type=int, default=0, help='per-GPU batch override')
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='weak: the per-GPU batch is fixed; strong: %d rows in all, split over the GPUs' % STRONG_BATCH)
-  ap.add_argument('--engine', default='auto', choices=['auto', 'ffma', 'tensor'])
+  ap.add_argument('--engine', default='auto', choices=['auto', 'ffma', 'tensor', 'tensor_f16x2', 'tensor_f16'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   ap.add_argument('--extra', default='c3,c4,c5,c1b,c2s',
                   help="other workloads measured briefly at N=1 and reported under 'other_workloads' ('' = none)")

@@ -7,6 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libddd1d.so')
+DEBUG_LIB_PATH = os.path.join(_HERE, 'libddd1d_debug.so')     # test-only laboratory kernels
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ESTATE = 0, -1, -2, -3, -4
 BURGERS, KDV, KS = 0, 1, 2
@@ -17,7 +18,8 @@ PROJ_NULLSPACE, PROJ_RAW, PROJ_RAW_UNBIASED = 0, 1, 2
 PROJ_DERIVATIVES, PROJ_TIME_DERIVATIVE, PROJ_FLUX = 3, 4, 5
 SCHEMES = {'rk3': 0, 'RK23': 0, 'bogacki_shampine': 0, 'midpoint': 1, 'euler': 2, 'rk4': 3}
 REAL_F32, REAL_F64 = 0, 1
-ENGINES = {'auto': 0, 'ffma': 1, 'tensor': 2}
+ENGINES = {'auto': 0, 'ffma': 1, 'tensor': 2, 'tensor_f16x2': 3, 'tensor_f16': 4}
+ENGINE_NAMES = {v: k for k, v in ENGINES.items() if v}
 WINDOW = 7
 
 
@@ -75,7 +77,7 @@ _SIGNATURES = {
     'ddd1d_engine': (ctypes.c_int, [_P]),
 }
 
-# test-only entry points (include/ddd1d_debug.h)
+# test-only entry points (include/ddd1d_debug.h), in their own library: load_debug()
 _DEBUG_SIGNATURES = {
     'ddd1d_debug_tc_probe': (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_int, _P]),
     'ddd1d_debug_tc_rate': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
@@ -97,7 +99,7 @@ def load():
           '%s not found: run `python __graft_entry__.py` (nvcc, sm_100a) first; '
           'there is no CPU fallback' % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (restype, argtypes) in list(_SIGNATURES.items()) + list(_DEBUG_SIGNATURES.items()):
+    for name, (restype, argtypes) in _SIGNATURES.items():
       fn = getattr(lib, name)
       fn.restype = restype
       fn.argtypes = argtypes
@@ -105,6 +107,25 @@ def load():
       raise Ddd1dError('libddd1d version %d, binding expects 1' % lib.ddd1d_version())
     _lib = lib
   return _lib
+
+
+_debug_lib = None
+
+
+def load_debug():
+  """The laboratory kernels of the tensor engine (descriptor probe, MMA rate / overlap microbenchmarks):
+  tests and scripts only, never loaded by the product path."""
+  global _debug_lib
+  if _debug_lib is None:
+    if not os.path.exists(DEBUG_LIB_PATH):
+      raise LibraryMissing('%s not found: run `python __graft_entry__.py` first' % DEBUG_LIB_PATH)
+    lib = ctypes.CDLL(DEBUG_LIB_PATH)
+    for name, (restype, argtypes) in _DEBUG_SIGNATURES.items():
+      fn = getattr(lib, name)
+      fn.restype = restype
+      fn.argtypes = argtypes
+    _debug_lib = lib
+  return _debug_lib
 
 
 def check(code, handle=None):

@@ -14,9 +14,9 @@
 #include <vector>
 
 #include "../../include/ddd1d.h"
-#include "../../include/ddd1d_debug.h"
 #include "ddd1d_device.cuh"
 #include "ddd1d_tc.cuh"
+#include "ddd1d_tc_host.h"
 #include "ddd1d_warp.cuh"
 
 using namespace ddd1d;
@@ -56,13 +56,13 @@ struct ddd1d_handle {
   int threads = 0, blocks_per_sm = 0, num_sms = 0;
   long long launches = 0;
   // tensor-core engine
-  Params Ptc;
+  tc::TcParams Ptc;
+  tc::TcEntry tc_entry;
   bool tc_ok = false;
+  int tc_engine = DDD1D_ENGINE_TENSOR;
   std::string tc_why;
   float* d_blob_tc = nullptr;
-  long long* d_trace_tc = nullptr; // debug event trace (DDD1D_TC_TRACE)
   float* d_scratch_tc = nullptr;   // tensor engine: per-CTA exchange scratch (stage rows, maxima, flux, forcing)
-  int tc_threads = 0;
   // staging for the *_host entry points
   void* d_stage_in = nullptr;
   void* d_stage_out = nullptr;
@@ -120,34 +120,58 @@ int engine_request(const ddd1d_handle* h) {
   if (e == DDD1D_ENGINE_AUTO && env) {
     if (!strcmp(env, "ffma")) e = DDD1D_ENGINE_FFMA;
     if (!strcmp(env, "tensor")) e = DDD1D_ENGINE_TENSOR;
+    if (!strcmp(env, "tensor_f16x2")) e = DDD1D_ENGINE_TENSOR_F16X2;
+    if (!strcmp(env, "tensor_f16")) e = DDD1D_ENGINE_TENSOR_F16;
   }
   return e;
 }
 
-// Build the tensor-core engine's blob and shared-memory plan (ddd1d_tc.cuh) when the net has the
-// shape that kernel is written for.  Not being eligible is not an error unless the caller forced
-// DDD1D_ENGINE_TENSOR.
+bool wants_tensor(int e) {
+  return e == DDD1D_ENGINE_TENSOR || e == DDD1D_ENGINE_TENSOR_F16X2 || e == DDD1D_ENGINE_TENSOR_F16;
+}
+
+// Build the tensor-core engine's operand blob and constant-bank tables (ddd1d_tc.cuh) when the net has the
+// shape that kernel is written for.  Not being eligible is not an error unless the caller forced a
+// DDD1D_ENGINE_TENSOR* engine.
 int finalize_tc(ddd1d_handle* h) {
   const ddd1d_config& c = h->cfg;
   h->tc_ok = false;
   h->tc_why.clear();
   const int N = c.num_points, D = c.num_derivatives;
   const int want = engine_request(h);
+  int tiles = 0, rpt = 1;
+  switch (N) {
+    case 128: tiles = 1; break;
+    case 256: tiles = 2; break;
+    case 512: tiles = 4; break;
+    case 64: tiles = 1; rpt = 2; break;      // two rows per 128-position tile
+    case 32: tiles = 1; rpt = 4; break;      // four
+    default: break;
+  }
   if (c.mode != DDD1D_MODE_LEARNED) h->tc_why = "not a learned-coefficient handle";
   else if (c.kernel_size != 5 || c.filter_size != tc::kF) h->tc_why = "needs kernel_size 5 and filter_size 32";
   else if (c.num_layers < 2 || c.num_layers > 3) h->tc_why = "needs 2 or 3 conv layers";
   else if (c.activation != DDD1D_ACT_RELU) h->tc_why = "needs the relu nonlinearity";
   else if (c.projection > DDD1D_PROJ_RAW_UNBIASED) h->tc_why = "only model_target='coefficients'";
-  else if (N != 128 && N != 256 && N != 512) h->tc_why = "needs num_points in {128, 256, 512}";
+  else if (tiles == 0) h->tc_why = "needs num_points in {32, 64, 128, 256, 512}";
+  else if (h->forcing_batch > 0 && h->forcing_P > 0 && h->forcing_M > kMaxModes) h->tc_why = "too many forcing modes";
   if (!h->tc_why.empty() || want == DDD1D_ENGINE_FFMA) {
-    if (want == DDD1D_ENGINE_TENSOR)
+    if (wants_tensor(want))
       return fail(h, DDD1D_EUNSUPPORTED, "tensor engine unavailable: %s", h->tc_why.c_str());
     return DDD1D_OK;
   }
-  Params P = h->P;   // equation / forcing / projection scalars are shared
+  const int prec = want == DDD1D_ENGINE_TENSOR_F16 ? 1 : want == DDD1D_ENGINE_TENSOR_F16X2 ? 2 : 3;
   const int L = c.num_layers;
   const int NL = (D * kWin <= 16) ? 16 : 32;
   const int K = 5, F = tc::kF;
+  tc::TcEntry entry;
+  if (!tc::lookup(tiles, rpt, NL, prec, &entry)) {
+    h->tc_why = "this (num_points, precision) combination is not compiled";
+    if (wants_tensor(want)) return fail(h, DDD1D_EUNSUPPORTED, "tensor engine unavailable: %s", h->tc_why.c_str());
+    return DDD1D_OK;
+  }
+  tc::TcParams T;
+  memset(&T, 0, sizeof(T));
   // linear map net channel -> window coefficient (projection folded into the last layer)
   const int Q = D * kWin;
   std::vector<double> pm((size_t)c.net_outputs * Q, 0.0), pbias(Q, 0.0);
@@ -168,19 +192,18 @@ int finalize_tc(ddd1d_handle* h) {
           pm[(size_t)(d * S + i2) * Q + d * kWin + i + ws] = v;
         }
   }
-  std::vector<float> blob;
-  auto reserve = [&](size_t n) { size_t off = blob.size(); blob.resize(off + n, 0.f); return (int)off; };
-  // Operand format of the tensor layers: fp16 x 2 planes, value * scale = hi + lo' * 2^-11 (~22 significant
-  // bits per operand, K = 16 per MMA); scales are powers of two, so they are exact.
-  const int planes = tc::kChunks / 2;     // 16-byte chunk planes per tap
-  const int cpp = 8;                      // input channels per 16-byte chunk
+  // Operand format of the tensor layers: fp16 planes, value * scale = hi + lo (~22 significant bits per
+  // operand, K = 16 per MMA); scales are powers of two, so they are exact.
+  std::vector<float> blob((size_t)(entry.blob_hidden_bytes + entry.blob_last_bytes) / 4, 0.f);
+  const int planes = 4;                   // 16-byte chunk planes per tap (8 input channels each)
+  const int cpp = 8;
   auto pow2_scale = [](double maxabs) {                       // largest 2^e with maxabs * 2^e < 2^14
     if (!(maxabs > 0.0)) return 1.0;
     int e;
     std::frexp(maxabs, &e);
     return std::ldexp(1.0, std::min(14 - e, 60));
   };
-  // writes one filter value into a [Whi | Wlo] plane pair (rows = 2 * nb)
+  // writes one filter value into a [Wh | Wl] plane pair (rows = 2 * nb)
   auto put_weight = [&](float* cat, int nb, int k, int ci, int col, double w, double sw) {
     const size_t plane = (size_t)(k * planes + ci / cpp) * (2 * nb) * 4;      // in floats (16 B per row)
     __half* hp = reinterpret_cast<__half*>(cat + plane);
@@ -189,52 +212,39 @@ int finalize_tc(ddd1d_handle* h) {
     hp[(size_t)col * 8 + (ci % 8)] = hi;
     hp[(size_t)(nb + col) * 8 + (ci % 8)] = __float2half_rn((v - __half2float(hi)) * tc::kLoScale);
   };
-  // first layer [5][32] + bias
   const HostLayer& l0 = h->layers[0];
-  P.tc_w1_off = reserve(K * F);
   for (int k = 0; k < K; ++k)
-    for (int co = 0; co < F; ++co) blob[P.tc_w1_off + k * F + co] = (L == 1) ? 0.f : l0.kernel[(size_t)k * F + co];
-  P.tc_b1_off = reserve(F);
-  for (int co = 0; co < F; ++co) blob[P.tc_b1_off + co] = l0.bias[co];
-  // hidden tensor-core layers
-  const int nhid = L - 2;
-  P.tc_bh_off = reserve((size_t)std::max(nhid, 1) * F);
-  P.tc_bl_off = reserve(32);
-  P.tc_bhid_stride = 2 * K * planes * F * 4;   // planes [tap*planes+chunk][2F rows: Whi then Wlo][16 B]
-  P.tc_w1abs = P.tc_b1abs = P.tc_whabs = P.tc_bhabs = 0.f;
-  P.tc_inv_sw_hid = P.tc_inv_sw_last = 1.f;
+    for (int co = 0; co < F; ++co) T.w1[k * F + co] = l0.kernel[(size_t)k * F + co];
+  T.inv_sw_hid = T.inv_sw_last = 1.f;
   for (int co = 0; co < F; ++co) {
+    T.b1[co] = l0.bias[co];
     double a = 0.0;
     for (int k = 0; k < K; ++k) a += std::fabs((double)l0.kernel[(size_t)k * F + co]);
-    P.tc_w1abs = std::max(P.tc_w1abs, (float)(a * (1.0 + 1e-6)));
-    P.tc_b1abs = std::max(P.tc_b1abs, std::fabs(l0.bias[co]));
+    T.w1abs = std::max(T.w1abs, (float)(a * (1.0 + 1e-6)));
+    T.b1abs = std::max(T.b1abs, std::fabs(l0.bias[co]));
   }
-  P.tc_bhid_lo = 0;
-  P.tc_bhid_off = reserve((size_t)std::max(nhid, 0) * P.tc_bhid_stride);
-  for (int l = 0; l < nhid; ++l) {
-    const HostLayer& hl = h->layers[1 + l];
-    for (int co = 0; co < F; ++co) blob[P.tc_bh_off + l * F + co] = hl.bias[co];
-    float* cat = blob.data() + P.tc_bhid_off + (size_t)l * P.tc_bhid_stride;
+  T.nhid = L - 2;
+  if (T.nhid == 1) {
+    const HostLayer& hl = h->layers[1];
     double wmax = 0.0;
     for (size_t i = 0; i < (size_t)K * F * F; ++i) wmax = std::max(wmax, std::fabs((double)hl.kernel[i]));
     const double sw = pow2_scale(wmax);
-    P.tc_inv_sw_hid = (float)(1.0 / sw);
+    T.inv_sw_hid = (float)(1.0 / sw);
     for (int co = 0; co < F; ++co) {
+      T.bh[co] = hl.bias[co];
       double a = 0.0;
       for (int k = 0; k < K; ++k)
         for (int ci = 0; ci < F; ++ci) a += std::fabs((double)hl.kernel[((size_t)k * F + ci) * F + co]);
-      P.tc_whabs = std::max(P.tc_whabs, (float)(a * (1.0 + 1e-6)));
-      P.tc_bhabs = std::max(P.tc_bhabs, std::fabs(hl.bias[co]));
+      T.whabs = std::max(T.whabs, (float)(a * (1.0 + 1e-6)));
+      T.bhabs = std::max(T.bhabs, std::fabs(hl.bias[co]));
     }
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
-        for (int co = 0; co < F; ++co) put_weight(cat, F, k, ci, co, hl.kernel[((size_t)k * F + ci) * F + co], sw);
+        for (int co = 0; co < F; ++co) put_weight(blob.data(), F, k, ci, co, hl.kernel[((size_t)k * F + ci) * F + co], sw);
   }
   // last layer with the projection folded in: W'[k][ci][q] = sum_c W[k][ci][c] pm[c][q]
-  const HostLayer& ll = h->layers[L - 1];
-  P.tc_blast_lo = 0;
-  P.tc_blast_off = reserve((size_t)2 * K * planes * NL * 4);
   {
+    const HostLayer& ll = h->layers[L - 1];
     std::vector<double> folded((size_t)K * F * Q, 0.0);
     double wmax = 0.0;
     for (int k = 0; k < K; ++k)
@@ -247,97 +257,61 @@ int finalize_tc(ddd1d_handle* h) {
           wmax = std::max(wmax, std::fabs(acc));
         }
     const double sw = pow2_scale(wmax);
-    P.tc_inv_sw_last = (float)(1.0 / sw);
-    float* cat = blob.data() + P.tc_blast_off;
+    T.inv_sw_last = (float)(1.0 / sw);
+    float* cat = blob.data() + entry.blob_hidden_bytes / 4;
     for (int k = 0; k < K; ++k)
       for (int ci = 0; ci < F; ++ci)
         for (int q = 0; q < Q; ++q) put_weight(cat, NL, k, ci, q, folded[((size_t)k * F + ci) * Q + q], sw);
     for (int q = 0; q < Q; ++q) {
       double acc = pbias[q];
       for (int ch = 0; ch < c.net_outputs; ++ch) acc += (double)ll.bias[ch] * pm[(size_t)ch * Q + q];
-      blob[P.tc_bl_off + q] = (float)acc;
+      T.bl[q] = (float)acc;
     }
   }
-  for (int i = 0; i < K * F; ++i) P.tc_w1[i] = blob[P.tc_w1_off + i];
-  for (int i = 0; i < F; ++i) {
-    P.tc_b1[i] = blob[P.tc_b1_off + i];
-    P.tc_bh[i] = blob[P.tc_bh_off + i];
-    P.tc_bl[i] = blob[P.tc_bl_off + i];
-  }
-  blob.resize(align_up((int)blob.size(), 32), 0.f);
-  P.blob_floats = (int)blob.size();
-  P.tc_nlast = NL;
-  P.tc_debug = getenv("DDD1D_TC_DEBUG") ? atoi(getenv("DDD1D_TC_DEBUG")) : 0;
-  // shared-memory plan: 512 / N row teams, each with up to two rows (slots) in flight.  A slot's shared
-  // region holds only its activation planes; what threads exchange goes through the global scratch.
-  const int plane = (N + 4) * 16;
-  int t = 0;
-  P.tc_t_act_hi = t; t += planes * plane;
-  P.tc_t_act_lo = t; t += planes * plane;
-  P.tc_team_stride = align_up(t, 128);
-  {
-    int f = 0;
-    f += 2 * 2 * (N + 2 * kHalo + 2);                       // (raw row + row / sigma) x stage parity
-    P.tc_sc_umax = f; f += 16;                              // row maximum of |u / sigma| (calibration only)
-    P.tc_sc_flux = f; f += N;
-    P.tc_sc_fs = f; f += tc::kFsWords + 4;                  // forcing amplitude sets + first-bad-step word
-    P.tc_sc_stride = align_up(f, 32);
-  }
-  P.off_bar = 0;                            // 1 + 2 * (teams * slots) <= 17 mbarriers
-  P.tc_off_slot = 144;                      // TMEM base address
-  P.off_blob = 256;
-  P.tc_off_team0 = align_up(P.off_blob + P.blob_floats * 4, 128);
-  P.tc_teams = 512 / N;
-  P.tc_slots = 2;                           // TMEM: teams * slots * (N / 128) tiles * 64 columns = 512
-  if (getenv("DDD1D_TC_SLOTS")) P.tc_slots = std::max(1, std::min(2, atoi(getenv("DDD1D_TC_SLOTS"))));
-  auto plan_bytes = [&]() { return P.tc_off_team0 + P.tc_teams * P.tc_slots * P.tc_team_stride; };
-  if (plan_bytes() > 227 * 1024) P.tc_slots = 1;
-  while (P.tc_teams > 1 && plan_bytes() > 227 * 1024) P.tc_teams -= 1;
-  P.smem_bytes = plan_bytes();
-  if (P.smem_bytes > 227 * 1024) {
-    h->tc_why = "shared memory plan does not fit";
-    if (want == DDD1D_ENGINE_TENSOR)
-      return fail(h, DDD1D_EUNSUPPORTED, "tensor engine needs %d bytes of shared memory", P.smem_bytes);
-    return DDD1D_OK;
-  }
+  T.eq = h->P.eq; T.D = D; T.S = c.stencil_size; T.wshift = 3 - (c.stencil_size / 2);
+  T.M = h->P.M; T.P = h->P.P; T.fcap = h->P.fcap;
+  T.sigma = h->P.sigma; T.eta = h->P.eta; T.inv_dx = h->P.inv_dx;
+  T.fparams = h->P.fparams; T.fbasis = h->P.fbasis;
+  T.debug = getenv("DDD1D_TC_DEBUG") ? atoi(getenv("DDD1D_TC_DEBUG")) : 0;
   CUDA_TRY(h, cudaSetDevice(c.device));
   if (h->d_blob_tc) CUDA_TRY(h, cudaFree(h->d_blob_tc));
+  h->d_blob_tc = nullptr;
   CUDA_TRY(h, cudaMalloc(&h->d_blob_tc, blob.size() * sizeof(float)));
   CUDA_TRY(h, cudaMemcpy(h->d_blob_tc, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
-  P.blob = h->d_blob_tc;
+  T.blob = h->d_blob_tc;
   if (h->d_scratch_tc) CUDA_TRY(h, cudaFree(h->d_scratch_tc));
   h->d_scratch_tc = nullptr;
-  const size_t scratch_floats = (size_t)h->num_sms * P.tc_teams * P.tc_slots * P.tc_sc_stride;
+  const size_t scratch_floats = (size_t)h->num_sms * entry.slots_per_cta * entry.sc_stride;
   CUDA_TRY(h, cudaMalloc(&h->d_scratch_tc, scratch_floats * sizeof(float)));
   CUDA_TRY(h, cudaMemset(h->d_scratch_tc, 0, scratch_floats * sizeof(float)));
-  P.tc_scratch = h->d_scratch_tc;
-  P.tc_trace = nullptr;
-  if (getenv("DDD1D_TC_TRACE")) {       // debug: [8 streams][kTraceCap] (tag << 48 | clock) records of CTA 0
-    if (!h->d_trace_tc) CUDA_TRY(h, cudaMalloc(&h->d_trace_tc, sizeof(long long) * 8 * tc::kTraceCap));
-    P.tc_trace = h->d_trace_tc;
-  }
-  const void* kern = (const void*)tc::tc_row_kernel;
-  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes));
-  P.tc_issuers = N == 128 ? 4 : 2;
-  if (getenv("DDD1D_TC_ISSUERS")) P.tc_issuers = std::max(1, std::min(tc::kMaxIssuers, atoi(getenv("DDD1D_TC_ISSUERS"))));
-  P.tc_issuers = std::min(P.tc_issuers, P.tc_teams * P.tc_slots);
-  h->tc_threads = P.tc_teams * N + 32 * P.tc_issuers;       // thread <-> grid point, plus the warps that issue the MMAs
+  T.scratch = h->d_scratch_tc;
+  CUDA_TRY(h, cudaFuncSetAttribute(entry.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, entry.smem_bytes));
   int occ = 0;
-  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, h->tc_threads, P.smem_bytes));
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, entry.kernel, entry.threads, entry.smem_bytes));
   if (occ < 1) {
     h->tc_why = "tensor kernel does not fit on an SM";
-    if (want == DDD1D_ENGINE_TENSOR) return fail(h, DDD1D_EUNSUPPORTED, "%s", h->tc_why.c_str());
+    if (wants_tensor(want)) return fail(h, DDD1D_EUNSUPPORTED, "%s", h->tc_why.c_str());
     return DDD1D_OK;
   }
-  h->Ptc = P;
+  h->tc_entry = entry;
+  h->Ptc = T;
   h->tc_ok = true;
+  h->tc_engine = prec == 1 ? DDD1D_ENGINE_TENSOR_F16 : prec == 2 ? DDD1D_ENGINE_TENSOR_F16X2 : DDD1D_ENGINE_TENSOR;
   return DDD1D_OK;
+}
+
+// CTAs of a tensor-engine launch: every team takes two slots per round
+int tc_grid(const ddd1d_handle* h, int batch) {
+  const tc::TcEntry& e = h->tc_entry;
+  const int units = (batch + e.rows_per_slot - 1) / e.rows_per_slot;
+  const int teams = e.slots_per_cta / 2;
+  return std::max(1, std::min((units + teams - 1) / teams, h->num_sms));
 }
 
 bool use_tc(const ddd1d_handle* h) {
   if (!h->tc_ok) return false;
   const int want = engine_request(h);
-  if (want == DDD1D_ENGINE_TENSOR) return true;
+  if (wants_tensor(want)) return true;
   if (want == DDD1D_ENGINE_FFMA) return false;
   return DDD1D_AUTO_PREFERS_TENSOR != 0;
 }
@@ -545,28 +519,15 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
   if (W.batch <= 0) return DDD1D_OK;
   const ddd1d_config& c = h->cfg;
   const Params& P = h->P;
-  if (c.equation == DDD1D_BURGERS && P.P > 0 && (W.op == OP_RHS || W.op == OP_INTEGRATE) &&
+  if (c.equation == DDD1D_BURGERS && P.P > 0 && (W.op == OP_RHS || W.op == OP_INTEGRATE || W.op == OP_ADAPTIVE) &&
       (W.sample_offset < 0 || W.sample_offset + W.batch > P.fcap))
     return fail(h, DDD1D_EINVAL, "samples [%d, %d) exceed the %d forcing rows set", W.sample_offset,
                 W.sample_offset + W.batch, P.fcap);
   CUDA_TRY(h, cudaSetDevice(c.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_tc(h) && W.op != OP_ADAPTIVE) {
-    const Params& T = h->Ptc;
-    const int teams_needed = (W.batch + T.tc_teams - 1) / T.tc_teams;
-    const int grid_tc = std::min(teams_needed, h->num_sms);
-    if (T.tc_trace) CUDA_TRY(h, cudaMemsetAsync(T.tc_trace, 0, sizeof(long long) * 8 * tc::kTraceCap, st));
-    tc::tc_row_kernel<<<grid_tc, h->tc_threads, T.smem_bytes, st>>>(T, W, make_tableau(W.scheme));
+    h->tc_entry.launch(h->Ptc, W, make_tableau(W.scheme), tc_grid(h, W.batch), st);
     CUDA_TRY(h, cudaGetLastError());
-    if (T.tc_trace) {                    // debug only: synchronous dump of the last launch's trace
-      std::vector<long long> host((size_t)8 * tc::kTraceCap);
-      CUDA_TRY(h, cudaStreamSynchronize(st));
-      CUDA_TRY(h, cudaMemcpy(host.data(), T.tc_trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      if (FILE* f = fopen(getenv("DDD1D_TC_TRACE"), "wb")) {
-        fwrite(host.data(), sizeof(long long), host.size(), f);
-        fclose(f);
-      }
-    }
     h->launches += 1;
     return DDD1D_OK;
   }
@@ -628,17 +589,18 @@ int ensure_stage(ddd1d_handle* h, void** buf, size_t* have, size_t need) {
 
 }  // namespace
 
-namespace {
-template <int KIND, int N1, int N2, int BROWS, int ALT, int DOFF2 = 128>
-int run_rate(int reps, int blocks, long long* d) {
-  const int smem = 128 + 2 * tc::kChunks * 516 * 16 + tc::kTaps * tc::kChunks * BROWS * 16;
-  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT, DOFF2>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT, DOFF2><<<blocks, 128, smem>>>(reps, d);
-  CUDA_TRY(nullptr, cudaGetLastError());
-  return DDD1D_OK;
+namespace ddd1d {
+namespace tc {
+bool lookup(int tiles, int rpt, int nl, int prec, TcEntry* out) {
+  if (rpt == 1 && tiles == 1) return lookup_t1(nl, prec, out);
+  if (rpt == 1 && tiles == 2) return lookup_t2(nl, prec, out);
+  if (rpt == 1 && tiles == 4) return lookup_t4(nl, prec, out);
+  if (tiles == 1 && rpt == 2) return lookup_p2(nl, prec, out);
+  if (tiles == 1 && rpt == 4) return lookup_p4(nl, prec, out);
+  return false;
 }
-}  // namespace
+}  // namespace tc
+}  // namespace ddd1d
 
 extern "C" {
 
@@ -701,7 +663,6 @@ int ddd1d_destroy(ddd1d_handle* h) {
   cudaFree(h->d_blob);
   cudaFree(h->d_blob_tc);
   cudaFree(h->d_scratch_tc);
-  cudaFree(h->d_trace_tc);
   cudaFree(h->d_fparams);
   cudaFree(h->d_fbasis);
   cudaFree(h->d_fparams64);
@@ -975,59 +936,6 @@ int ddd1d_weno_reconstruct(int device, int real, const void* u, void* left, void
   return DDD1D_OK;
 }
 
-// variant: index into a fixed table of compile-time MMA patterns (scripts/tc_rate.py lists them)
-int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long* cycles_host) {
-  if (reps < 1 || blocks < 1 || !cycles_host) return fail(nullptr, DDD1D_EINVAL, "bad argument");
-  CUDA_TRY(nullptr, cudaSetDevice(device));
-  long long* d = nullptr;
-  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * sizeof(long long)));
-  int rc = DDD1D_EINVAL;
-  switch (variant) {
-    case 0: rc = run_rate<0, 16, 0, 16, 1>(reps, blocks, d); break;
-    case 1: rc = run_rate<0, 32, 0, 32, 1>(reps, blocks, d); break;
-    case 2: rc = run_rate<0, 64, 0, 64, 1>(reps, blocks, d); break;
-    case 3: rc = run_rate<0, 128, 0, 128, 1>(reps, blocks, d); break;
-    case 4: rc = run_rate<0, 32, 0, 64, 1>(reps, blocks, d); break;    // N=32 out of a 64-row plane
-    case 5: rc = run_rate<0, 32, 0, 32, 0>(reps, blocks, d); break;    // single accumulator
-    case 6: rc = run_rate<0, 64, 32, 64, 1>(reps, blocks, d); break;   // production hidden layer
-    case 7: rc = run_rate<0, 32, 16, 32, 1>(reps, blocks, d); break;   // production last layer
-    case 8: rc = run_rate<0, 32, 32, 32, 1>(reps, blocks, d); break;
-    case 9: rc = run_rate<1, 32, 0, 32, 1>(reps, blocks, d); break;    // bf16 K=16
-    case 10: rc = run_rate<1, 64, 0, 64, 1>(reps, blocks, d); break;
-    case 11: rc = run_rate<1, 96, 0, 96, 1>(reps, blocks, d); break;
-    case 12: rc = run_rate<1, 96, 64, 96, 1>(reps, blocks, d); break;  // bf16x3 first two of a step
-    case 13: rc = run_rate<1, 128, 0, 128, 1>(reps, blocks, d); break;
-    case 14: rc = run_rate<1, 64, 32, 64, 0, 128>(reps, blocks, d); break;  // f16 hidden step, separate accumulators
-    case 15: rc = run_rate<1, 64, 32, 64, 0, 32>(reps, blocks, d); break;   // f16 hidden step, production D overlap
-    case 16: rc = run_rate<1, 32, 16, 32, 0, 16>(reps, blocks, d); break;   // f16 last step, production D overlap
-    case 17: rc = run_rate<1, 96, 0, 96, 0>(reps, blocks, d); break;        // one MMA per step, N = 96
-    default: return fail(nullptr, DDD1D_EINVAL, "unknown variant");
-  }
-  if (rc) return rc;
-  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * sizeof(long long), cudaMemcpyDeviceToHost));
-  CUDA_TRY(nullptr, cudaFree(d));
-  return DDD1D_OK;
-}
-
-int ddd1d_debug_tc_overlap(int device, int mode, int reps, int iters, int blocks, long long* cycles_host) {
-  if (reps < 1 || iters < 1 || blocks < 1 || !cycles_host) return fail(nullptr, DDD1D_EINVAL, "bad argument");
-  CUDA_TRY(nullptr, cudaSetDevice(device));
-  long long* d = nullptr;
-  float* sink = nullptr;
-  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * 2 * sizeof(long long)));
-  CUDA_TRY(nullptr, cudaMemset(d, 0, (size_t)blocks * 2 * sizeof(long long)));
-  CUDA_TRY(nullptr, cudaMalloc(&sink, (256 + 1024) * sizeof(float)));
-  CUDA_TRY(nullptr, cudaMemset(sink, 0, (256 + 1024) * sizeof(float)));
-  const int smem = 128 + 2 * 4 * 260 * 16 + tc::kTaps * 4 * 64 * 16 + 8192;
-  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc::tc_overlap_kernel<<<blocks, 256, smem>>>(reps, mode, iters, d, sink);
-  CUDA_TRY(nullptr, cudaGetLastError());
-  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
-  CUDA_TRY(nullptr, cudaFree(d));
-  CUDA_TRY(nullptr, cudaFree(sink));
-  return DDD1D_OK;
-}
-
 long long ddd1d_launch_count(const ddd1d_handle* h) { return h ? h->launches : 0; }
 
 int ddd1d_engine(const ddd1d_handle* handle) {
@@ -1035,17 +943,7 @@ int ddd1d_engine(const ddd1d_handle* handle) {
   if (!h) return fail(nullptr, DDD1D_EINVAL, "null handle");
   int rc = finalize(h);
   if (rc) return rc;
-  return use_tc(h) ? DDD1D_ENGINE_TENSOR : DDD1D_ENGINE_FFMA;
-}
-
-int ddd1d_debug_tc_probe(int device, const float* x, const float* w_cat, float* out, int nout, void* stream) {
-  if (!x || !w_cat || !out || (nout != 16 && nout != 32)) return fail(nullptr, DDD1D_EINVAL, "bad argument");
-  CUDA_TRY(nullptr, cudaSetDevice(device));
-  const int smem = 128 + 2 * tc::kChunks * 132 * 16 + 2 * tc::kTaps * tc::kChunks * nout * 16;
-  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc::tc_probe_kernel<<<1, 160, smem, static_cast<cudaStream_t>(stream)>>>(x, w_cat, out, nout);
-  CUDA_TRY(nullptr, cudaGetLastError());
-  return DDD1D_OK;
+  return use_tc(h) ? h->tc_engine : DDD1D_ENGINE_FFMA;
 }
 
 int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* block, int* shared_bytes) {
@@ -1054,9 +952,9 @@ int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* bl
   int rc = finalize(h);
   if (rc) return rc;
   if (use_tc(h)) {
-    if (grid) *grid = std::min((batch + h->Ptc.tc_teams - 1) / h->Ptc.tc_teams, h->num_sms);
-    if (block) *block = h->tc_threads;
-    if (shared_bytes) *shared_bytes = h->Ptc.smem_bytes;
+    if (grid) *grid = tc_grid(h, batch);
+    if (block) *block = h->tc_entry.threads;
+    if (shared_bytes) *shared_bytes = h->tc_entry.smem_bytes;
     return DDD1D_OK;
   }
   if (use_warp_rows(h, OP_INTEGRATE)) {     // (the shape of ddd1d_integrate launches)

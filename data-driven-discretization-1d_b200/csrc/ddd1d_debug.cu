@@ -1,0 +1,464 @@
+// Laboratory kernels of the tensor engine: descriptor probe, MMA issue-rate and overlap microbenchmarks.
+// TEST-ONLY: built into libddd1d_debug.so (include/ddd1d_debug.h), never into the product library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/ddd1d.h"
+#include "../../include/ddd1d_debug.h"
+#include "ddd1d_tc_common.cuh"
+
+namespace ddd1d {
+namespace tc {
+
+// Issue every MMA of one layer for one 128-position tile.  Must be called by a converged warp with
+// warp-uniform arguments; one elected lane issues.
+//   act_hi/act_lo : shared addresses of the tile's team planes (position 0 of the row)
+//   b             : shared address of the layer's [Whi | Wlo] planes, b_plane_bytes = 2*NB*16
+//   d_col         : TMEM column of the tile's accumulator block; layout
+//                   [even taps: main NB | cross NB][odd taps: main NB | cross NB]
+// F16 = false: TF32 planes, 8 chunk planes of 4 floats, K = 8 per MMA (4 ci-blocks per tap);
+// F16 = true : fp16 planes, 4 chunk planes of 8 halfs, K = 16 per MMA (2 ci-blocks per tap).
+// EO = true : taps accumulate alternately into two D blocks [even main|cross][odd main|cross] (halves the
+//             accumulate chain; the TF32 probe uses it);  EO = false: one block [main | cross].
+template <bool F16, bool EO>
+__device__ __forceinline__ void issue_layer(uint32_t act_hi, uint32_t act_lo, uint32_t plane_bytes, uint32_t b,
+                                            uint32_t b_plane_bytes, int tile, uint32_t d_col, int nb) {
+  constexpr int kPlanes = F16 ? kChunks / 2 : kChunks;
+  const uint32_t desc_hi = (128u >> 4) | (1u << 14);          // SBO = 128 B, version 1 (bits 32..47)
+  const uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
+  const uint32_t ah0 = (((act_hi >> 4) + (uint32_t)tile * 128u) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t al0 = (((act_lo >> 4) + (uint32_t)tile * 128u) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t b0 = ((b >> 4) & 0x3FFFu) | (bplane16 << 16);
+  const uint32_t idesc_wide = F16 ? instr_desc_f16(128, 2 * nb) : instr_desc_tf32(128, 2 * nb);
+  const uint32_t idesc_narrow = F16 ? instr_desc_f16(128, nb) : instr_desc_tf32(128, nb);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+      const uint32_t d_main = d_col + (EO ? (uint32_t)((k & 1) * 2 * nb) : 0u);
+      const uint32_t d_cross = d_main + (uint32_t)nb;
+#pragma unroll
+      for (int kb = 0; kb < kPlanes / 2; ++kb) {
+        const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+        const uint32_t bo = (uint32_t)(k * kPlanes + 2 * kb) * bplane16;
+        const uint32_t first = (k < (EO ? 2 : 1) && kb == 0) ? 0u : 1u;     // first touch of a D block
+        if (F16) {
+          mma_f16_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);    // hi*[Wh|Wl'] -> main | cross
+          mma_f16_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);    // lo'*Wh      -> cross
+        } else {
+          mma_tf32_split(d_main, ah0 + ao, b0 + bo, desc_hi, idesc_wide, first);   // hi*[Whi|Wlo] -> main | cross
+          mma_tf32_split(d_cross, al0 + ao, b0 + bo, desc_hi, idesc_narrow, 1u);   // lo*Whi       -> cross
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Probe: one 128-position tile of a 32 -> NOUT, 5-tap periodic-free conv through the same
+// descriptor / split / TMEM path.  Used by tests to validate layouts in isolation.
+//   x     [132][32] float  (positions -2..129)
+//   w_cat packed B planes [5*8][2*NOUT][4]: rows 0..NOUT-1 = Whi, NOUT..2*NOUT-1 = Wlo
+//   out   [128][NOUT] float
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restrict__ xin,
+                                                          const float* __restrict__ w_cat, float* __restrict__ out,
+                                                          int nout) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t plane_bytes = 132u * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned char* a_hi = smem_raw + 128;
+  unsigned char* a_lo = a_hi + kChunks * plane_bytes;
+  float* b_cat = reinterpret_cast<float*>(a_lo + kChunks * plane_bytes);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(slot, 128);
+  for (int i = tid; i < 132 * kChunks; i += blockDim.x) {
+    const int pos = i / kChunks, c4 = i % kChunks;
+    const float4 v = *reinterpret_cast<const float4*>(xin + (size_t)pos * kF + 4 * c4);
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(a_hi + (size_t)c4 * plane_bytes + (size_t)pos * 16) = h;
+    *reinterpret_cast<float4*>(a_lo + (size_t)c4 * plane_bytes + (size_t)pos * 16) = l;
+  }
+  for (int i = tid; i < kTaps * kChunks * 2 * nout * 4; i += blockDim.x) b_cat[i] = w_cat[i];
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  if (warp == 4) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    issue_layer<false, true>(smem_u32(a_hi), smem_u32(a_lo), plane_bytes, smem_u32(b_cat), 2u * (uint32_t)nout * 16u, 0, base_u,
+                nout);
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+  } else {
+    mbar_wait_guarded(bar, 0);
+    fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (nout == 16) {
+      float v[16];
+      tmem_sum16(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[(size_t)tid * 16 + i] = v[i];
+    } else {
+      float v[32];
+      tmem_sum32(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) out[(size_t)tid * 32 + i] = v[i];
+    }
+    fence_before();
+  }
+  __syncthreads();
+  fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MMA issue-rate microbenchmark (debug): one warp issues reps x 20 (tap, ci-block) steps on planes of
+// arbitrary data; the CTA measures the clocks until tcgen05.commit fires.  Per step up to two MMAs:
+//   first : A = plane set 0, N = n1, D columns at d_off1 (+ 128 * (k & 1) when alt != 0)
+//   second: A = plane set `a2`, N = n2, D columns at d_off2 (same alternation)
+// n == 0 skips that MMA.  kind 0 = tf32 (K = 8, 4-byte elements), 1 = bf16 (kind::f16, K = 16).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t instr_desc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int KIND, int N1, int N2, int BROWS, int ALT, int DOFF2 = 128>
+__global__ void __launch_bounds__(128, 1) tc_rate_kernel(int reps, long long* __restrict__ cycles) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t plane_bytes = 516u * 16u;
+  constexpr uint32_t b_plane_bytes = (uint32_t)BROWS * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned char* a_0 = smem_raw + 128;
+  unsigned char* a_1 = a_0 + kChunks * plane_bytes;
+  unsigned char* b_cat = a_1 + kChunks * plane_bytes;
+  for (uint32_t i = tid; i < (2 * kChunks * plane_bytes + kTaps * kChunks * b_plane_bytes) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(a_0)[i] = 0x3c003c00u + (i & 63u);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  long long t0 = 0;
+  if (warp == 0) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
+    const uint32_t a00 = ((smem_u32(a_0) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t a10 = ((smem_u32(a_1) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t b0 = ((smem_u32(b_cat) >> 4) & 0x3FFFu) | (bplane16 << 16);
+    const uint32_t id1 = KIND ? instr_desc_bf16(128, N1 ? N1 : 16) : instr_desc_tf32(128, N1 ? N1 : 16);
+    const uint32_t id2 = KIND ? instr_desc_bf16(128, N2 ? N2 : 16) : instr_desc_tf32(128, N2 ? N2 : 16);
+    t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+#pragma unroll
+          for (int kb = 0; kb < kChunks / 2; ++kb) {
+            const uint32_t dsel = ALT ? (uint32_t)(k & 1) * 256u : 0u;
+            const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+            const uint32_t bo = (uint32_t)(k * kChunks + 2 * kb) * bplane16;
+            if (N1) {
+              if (KIND) mma_bf16_split(base_u + dsel, a00 + ao, b0 + bo, desc_hi, id1, 1u);
+              else mma_tf32_split(base_u + dsel, a00 + ao, b0 + bo, desc_hi, id1, 1u);
+            }
+            if (N2) {
+              if (KIND) mma_bf16_split(base_u + dsel + (uint32_t)DOFF2, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+              else mma_tf32_split(base_u + dsel + (uint32_t)DOFF2, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+    mbar_wait_guarded(bar, 0);
+    if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Overlap experiment: warp 0 streams fp16 MMAs (M128 N64 K16 + M128 N32 K16 per step, operands in shared
+// memory, the production hidden-layer step) while warps 4..7 run a CUDA-core workload:
+//   work 0 nothing, 1 FFMA chain, 2 STS.128 + LDS.128, 3 packed fp16 conversions, 4 tcgen05.ld, 5 SHFL,
+//        6 LDG (L1-resident), 7 LDS.128 only, 8 STS.128 only, 9 mbarrier arrive + wait, 10 bar.sync,
+//        11 STS + fence.proxy.async, 12 tcgen05 fences, 13 plane store + fence + mbarrier round
+// mode bit 0 = run the MMAs, bits 1.. = work.  cycles[2*b] = MMA stream, cycles[2*b+1] = CUDA stream.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) tc_overlap_kernel(int reps, int mode, int iters,
+                                                            long long* __restrict__ cycles, float* __restrict__ sink) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t plane_bytes = 260u * 16u, b_plane_bytes = 64u * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned char* a_0 = smem_raw + 128;
+  unsigned char* a_1 = a_0 + 4 * plane_bytes;
+  unsigned char* b_cat = a_1 + 4 * plane_bytes;
+  unsigned char* scratch = b_cat + kTaps * 4 * b_plane_bytes;       // 4 warps x 32 lanes x 16 B x 4
+  const uint32_t init_words = (2 * 4 * plane_bytes + kTaps * 4 * b_plane_bytes + 8192) / 4;
+  for (uint32_t i = tid; i < init_words; i += blockDim.x) reinterpret_cast<uint32_t*>(a_0)[i] = 0x3c003c00u + (i & 63u);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    for (int w = 0; w < 4; ++w) mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 32) + w, 32);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  const bool run_mma = mode & 1;
+  const int work = mode >> 1;
+  if (warp == 0 && run_mma) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    constexpr uint32_t plane16 = plane_bytes >> 4, bplane16 = b_plane_bytes >> 4;
+    const uint32_t a00 = ((smem_u32(a_0) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t a10 = ((smem_u32(a_1) >> 4) & 0x3FFFu) | (plane16 << 16);
+    const uint32_t b0 = ((smem_u32(b_cat) >> 4) & 0x3FFFu) | (bplane16 << 16);
+    const uint32_t id1 = instr_desc_f16(128, 64), id2 = instr_desc_f16(128, 32);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+            const uint32_t bo = (uint32_t)(k * 4 + 2 * kb) * bplane16;
+            mma_f16_split(base_u + 256u, a00 + ao, b0 + bo, desc_hi, id1, 1u);
+            mma_f16_split(base_u + 288u, a10 + ao, b0 + bo, desc_hi, id2, 1u);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+    mbar_wait_guarded(bar, 0);
+    if (tid == 0) cycles[2 * blockIdx.x] = clock64() - t0;
+  }
+  if (warp >= 4 && work > 0) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (float)(lane + i);
+    uint4* mine = reinterpret_cast<uint4*>(scratch) + (warp - 4) * 128 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (work == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], 1.0001f, 0.5f);
+      } else if (work == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v = mine[j * 32];
+          v.x += (uint32_t)it;
+          mine[j * 32] = v;
+        }
+      } else if (work == 3) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            uint32_t hi, lo;
+            split_half2(acc[i], acc[i + 1], hi, lo);
+            acc[i] += __uint_as_float(hi & 0x3fffffu);
+            acc[i + 1] += __uint_as_float(lo & 0x3fffffu);
+          }
+      } else if (work == 4) {
+        uint32_t r[16];
+        tmem_ld16_issue(taddr + (uint32_t)((it & 7) * 16), r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __uint_as_float(r[i]) + __uint_as_float(r[i + 8]);
+      } else if (work == 5) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], 1);
+      } else if (work == 6) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += __ldg(sink + 256 + ((it + j * 32 + lane) & 1023));
+      } else if (work == 7) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 v = mine[j * 32];
+          acc[j] += __uint_as_float(v.x & 0x3fffffu);
+        }
+      } else if (work == 8) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine[j * 32] = make_uint4((uint32_t)it, 0u, 0u, 0u);
+      } else if (work == 9) {
+        // mbarrier round: every lane arrives on the warp's own barrier, then waits for the phase
+        uint64_t* wb = reinterpret_cast<uint64_t*>(smem_raw + 32) + (warp - 4);
+        mbar_arrive(wb);
+        mbar_wait_guarded(wb, (uint32_t)(it & 1));
+      } else if (work == 10) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1) : "memory");     // named barrier among warps 4..7
+      } else if (work == 11) {
+        mine[0] = make_uint4((uint32_t)it, 0u, 0u, 0u);
+        fence_async_smem();                                        // generic -> async proxy fence after a store
+      } else if (work == 12) {
+        fence_before();
+        fence_after();
+      } else {
+        // plane store as the row kernel does it: 8 STS.128 into a [chunk][pos] plane + fence + mbarrier arrive
+        uint4* plane = reinterpret_cast<uint4*>(scratch);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) plane[j * 128 + (warp - 4) * 32 + lane] = make_uint4((uint32_t)it, 1u, 2u, 3u);
+        fence_async_smem();
+        uint64_t* wb = reinterpret_cast<uint64_t*>(smem_raw + 32) + (warp - 4);
+        mbar_arrive(wb);
+        mbar_wait_guarded(wb, (uint32_t)(it & 1));
+      }
+    }
+    const long long t1 = clock64();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += acc[i];
+    if (sum == 1.2345f) sink[tid] = sum;
+    if (tid == 128) cycles[2 * blockIdx.x + 1] = t1 - t0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+}  // namespace ddd1d
+
+using namespace ddd1d;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const char* what) {
+  g_error = what;
+  fprintf(stderr, "ddd1d_debug: %s\n", what);
+  return DDD1D_EINVAL;
+}
+
+#define CUDA_TRY(h, expr)                                                        \
+  do {                                                                           \
+    cudaError_t e_ = (expr);                                                     \
+    if (e_ != cudaSuccess) {                                                     \
+      fprintf(stderr, "ddd1d_debug: %s failed: %s\n", #expr, cudaGetErrorString(e_)); \
+      return DDD1D_ECUDA;                                                        \
+    }                                                                            \
+  } while (0)
+
+template <int KIND, int N1, int N2, int BROWS, int ALT, int DOFF2 = 128>
+int run_rate(int reps, int blocks, long long* d) {
+  const int smem = 128 + 2 * tc::kChunks * 516 * 16 + tc::kTaps * tc::kChunks * BROWS * 16;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT, DOFF2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_rate_kernel<KIND, N1, N2, BROWS, ALT, DOFF2><<<blocks, 128, smem>>>(reps, d);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// variant: index into a fixed table of compile-time MMA patterns (scripts/tc_rate.py lists them)
+int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long* cycles_host) {
+  if (reps < 1 || blocks < 1 || !cycles_host) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  long long* d = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * sizeof(long long)));
+  int rc = DDD1D_EINVAL;
+  switch (variant) {
+    case 0: rc = run_rate<0, 16, 0, 16, 1>(reps, blocks, d); break;
+    case 1: rc = run_rate<0, 32, 0, 32, 1>(reps, blocks, d); break;
+    case 2: rc = run_rate<0, 64, 0, 64, 1>(reps, blocks, d); break;
+    case 3: rc = run_rate<0, 128, 0, 128, 1>(reps, blocks, d); break;
+    case 4: rc = run_rate<0, 32, 0, 64, 1>(reps, blocks, d); break;    // N=32 out of a 64-row plane
+    case 5: rc = run_rate<0, 32, 0, 32, 0>(reps, blocks, d); break;    // single accumulator
+    case 6: rc = run_rate<0, 64, 32, 64, 1>(reps, blocks, d); break;   // production hidden layer
+    case 7: rc = run_rate<0, 32, 16, 32, 1>(reps, blocks, d); break;   // production last layer
+    case 8: rc = run_rate<0, 32, 32, 32, 1>(reps, blocks, d); break;
+    case 9: rc = run_rate<1, 32, 0, 32, 1>(reps, blocks, d); break;    // bf16 K=16
+    case 10: rc = run_rate<1, 64, 0, 64, 1>(reps, blocks, d); break;
+    case 11: rc = run_rate<1, 96, 0, 96, 1>(reps, blocks, d); break;
+    case 12: rc = run_rate<1, 96, 64, 96, 1>(reps, blocks, d); break;  // bf16x3 first two of a step
+    case 13: rc = run_rate<1, 128, 0, 128, 1>(reps, blocks, d); break;
+    case 14: rc = run_rate<1, 64, 32, 64, 0, 128>(reps, blocks, d); break;  // f16 hidden step, separate accumulators
+    case 15: rc = run_rate<1, 64, 32, 64, 0, 32>(reps, blocks, d); break;   // f16 hidden step, production D overlap
+    case 16: rc = run_rate<1, 32, 16, 32, 0, 16>(reps, blocks, d); break;   // f16 last step, production D overlap
+    case 17: rc = run_rate<1, 96, 0, 96, 0>(reps, blocks, d); break;        // one MMA per step, N = 96
+    default: return fail("unknown variant");
+  }
+  if (rc) return rc;
+  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_overlap(int device, int mode, int reps, int iters, int blocks, long long* cycles_host) {
+  if (reps < 1 || iters < 1 || blocks < 1 || !cycles_host) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  long long* d = nullptr;
+  float* sink = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * 2 * sizeof(long long)));
+  CUDA_TRY(nullptr, cudaMemset(d, 0, (size_t)blocks * 2 * sizeof(long long)));
+  CUDA_TRY(nullptr, cudaMalloc(&sink, (256 + 1024) * sizeof(float)));
+  CUDA_TRY(nullptr, cudaMemset(sink, 0, (256 + 1024) * sizeof(float)));
+  const int smem = 128 + 2 * 4 * 260 * 16 + tc::kTaps * 4 * 64 * 16 + 8192;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_overlap_kernel<<<blocks, 256, smem>>>(reps, mode, iters, d, sink);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
+  CUDA_TRY(nullptr, cudaFree(sink));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_probe(int device, const float* x, const float* w_cat, float* out, int nout, void* stream) {
+  if (!x || !w_cat || !out || (nout != 16 && nout != 32)) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  const int smem = 128 + 2 * tc::kChunks * 132 * 16 + 2 * tc::kTaps * tc::kChunks * nout * 16;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_probe_kernel<<<1, 160, smem, static_cast<cudaStream_t>(stream)>>>(x, w_cat, out, nout);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+
+}  // extern "C"

@@ -64,26 +64,6 @@ struct Params {
   int off_ustd, off_kd, off_fluxd, off_fsd;   // float64 twins (float64 WENO path only)
   int smem_bytes;
   int use_bulk_copy;
-  // ---- tensor-core engine (ddd1d_tc.cuh); offsets into its own blob / shared layout ----
-  // tc_debug (env DDD1D_TC_DEBUG): TIMING EXPERIMENTS ONLY, results are meaningless when set --
-  // bit 0 no MMAs (CUDA-core side alone), bit 2 issuers sleep when idle, bit 6 MMA stream alone (teams sit out)
-  int tc_teams, tc_nlast, tc_debug;
-  int tc_off_slot, tc_off_tab, tc_off_team0, tc_team_stride;
-  int tc_t_act_hi, tc_t_act_lo;   // byte offsets of the activation planes inside a slot's shared region
-  long long* tc_trace;            // debug: clock64 event trace of CTA 0 (DDD1D_TC_TRACE=<file>), else null
-  float* tc_scratch;              // global scratch [grid][teams * slots][tc_sc_stride] floats (L1 / L2 resident)
-  int tc_sc_stride, tc_sc_umax, tc_sc_flux, tc_sc_fs;   // float offsets inside a slot's scratch
-  int tc_issuers;           // warps that issue the MMAs
-  int tc_slots;             // rows in flight per team (their CUDA-core and tensor phases interleave)
-  float tc_w1abs, tc_b1abs, tc_whabs, tc_bhabs;   // operator-norm bounds behind the fp16 plane scales
-  float tc_inv_sw_hid, tc_inv_sw_last;            // 1 / power-of-two filter scales
-  int tc_w1_off, tc_b1_off, tc_bh_off, tc_bl_off;                          // float offsets into the blob
-  int tc_bhid_off, tc_bhid_stride, tc_bhid_lo, tc_blast_off, tc_blast_lo;
-  // small tables read as constant-bank FFMA operands by every thread (no shared-memory traffic)
-  float tc_w1[5 * 32];      // first layer [tap][channel]
-  float tc_b1[32];          // first-layer bias
-  float tc_bh[32];          // bias of the (single) hidden tensor layer
-  float tc_bl[32];          // folded bias of the last layer
 };
 
 struct Work {
@@ -193,7 +173,7 @@ __device__ __forceinline__ int wrap(int x, int n) {
   return x < 0 ? x + n : x;
 }
 
-__device__ __noinline__ float activate_rare(float x, int act) {
+static __device__ __noinline__ float activate_rare(float x, int act) {
   switch (act) {   // model.py:411-417
     case ACT_RELU6: return fminf(fmaxf(x, 0.f), 6.f);
     case ACT_TANH: return tanhf(x);
@@ -749,7 +729,7 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
 // u_minus / u_plus reconstructed from the float64 row, the remaining derivatives from the float32
 // stencils (a TF float32 graph in the reference, integrate.py:104-105,134), Godunov flux, flux
 // difference and forcing in float64 (NumPy semantics: python-scalar * float32 array stays float32).
-__device__ __noinline__ void row_rhs_weno_f64(const Params& P, int sample, double t, int kslot) {
+static __device__ __noinline__ void row_rhs_weno_f64(const Params& P, int sample, double t, int kslot) {
   const Smem S = carve(P, dyn_smem);
   const int N = P.N;
   double* kout = S.kd + kslot * N;

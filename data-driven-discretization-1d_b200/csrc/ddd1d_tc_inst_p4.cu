@@ -1,0 +1,5 @@
+// tc_row_kernel instantiations: TILES = 1, rows per tile = 4 (see ddd1d_tc_inst.inc)
+#define DDD1D_TC_TILES 1
+#define DDD1D_TC_RPT 4
+#define DDD1D_TC_NAME p4
+#include "ddd1d_tc_inst.inc"

@@ -16,15 +16,38 @@ from . import runtime
 FINITE_DIFF = polynomials.Method.FINITE_DIFFERENCES
 FINITE_VOL = polynomials.Method.FINITE_VOLUMES
 
-_SOLVERS = {}
+import collections
+import os
+
+_SOLVERS = collections.OrderedDict()     # least recently used first
+_MAX_SOLVERS = 32
+_FINGERPRINTS = {}                       # id(weights) -> (weights, fingerprint): hash each weight list once
 
 
 def _cached(key, build):
-  if key not in _SOLVERS:
-    if len(_SOLVERS) > 32:
-      _SOLVERS.clear()
-    _SOLVERS[key] = build()
+  """Solver cache with least-recently-used eviction (one handle at a time: callers never see a
+  solver they hold disappear wholesale)."""
+  if key in _SOLVERS:
+    _SOLVERS.move_to_end(key)
+    return _SOLVERS[key]
+  while len(_SOLVERS) >= _MAX_SOLVERS:
+    _SOLVERS.popitem(last=False)
+  _SOLVERS[key] = build()
   return _SOLVERS[key]
+
+
+def _fingerprint(hparams, weights):
+  """SHA-1 of (hparams, weights), computed once per weights object: func(y, t) evaluations call
+  predict_* thousands of times with the same list."""
+  hit = _FINGERPRINTS.get(id(weights))
+  values = tuple(sorted((k, str(v)) for k, v in hparams.values().items()))
+  if hit is not None and hit[0] is weights and hit[1] == values:
+    return hit[2]
+  fp = runtime.weights_fingerprint(hparams, weights)
+  if len(_FINGERPRINTS) > 4 * _MAX_SOLVERS:
+    _FINGERPRINTS.clear()
+  _FINGERPRINTS[id(weights)] = (weights, values, fp)
+  return fp
 
 
 def assert_consistent_solution(equation, solution):
@@ -38,7 +61,8 @@ def _learned(hparams, weights):
   if weights is None:
     raise ValueError('weights must be given explicitly: [(kernel[k,cin,cout], bias[cout]), ...]')
   _, equation = equations_lib.from_hparams(hparams)
-  key = ('learned', runtime.weights_fingerprint(hparams, weights))
+  # (the engine override of the environment is part of the key: a cached solver keeps the engine it was built for)
+  key = ('learned', _fingerprint(hparams, weights), os.environ.get('DDD1D_ENGINE', ''))
   return equation, _cached(key, lambda: runtime.learned_solver(equation, hparams, weights, forcing=False))
 
 
@@ -98,7 +122,7 @@ def apply_fixed_stencils(inputs, stencils):
   if not 1 <= len(stencils) <= 2:
     raise ValueError('1 or 2 stencils at a time')
   carrier = equations_lib.BurgersEquation(n, period=float(n))     # D = 2 channels, dx = 1
-  key = ('stencils', n, tuple(np.concatenate([np.asarray(s, dtype=np.float64) for s in stencils])))
+  key = ('stencils', n, tuple(tuple(float(v) for v in np.asarray(s, dtype=np.float64).ravel()) for s in stencils))
   def build():
     solver = runtime.stencil_solver(carrier, forcing=False)
     rows = np.zeros((2, _lib.WINDOW))

@@ -328,11 +328,11 @@ class RowSolver(object):
     return snaps, bad
 
   def engine(self):
-    """'ffma' or 'tensor': the kernel the next launch will use."""
+    """'ffma', 'tensor', 'tensor_f16x2' or 'tensor_f16': the kernel the next launch will use."""
     code = self._lib.ddd1d_engine(self._handle)
     if code < 0:
       self._check(code)
-    return {1: 'ffma', 2: 'tensor'}[code]
+    return _lib.ENGINE_NAMES[code]
 
   def launch_count(self):
     return int(self._lib.ddd1d_launch_count(self._handle))

@@ -81,11 +81,16 @@ enum {
   DDD1D_RK4 = 3
 };
 
-/* conv-stack engine (learned mode).  AUTO picks the tcgen05 kernel when the net is
- * the shape it is built for (kernel_size 5, filter_size 32, relu, 2 or 3 layers, N in
- * {128, 256, 512}) and the FP32-FFMA kernel otherwise; both satisfy the same
- * float32 tolerances (the tensor path splits every operand into fp16 hi + lo, 22 bits, FP32 accumulate). */
-enum { DDD1D_ENGINE_AUTO = 0, DDD1D_ENGINE_FFMA = 1, DDD1D_ENGINE_TENSOR = 2 };
+/* conv-stack engine (learned mode).  AUTO picks the tcgen05 kernel in its FP32-faithful form (TENSOR) when
+ * the net is the shape it is built for (kernel_size 5, filter_size 32, relu, 2 or 3 layers, N in
+ * {32, 64, 128, 256, 512}) and the FP32-FFMA kernel otherwise.  FFMA and TENSOR satisfy the same float32
+ * tolerances: TENSOR splits every operand into fp16 hi + lo (22 bits) and accumulates in FP32.  The two
+ * cheaper tensor forms are opt-in only, with their own (looser) accuracy, measured over the configured
+ * 10 000-step horizons in profiles/r02/tc_trajectory_error.json:
+ *   TENSOR_F16X2  activations rounded to fp16 (11 bits), filters at 22 bits: one MMA per K step, no lo planes;
+ *   TENSOR_F16    plain fp16 operands, FP32 accumulate. */
+enum { DDD1D_ENGINE_AUTO = 0, DDD1D_ENGINE_FFMA = 1, DDD1D_ENGINE_TENSOR = 2, DDD1D_ENGINE_TENSOR_F16X2 = 3,
+       DDD1D_ENGINE_TENSOR_F16 = 4 };
 
 /* arithmetic of the WENO reconstruction: float32 (TF path, model.py:81-87) or
  * float64 (NumPy path of WENODifferentiator, integrate.py:137-138) */

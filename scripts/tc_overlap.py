@@ -4,7 +4,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ddd1d_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_debug()
 WORK = {1: ('FFMA chain', 400), 2: ('STS.128 + LDS.128', 2000), 3: ('packed fp16 splits', 800), 4: ('tcgen05.ld x16', 4000),
         5: ('SHFL', 2000), 6: ('LDG (L1 hits)', 2000), 7: ('LDS.128 only', 2000), 8: ('STS.128 only', 4000),
         9: ('mbarrier arrive+wait', 2000), 10: ('bar.sync 128', 4000),

@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ddd1d_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_debug()
 MASK = np.uint32(0xffffe000)
 
 def rn_tf32(a):

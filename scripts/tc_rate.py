@@ -4,7 +4,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ddd1d_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_debug()
 VARIANTS = ['tf32 N=16', 'tf32 N=32', 'tf32 N=64', 'tf32 N=128', 'tf32 N=32 of a 64-row B plane', 'tf32 N=32 single accumulator',
             'tf32 64+32 (hidden layer step)', 'tf32 32+16 (last layer step)', 'tf32 32+32',
             'bf16 N=32 (K=16)', 'bf16 N=64', 'bf16 N=96', 'bf16 96+64', 'bf16 N=128',

@@ -3,7 +3,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ddd1d_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_debug()
 for blocks in (1, 148):
   for reps in (100, 1000, 10000, 60000):
     out = np.zeros(blocks, np.int64)

@@ -32,8 +32,12 @@ def cpu(t):
 @pytest.mark.parametrize('kind', KINDS)
 @pytest.mark.parametrize('variant', VARIANTS)
 @pytest.mark.parametrize('n', (32, 64))
-def test_learned_against_reference_fixture(golden, kind, variant, n):
+@pytest.mark.parametrize('engine', ('ffma', 'tensor'))
+def test_learned_against_reference_fixture(golden, monkeypatch, kind, variant, n, engine):
+  """Both engines at the reference's own grid sizes; the tensor engine packs 4 (N=32) or 2 (N=64)
+  rows into one 128-position MMA tile."""
   from ddd1d_b200 import model, integrate
+  monkeypatch.setenv('DDD1D_ENGINE', engine)
   g = golden('learned')
   key = 'default/%s/%s/%d' % (kind, variant, n)
   hp = G.product_hparams(kind, variant, n)
@@ -45,6 +49,7 @@ def test_learned_against_reference_fixture(golden, kind, variant, n):
   # the Differentiator surface SciPy calls (adds forcing for Burgers)
   eq = G.product_equation(kind, variant, n, seed=7)
   d = integrate.SavedModelDifferentiator(w, eq, hp)
+  assert d.solver.engine() == engine
   got = d(float(g[key + '/t']), u[0].astype(np.float64))
   assert got.dtype == np.float64
   assert rel_err(got, g[key + '/differentiator']) < RHS_TOL

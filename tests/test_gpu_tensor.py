@@ -46,7 +46,7 @@ def test_descriptor_probe(nout):
   main/cross x even/odd accumulator layout and the TMEM read-back in isolation."""
   import torch
   from ddd1d_b200 import _lib
-  lib = _lib.load()
+  lib = _lib.load_debug()
   rs = np.random.RandomState(nout)
   x = rs.randn(132, 32).astype(np.float32)
   w = (rs.randn(5, 32, nout) / 8).astype(np.float32)
@@ -152,9 +152,9 @@ def test_tensor_engine_other_nets_and_schemes():
 
 def test_tensor_engine_rejects_unsupported_shapes():
   from ddd1d_b200 import runtime
-  eq = G.product_equation('burgers', 'plain', 64)
-  hp = G.product_hparams('burgers', 'plain', 64)
-  w = O.glorot_weights(G.oracle_equation('burgers', 'plain', 64), O.NetSpec(), seed=0)
+  eq = G.product_equation('burgers', 'plain', 200)       # the reference's own test size: not a tile multiple
+  hp = G.product_hparams('burgers', 'plain', 200)
+  w = O.glorot_weights(G.oracle_equation('burgers', 'plain', 200), O.NetSpec(), seed=0)
   with pytest.raises(NotImplementedError):
     runtime.learned_solver(eq, hp, w, engine='tensor').engine()
   assert runtime.learned_solver(eq, hp, w).engine() == 'ffma'
@@ -163,3 +163,57 @@ def test_tensor_engine_rejects_unsupported_shapes():
   hp = G.product_hparams('burgers', 'plain', 128, nonlinearity='tanh')
   w = O.glorot_weights(G.oracle_equation('burgers', 'plain', 128), O.NetSpec(nonlinearity='tanh'), seed=0)
   assert runtime.learned_solver(eq, hp, w).engine() == 'ffma'
+
+
+@pytest.mark.parametrize('n', (32, 64))
+@pytest.mark.parametrize('kind', KINDS)
+def test_packed_rows_trajectories(n, kind):
+  """The reference's own grids (notebooks/time-integration.ipynb: N = 32 / 64): 4 or 2 rows share one
+  128-position MMA tile.  Batches that do not fill a tile, a slot or a wave; every row against the oracle;
+  conservative form too (its flux difference wraps inside the tile)."""
+  import torch
+  from ddd1d_b200 import runtime
+  dt = {'burgers': 1e-3, 'kdv': 2.5e-5, 'ks': 1e-5}[kind]
+  for variant, batch in (('plain', 1), ('plain', 7), ('conservative', 5), ('plain', 2500)):
+    eqs = [G.product_equation(kind, variant, n, seed=s) for s in range(batch)]
+    oeq0 = G.oracle_equation(kind, variant, n)
+    w = O.glorot_weights(oeq0, O.NetSpec(), seed=2, last_layer_scale=0.05, bias_scale=0.1)
+    solver = runtime.learned_solver(eqs, G.product_hparams(kind, variant, n), w, engine='tensor')
+    assert solver.engine() == 'tensor'
+    u0 = G.smooth_rows(batch, n, seed=batch + n)
+    steps = 6
+    got, bad = solver.integrate(u0, 0.05, dt, steps, 3, return_first_bad=True)
+    assert tuple(got.shape) == (2, batch, n)
+    assert (cpu(bad) == -1).all()
+    pick = sorted({0, 1, batch // 2, batch - 2, batch - 1} & set(range(batch)))
+    oeqs = [G.oracle_equation(kind, variant, n, seed=i) for i in pick]
+    rhs = O.batched_rhs(oeqs, O.NetSpec(), w, mode='learned')
+    want = O.fixed_step_integrate(rhs, u0[pick], 0.05, dt, steps, 3)
+    assert rel_err(cpu(got[:, pick]), want) < TRAJ_TOL, (variant, batch)
+    assert torch.equal(solver.integrate(u0, 0.05, dt, steps, 3), got)
+    # per-call hooks on packed rows
+    net = O.NetSpec()
+    c32 = O.predict_coefficients(u0[pick], oeq0, net, w)
+    assert rel_err(cpu(solver.coefficients(u0))[pick], c32) < RHS_TOL
+    solver.close()
+
+
+@pytest.mark.parametrize('engine,tol', (('tensor_f16x2', 2e-3), ('tensor_f16', 4e-3)))
+def test_reduced_precision_engines(engine, tol):
+  """The opt-in cheaper operand formats: same kernel, fewer products.  Their per-call accuracy is that of
+  fp16 activations (2^-12 relative per element), stated here; the trajectory-level numbers are in
+  profiles/r02/tc_trajectory_error.json."""
+  from ddd1d_b200 import runtime
+  for n in (64, 128, 256):
+    eq = G.product_equation('burgers', 'plain', n, seed=3)
+    oeq = G.oracle_equation('burgers', 'plain', n, seed=3)
+    w = O.glorot_weights(oeq, O.NetSpec(), seed=0, last_layer_scale=0.1, bias_scale=0.1)
+    solver = runtime.learned_solver(eq, G.product_hparams('burgers', 'plain', n), w, engine=engine)
+    assert solver.engine() == engine
+    u = G.smooth_rows(5, n, seed=7)
+    c64 = O.predict_coefficients(u, oeq, O.NetSpec(), w, dtype=np.float64)
+    err = rel_err(cpu(solver.coefficients(u)), c64)
+    assert err < tol, (n, err)
+    faithful = runtime.learned_solver(eq, G.product_hparams('burgers', 'plain', n), w, engine='tensor')
+    assert rel_err(cpu(faithful.coefficients(u)), c64) < err      # and the faithful form is closer
+    solver.close(), faithful.close()
