@@ -20,7 +20,7 @@ SCHEMES = {'rk3': 0, 'RK23': 0, 'bogacki_shampine': 0, 'midpoint': 1, 'euler': 2
 REAL_F32, REAL_F64 = 0, 1
 ENGINES = {'auto': 0, 'ffma': 1, 'tensor': 2, 'tensor_f16x2': 3, 'tensor_f16': 4}
 ENGINE_NAMES = {v: k for k, v in ENGINES.items() if v}
-WINDOW = 7
+WINDOW = 11         # DDD1D_WINDOW: offsets -5..+5
 
 
 class Config(ctypes.Structure):
@@ -103,8 +103,8 @@ def load():
       fn = getattr(lib, name)
       fn.restype = restype
       fn.argtypes = argtypes
-    if lib.ddd1d_version() != 1:
-      raise Ddd1dError('libddd1d version %d, binding expects 1' % lib.ddd1d_version())
+    if lib.ddd1d_version() != 2:
+      raise Ddd1dError('libddd1d version %d, binding expects 2' % lib.ddd1d_version())
     _lib = lib
   return _lib
 
@@ -144,14 +144,15 @@ def host_ptr(array):
 
 
 def to_window(stencil):
-  """Place an s-point stencil in the 7-slot window (offsets -3..+3) using the
+  """Place an s-point stencil in the 11-slot window (offsets -5..+5) using the
   reference's centred alignment: ceil((s-1)/2) points left of the output point
   (layers.py:76-79 via nn_conv1d_periodic(center=True))."""
   stencil = np.asarray(stencil, dtype=np.float64)
   s = stencil.shape[-1]
   left = -(-(s - 1) // 2)
-  if left > 3 or (s - 1 - left) > 3:
-    raise NotImplementedError('stencil of %d points does not fit the 7-point window' % s)
+  half = WINDOW // 2
+  if left > half or (s - 1 - left) > half:
+    raise NotImplementedError('stencil of %d points does not fit the %d-point window' % (s, WINDOW))
   out = np.zeros(stencil.shape[:-1] + (WINDOW,), dtype=np.float64)
-  out[..., 3 - left:3 - left + s] = stencil
+  out[..., half - left:half - left + s] = stencil
   return out

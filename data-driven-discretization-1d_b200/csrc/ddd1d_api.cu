@@ -18,6 +18,7 @@
 #include "ddd1d_tc.cuh"
 #include "ddd1d_tc_host.h"
 #include "ddd1d_warp.cuh"
+#include "ddd1d_weno.cuh"
 
 using namespace ddd1d;
 
@@ -53,7 +54,7 @@ struct ddd1d_handle {
   double* d_fparams64 = nullptr;
   double* d_fbasis64 = nullptr;
   int forcing_batch = 0, forcing_P = 0, forcing_M = 0;
-  int threads = 0, blocks_per_sm = 0, num_sms = 0;
+  int threads = 0, blocks_per_sm = 0, num_sms = 0, weno_block_occ = 0;
   long long launches = 0;
   // tensor-core engine
   tc::TcParams Ptc;
@@ -101,6 +102,12 @@ int expected_derivatives(int equation, int variant) {
 
 int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
+// Host tables arrive in the ABI's 11-slot window (offsets -5..+5); a handle is "wide" when any of them reaches
+// beyond the central 7 slots (a 9- or 10-point coefficient grid), else every kernel works on those 7.
+bool tables_are_wide(const ddd1d_handle* h);
+constexpr int kWinHost = kWinWide;
+constexpr int kCentre = (kWinWide - kWin) / 2;      // first host slot of the 7-slot window
+
 double plan_cost(int cout, int N, int nwarps, int cg, int pbt) {
   int ncg = (cout + cg - 1) / cg;
   int npb = (N + 127) / 128;
@@ -113,6 +120,18 @@ double plan_cost(int cout, int N, int nwarps, int cg, int pbt) {
 }
 
 
+
+bool tables_are_wide(const ddd1d_handle* h) {
+  auto outer = [](const std::vector<double>& t) {
+    for (size_t r = 0; r + kWinHost <= t.size(); r += kWinHost)
+      for (int j = 0; j < kCentre; ++j)
+        if (t[r + j] != 0.0 || t[r + kWinHost - 1 - j] != 0.0) return true;
+    return false;
+  };
+  const ddd1d_config& c = h->cfg;
+  if (c.mode == DDD1D_MODE_LEARNED && c.projection <= DDD1D_PROJ_RAW_UNBIASED && c.stencil_size > kWin) return true;
+  return (h->have_stencils && outer(h->stencils)) || (h->have_projection && outer(h->nullspace));
+}
 
 int engine_request(const ddd1d_handle* h) {
   int e = h->cfg.engine;
@@ -154,6 +173,7 @@ int finalize_tc(ddd1d_handle* h) {
   else if (c.activation != DDD1D_ACT_RELU) h->tc_why = "needs the relu nonlinearity";
   else if (c.projection > DDD1D_PROJ_RAW_UNBIASED) h->tc_why = "only model_target='coefficients'";
   else if (tiles == 0) h->tc_why = "needs num_points in {32, 64, 128, 256, 512}";
+  else if (tables_are_wide(h)) h->tc_why = "coefficient grids beyond 7 points run on the FFMA engine";
   else if (h->forcing_batch > 0 && h->forcing_P > 0 && h->forcing_M > kMaxModes) h->tc_why = "too many forcing modes";
   if (!h->tc_why.empty() || want == DDD1D_ENGINE_FFMA) {
     if (wants_tensor(want))
@@ -179,9 +199,9 @@ int finalize_tc(ddd1d_handle* h) {
     int ch = 0;
     for (int d = 0; d < D; ++d)
       for (int i = 0; i < h->input_sizes[d]; ++i, ++ch)
-        for (int j = 0; j < kWin; ++j) pm[(size_t)ch * Q + d * kWin + j] = h->nullspace[(size_t)ch * kWin + j];
+        for (int j = 0; j < kWin; ++j) pm[(size_t)ch * Q + d * kWin + j] = h->nullspace[(size_t)ch * kWinHost + kCentre + j];
     for (int d = 0; d < D; ++d)
-      for (int j = 0; j < kWin; ++j) pbias[d * kWin + j] = h->stencils[d * kWin + j];
+      for (int j = 0; j < kWin; ++j) pbias[d * kWin + j] = h->stencils[d * kWinHost + kCentre + j];
   } else {
     const int S = c.stencil_size, ws = 3 - S / 2;
     for (int d = 0; d < D; ++d)
@@ -326,6 +346,12 @@ int finalize(ddd1d_handle* h) {
   if (!h->have_stencils && !(c.mode == DDD1D_MODE_LEARNED && c.projection != DDD1D_PROJ_NULLSPACE))
     return fail(h, DDD1D_ESTATE, "ddd1d_set_stencils has not been called");
 
+  // window of this handle's kernels: the central 7 slots unless a table reaches offsets +-4
+  const bool wide = tables_are_wide(h);
+  if (wide && c.mode != DDD1D_MODE_LEARNED)
+    return fail(h, DDD1D_EUNSUPPORTED, "fixed stencils wider than 7 points are not built (offsets beyond +-3)");
+  const int win = wide ? kWinWide : kWin, wpitch = wide ? kWinWidePad : kWinPad, first = wide ? 0 : kCentre;
+  P.win = win;
   std::vector<float> blob;
   P.nlayers = 0;
   P.fast_conv = 0;
@@ -382,7 +408,7 @@ int finalize(ddd1d_handle* h) {
     P.C = c.net_outputs;
     P.projection = c.projection;
     P.S = c.stencil_size;
-    P.wshift = 3 - (c.stencil_size / 2);   // 3 - ceil((S-1)/2)
+    P.wshift = win / 2 - (c.stencil_size / 2);   // win/2 - ceil((S-1)/2)
     if (c.projection == DDD1D_PROJ_NULLSPACE) {
       if (!h->have_projection) return fail(h, DDD1D_ESTATE, "ddd1d_set_projection has not been called");
       int total = 0;
@@ -395,10 +421,10 @@ int finalize(ddd1d_handle* h) {
       if (total != c.net_outputs)
         return fail(h, DDD1D_EINVAL, "sum(input_sizes)=%d but net_outputs=%d", total, c.net_outputs);
       P.ns_off = (int)blob.size();
-      blob.resize(blob.size() + (size_t)c.net_outputs * kWinPad, 0.f);
+      blob.resize(blob.size() + (size_t)c.net_outputs * wpitch, 0.f);
       for (int ch = 0; ch < c.net_outputs; ++ch)
-        for (int j = 0; j < kWin; ++j)
-          blob[P.ns_off + ch * kWinPad + j] = (float)h->nullspace[(size_t)ch * kWin + j];
+        for (int j = 0; j < win; ++j)
+          blob[P.ns_off + ch * wpitch + j] = (float)h->nullspace[(size_t)ch * kWinHost + first + j];
     } else {
       const int want_out = c.projection == DDD1D_PROJ_DERIVATIVES ? D
                            : c.projection >= DDD1D_PROJ_TIME_DERIVATIVE ? 1 : D * c.stencil_size;
@@ -415,10 +441,10 @@ int finalize(ddd1d_handle* h) {
   }
   // stencil / bias window table [kMaxD][8]
   P.st_off = (int)blob.size();
-  blob.resize(blob.size() + kMaxD * kWinPad, 0.f);
+  blob.resize(blob.size() + kMaxD * wpitch, 0.f);
   if (h->have_stencils)
     for (int d = 0; d < D; ++d)
-      for (int j = 0; j < kWin; ++j) blob[P.st_off + d * kWinPad + j] = (float)h->stencils[d * kWin + j];
+      for (int j = 0; j < win; ++j) blob[P.st_off + d * wpitch + j] = (float)h->stencils[d * kWinHost + first + j];
   blob.resize(align_up((int)blob.size(), 4), 0.f);
 
   P.eq = c.equation * 3 + c.variant;
@@ -436,7 +462,7 @@ int finalize(ddd1d_handle* h) {
   int off = 0;
   P.off_bar = off; off += 16;
   P.off_blob = off; off += P.blob_floats * 4;
-  P.off_ust = off; off += align_up((N + 2 * kHalo) * 4, 16);
+  P.off_ust = off; off += align_up((N + 2 * kRowHalo) * 4, 16);
   P.off_ydbl = off; off += align_up(N * 8, 16);
   P.off_ynew = off; off += align_up(N * 8, 16);
   P.off_red = off; off += 34 * 8;
@@ -446,7 +472,7 @@ int finalize(ddd1d_handle* h) {
   P.off_ustd = P.off_kd = P.off_fluxd = P.off_fsd = off;
   if (c.mode == DDD1D_MODE_WENO && c.weno_real == DDD1D_REAL_F64) {
     off = align_up(off, 16);
-    P.off_ustd = off; off += align_up((N + 2 * kHalo) * 8, 16);
+    P.off_ustd = off; off += align_up((N + 2 * kRowHalo) * 8, 16);
     P.off_kd = off; off += kMaxStages * N * 8;
     P.off_fluxd = off; off += align_up((N + 1) * 8, 16);
     P.off_fsd = off; off += (2 * kMaxModes + 3 * kMaxForcing) * 8;
@@ -513,6 +539,27 @@ bool use_warp_rows(const ddd1d_handle* h, int op) {
   return getenv("DDD1D_NO_WARP_ROWS") == nullptr;
 }
 
+// The register-resident CTA-per-row WENO5 integrator (ddd1d_weno.cuh) takes the fused fixed-step integration of
+// float32 WENO rows of 4 points per thread: N a multiple of 128 up to 2048 (BASELINE config 5).
+bool use_weno_block(const ddd1d_handle* h, int op) {
+  const ddd1d_config& c = h->cfg;
+  if (op != OP_INTEGRATE || c.mode != DDD1D_MODE_WENO || c.weno_real != DDD1D_REAL_F32) return false;
+  const int n = c.num_points;
+  if (n % 128 != 0 || n <= 256 || n > 2048) return false;
+  if (h->P.P > 32) return false;            // one forcing term per lane of warp 0
+  return getenv("DDD1D_NO_WENO_BLOCK") == nullptr;
+}
+
+int weno_block_grid(ddd1d_handle* h, int batch) {
+  if (h->weno_block_occ == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weno_block_kernel, h->cfg.num_points / kWenoPpt, 0) != cudaSuccess || occ < 1)
+      occ = 1;
+    h->weno_block_occ = occ;
+  }
+  return std::max(1, std::min(batch, h->num_sms * h->weno_block_occ));
+}
+
 int launch(ddd1d_handle* h, Work& W, void* stream) {
   int rc = finalize(h);
   if (rc) return rc;
@@ -552,6 +599,12 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
       default: DDD1D_WARP_LAUNCH(8); break;
     }
 #undef DDD1D_WARP_LAUNCH
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return DDD1D_OK;
+  }
+  if (use_weno_block(h, W.op) && W.u) {
+    weno_block_kernel<<<weno_block_grid(h, W.batch), c.num_points / kWenoPpt, 0, st>>>(P, W, make_tableau(W.scheme));
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;
@@ -640,9 +693,9 @@ int ddd1d_create(const ddd1d_config* config, ddd1d_handle** out) {
       return fail(nullptr, DDD1D_EINVAL, "unknown activation %d", c.activation);
     if (c.projection < 0 || c.projection > DDD1D_PROJ_FLUX)
       return fail(nullptr, DDD1D_EINVAL, "unknown projection %d", c.projection);
-    if (c.projection <= DDD1D_PROJ_RAW_UNBIASED && (c.stencil_size < 1 || c.stencil_size > kWin))
+    if (c.projection <= DDD1D_PROJ_RAW_UNBIASED && (c.stencil_size < 1 || c.stencil_size > kWinHost))
       return fail(nullptr, DDD1D_EUNSUPPORTED,
-                  "coefficient grid of %d points exceeds the %d-point window", c.stencil_size, kWin);
+                  "coefficient grid of %d points exceeds the %d-point window", c.stencil_size, kWinHost);
     if (!(c.standard_deviation > 0)) return fail(nullptr, DDD1D_EINVAL, "standard_deviation must be positive");
   }
   int ndev = 0;
@@ -677,7 +730,7 @@ int ddd1d_destroy(ddd1d_handle* h) {
 
 int ddd1d_set_stencils(ddd1d_handle* h, const double* w) {
   if (!h || !w) return fail(h, DDD1D_EINVAL, "null argument");
-  h->stencils.assign(w, w + (size_t)h->cfg.num_derivatives * kWin);
+  h->stencils.assign(w, w + (size_t)h->cfg.num_derivatives * kWinHost);
   h->have_stencils = true;
   h->dirty = true;
   return DDD1D_OK;
@@ -709,7 +762,7 @@ int ddd1d_set_projection(ddd1d_handle* h, const double* ns, const int* input_siz
   }
   if (total != h->cfg.net_outputs)
     return fail(h, DDD1D_EINVAL, "sum(input_sizes)=%d but net_outputs=%d", total, h->cfg.net_outputs);
-  h->nullspace.assign(ns, ns + (size_t)total * kWin);
+  h->nullspace.assign(ns, ns + (size_t)total * kWinHost);
   h->input_sizes.assign(input_sizes, input_sizes + h->cfg.num_derivatives);
   h->have_projection = true;
   h->dirty = true;
@@ -955,6 +1008,12 @@ int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* bl
     if (grid) *grid = tc_grid(h, batch);
     if (block) *block = h->tc_entry.threads;
     if (shared_bytes) *shared_bytes = h->tc_entry.smem_bytes;
+    return DDD1D_OK;
+  }
+  if (use_weno_block(h, OP_INTEGRATE)) {
+    if (grid) *grid = weno_block_grid(h, batch);
+    if (block) *block = h->cfg.num_points / kWenoPpt;
+    if (shared_bytes) *shared_bytes = (int)sizeof(WenoShared);
     return DDD1D_OK;
   }
   if (use_warp_rows(h, OP_INTEGRATE)) {     // (the shape of ddd1d_integrate launches)

@@ -15,9 +15,12 @@
 namespace ddd1d {
 
 constexpr int kMaxD = 4;        // derivative channels (DDD1D_MAX_DERIVATIVES)
-constexpr int kWin = 7;         // stencil window, offsets -3..+3
-constexpr int kWinPad = 8;      // row pitch of window tables
-constexpr int kHalo = 3;        // halo of the raw stage row
+constexpr int kWin = 7;         // stencil window of the kernels' common case, offsets -3..+3
+constexpr int kWinPad = 8;      // row pitch of the 7-slot window tables
+constexpr int kWinWide = 11;    // the window of the C ABI (DDD1D_WINDOW), offsets -5..+5: 9- and 10-point coefficient grids
+constexpr int kWinWidePad = 12; // row pitch of 11-slot tables
+constexpr int kHalo = 3;        // halo of a 7-slot window
+constexpr int kRowHalo = 5;     // halo of the stage row in row_kernel's shared memory (covers the 11-slot window)
 constexpr int kMaxLayers = 6;
 constexpr int kMaxStages = 4;
 constexpr int kMaxModes = 8;
@@ -43,6 +46,7 @@ struct LayerPlan {
 
 struct Params {
   int eq, mode, N, D, S, wshift, weno_real;
+  int win;                  // 7, or 11 when a coefficient grid reaches beyond offsets +-3 (learned mode, FFMA engine only)
   float sigma, eta, inv_dx;
   double inv_dx_d;          // 1 / dx in float64 (float64 WENO path)
   // conv net
@@ -376,7 +380,7 @@ __device__ __forceinline__ void fill_halo(float* buf, int channels, int N, int p
 struct Smem {
   uint64_t* bar;
   float* blob;
-  float* ust;     // raw stage row, index x + kHalo, halo filled
+  float* ust;     // raw stage row, index x + kRowHalo, halo filled
   double* ydbl;   // float64 state
   double* ynew;   // float64 trial state (adaptive stepping)
   double* red;    // reduction scratch [34]
@@ -427,14 +431,14 @@ __device__ __forceinline__ void write_stage_row(const Params& P, const Smem& S, 
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
     const double vd = value(p);
     const float v = (float)vd;         // the float32 placeholder feed (integrate.py:57-60,71)
-    S.ust[p + kHalo] = v;
-    // wrapped copies (also correct when N < kHalo: every halo slot is assigned by some p)
-    for (int q = p - N; q >= -kHalo; q -= N) S.ust[q + kHalo] = v;
-    for (int q = p + N; q < N + kHalo; q += N) S.ust[q + kHalo] = v;
+    S.ust[p + kRowHalo] = v;
+    // wrapped copies (also correct when N < kRowHalo: every halo slot is assigned by some p)
+    for (int q = p - N; q >= -kRowHalo; q -= N) S.ust[q + kRowHalo] = v;
+    for (int q = p + N; q < N + kRowHalo; q += N) S.ust[q + kRowHalo] = v;
     if (f64) {                         // the float64 row the NumPy WENO code sees (integrate.py:137-138)
-      S.ustd[p + kHalo] = vd;
-      for (int q = p - N; q >= -kHalo; q -= N) S.ustd[q + kHalo] = vd;
-      for (int q = p + N; q < N + kHalo; q += N) S.ustd[q + kHalo] = vd;
+      S.ustd[p + kRowHalo] = vd;
+      for (int q = p - N; q >= -kRowHalo; q -= N) S.ustd[q + kRowHalo] = vd;
+      for (int q = p + N; q < N + kRowHalo; q += N) S.ustd[q + kRowHalo] = vd;
     }
     if (learned) {
       const float vn = __fdiv_rn(v, P.sigma);
@@ -526,10 +530,12 @@ __device__ __forceinline__ float forcing_at(const Params& P, const Smem& S, int 
 
 // Spatial derivatives at point p.  dv[d] for d < D; optionally exports the
 // coefficient rows (OP_COEF).
-template <int MODE>
+// WIN = 7 (offsets -3..+3, the common case) or 11 (hparams.coefficient_grid_min_size = 9: 9 centred or 10 staggered points).
+template <int MODE, int WIN = kWin>
 __device__ __forceinline__ void point_derivatives(const Params& P, const Smem& S, const float* net, int p,
                                                   float (&dv)[kMaxD], float* gcoef) {
-  const float* up = S.ust + p;   // up[j] = u[p + j - 3]
+  constexpr int kWin = WIN, kWinPad = WIN == 7 ? ddd1d::kWinPad : kWinWidePad;      // (shadow the 7-slot constants)
+  const float* up = S.ust + p + (kRowHalo - WIN / 2);   // up[j] = u[p + j - WIN / 2]
   float u7[kWin];
 #pragma unroll
   for (int j = 0; j < kWin; ++j) u7[j] = up[j];
@@ -596,7 +602,7 @@ __device__ __forceinline__ void point_derivatives(const Params& P, const Smem& S
   if (MODE == MODE_WENO) {
     // u_minus / u_plus replaced by WENO5 (integrate.py:134-138)
     float um, upv;
-    weno_pair<float>(up + kHalo, um, upv);
+    weno_pair<float>(S.ust + p + kRowHalo, um, upv);
     dv[0] = um;
     dv[1] = upv;
   }
@@ -681,7 +687,8 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
   for (int p = threadIdx.x; p < N; p += blockDim.x) {
     float dv[kMaxD];
     float* gc = (op == OP_COEF) ? gout_row + (size_t)p * P.D * P.S : nullptr;
-    point_derivatives<MODE>(P, S, net, p, dv, gc);
+    if (MODE == MODE_LEARNED && P.win == kWinWide) point_derivatives<MODE, kWinWide>(P, S, net, p, dv, gc);
+    else point_derivatives<MODE>(P, S, net, p, dv, gc);
     if (op == OP_DERIV) {
 #pragma unroll
       for (int d = 0; d < kMaxD; ++d)
@@ -699,7 +706,7 @@ __device__ __noinline__ void row_rhs(const Params& P, const ForcingTerm& fterm, 
       S.flux[p] = net[p + P.kleft];      // model_target='flux' (model.py:609-615)
       continue;
     }
-    float r = equation_point(P.eq, S.ust[p + kHalo], dv, P.eta);
+    float r = equation_point(P.eq, S.ust[p + kRowHalo], dv, P.eta);
     if (cons) {
       S.flux[p] = r;
     } else {
@@ -749,7 +756,7 @@ static __device__ __noinline__ void row_rhs_weno_f64(const Params& P, int sample
     float dv[kMaxD];
     point_derivatives<MODE_STENCIL>(P, S, nullptr, p, dv, nullptr);     // float32 stencil channels
     double um, up;
-    weno_pair<double>(S.ustd + p + kHalo, um, up);
+    weno_pair<double>(S.ustd + p + kRowHalo, um, up);
     const double g = godunov_flux<double>(um, up);
     double flux;
     if (P.eq == EQ_BURGERS_GOD) flux = g - (double)__fmul_rn(P.eta, dv[2]);

@@ -403,19 +403,13 @@ __device__ __forceinline__ void set_k(SlotState& st, int s, float r) {
   else st.k3 = r;
 }
 
-// OP_COEF / OP_DERIV exports of the last epilogue (per-call parity hooks, not on the integration path)
-template <int NLV>
-__device__ __noinline__ void export_point(const TcParams& P, const Work& W, const float (&cf)[NLV],
-                                          const float (&dv)[kMaxD], size_t point) {
-  for (int d = 0; d < P.D; ++d) {
-    if (W.op == OP_DERIV) {
-      W.out[point * P.D + d] = dv[d];
-      continue;
-    }
-    for (int j = 0; j < kWin; ++j) {
-      const int i = j - P.wshift;
-      if (i >= 0 && i < P.S && d * kWin + j < NLV) W.out[(point * P.D + d) * P.S + i] = cf[d * kWin + j];
-    }
+// OP_COEF export of the last epilogue (per-call parity hook, not on the integration path): sixteen window
+// columns starting at column q0 of one grid point
+static __device__ __noinline__ void export_coefficients(const TcParams& P, const Work& W, const float (&c16)[16], int q0,
+                                                        size_t point) {
+  for (int i = 0; i < 16; ++i) {
+    const int q = q0 + i, d = q / kWin, slot = q % kWin - P.wshift;
+    if (d < P.D && slot >= 0 && slot < P.S) W.out[(point * P.D + d) * P.S + slot] = c16[i];
   }
 }
 
@@ -594,25 +588,29 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         if (!nowait) mbar_wait_spin(done0 + sl * TILES, done_parity);
         if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + sl * TILES, done_parity);     // before the next stage rewrites the planes
         fence_after();
-        float cf[NL];
-        tmem_read<NL, PREC>(taddr0 + (uint32_t)(sl * TILES * G::COLS), cf);
-        fence_before();
-        // window coefficients = accumulators + folded bias, then the stencil dot products (model.py:536-548)
+        // window coefficients = accumulators + folded bias, then the stencil dot products (model.py:536-548);
+        // sixteen columns at a time keeps the register peak low
         float dv[kMaxD];
 #pragma unroll
-        for (int d = 0; d < kMaxD; ++d) {
-          dv[d] = 0.f;
-          if (d * kWin + kWin > NL) continue;
-          float sum = 0.f;
+        for (int d = 0; d < kMaxD; ++d) dv[d] = 0.f;
+        const uint32_t taddr = taddr0 + (uint32_t)(sl * TILES * G::COLS);
 #pragma unroll
-          for (int j = 0; j < kWin; ++j) {
-            cf[d * kWin + j] = fmaf(cf[d * kWin + j], inv_last, P.bl[d * kWin + j]);
-            sum = fmaf(cf[d * kWin + j], u7[j], sum);
+        for (int half = 0; half < NL / 16; ++half) {
+          float2 v[8];
+          tmem_read_pairs<PREC>(taddr + 16 * half, taddr + NL + 16 * half, v);
+          float c16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int q = 16 * half + i;                    // column = derivative * 7 + window slot
+            c16[i] = fmaf(i & 1 ? v[i >> 1].y : v[i >> 1].x, inv_last, P.bl[q]);
+            if (q < kMaxD * kWin) dv[q / kWin] = fmaf(c16[i], u7[q % kWin], dv[q / kWin]);
           }
-          dv[d] = sum;
+          if (W.op == OP_COEF && live) export_coefficients(P, W, c16, 16 * half, (size_t)row * N + x);
         }
+        fence_before();
         if (!fast_op) {
-          if (live) export_point<NL>(P, W, cf, dv, (size_t)row * N + x);
+          if (W.op == OP_DERIV && live)
+            for (int d = 0; d < P.D; ++d) W.out[((size_t)row * N + x) * P.D + d] = dv[d];
           return;
         }
         float r = equation_point(P.eq, u7[kHalo], dv, P.eta);

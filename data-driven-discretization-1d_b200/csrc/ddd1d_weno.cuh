@@ -1,0 +1,249 @@
+// CTA-per-row fused WENO5 integrator with the row in registers (float32 WENO, BASELINE config 5:
+// Godunov Burgers, N = 2048), sm_100a.
+//
+// row_kernel<MODE_WENO> keeps the stage row, the stage derivatives and the flux in shared memory and walks
+// the points with a strided loop: 576 thread instructions per point-stage, of which 35 % are IEEE divisions
+// and 9 % the forcing basis loads (profiles/r01/row_kernel_weno_c5_ncu_full.json).  Here a thread owns PPT = 4
+// CONSECUTIVE points for the whole launch -- float64 solution, float32 stage derivatives and the stage values
+// in registers -- so that
+//   * the smoothness indicators (weno.py:46-57) are computed once per stencil centre and shared by the right
+//     reconstruction of point p and the left reconstruction of point p + 1 (the reference computes them twice);
+//   * 1 / (eps + beta)^2 is one MUFU.RCP (1 ulp) per indicator, shared by both sides, the weight normalisation
+//     one reciprocal per side and the /3, /6 of weno.py:82-88 multiplications (3 + 2 reciprocals per point instead
+//     of 22 IEEE divisions; every factor within 1-2 ulp of the reference's quotient, far inside the 2e-5 gate of
+//     the float32 WENO path, tests/test_gpu_parity.py);
+//   * the flux is evaluated at PPT + 1 points per thread, so the flux difference needs no second exchange;
+//   * halos (3 left, 4 right) come from the neighbouring lanes by shuffles; only the first / last lane of a warp
+//     goes through shared memory (one block barrier per stage, double buffered);
+//   * the forcing basis of the thread's 4 points is 6 LDG.128 per stage from L1, the mode amplitudes are
+//     computed by warp 0 (one forcing term per lane) ahead of the same barrier.
+// Reference: weno.py:43-123, integrate.WENODifferentiator (integrate.py:124-140), model.py:81-97 (float32
+// form), equations.py:341-370 (Godunov flux), :196-227 (forcing), integrate.odeint's Bogacki-Shampine steps.
+#pragma once
+#include "ddd1d_device.cuh"
+
+namespace ddd1d {
+
+struct WenoBeta { float i0, i1, i2; };      // 1 / (eps + beta_k)^2 of one stencil centre
+
+// MUFU.RCP: reciprocal to 1 ulp, no slow path (arguments here are positive and normal for any finite row)
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// weno.py:46-57 + the reciprocal squares of weno.py:60-66, centred on c
+__device__ __forceinline__ WenoBeta weno_inverse_beta(float a, float b, float c, float d, float e) {
+  const float eps = 1e-6f;
+  const float q0 = a - 4.f * b + 3.f * c, r0 = a - 2.f * b + c;
+  const float q1 = b - d, r1 = b - 2.f * c + d;
+  const float q2 = 3.f * c - 4.f * d + e, r2 = c - 2.f * d + e;
+  const float b0 = 0.25f * (q0 * q0) + (13.f / 12.f) * (r0 * r0);
+  const float b1 = 0.25f * (q1 * q1) + (13.f / 12.f) * (r1 * r1);
+  const float b2 = 0.25f * (q2 * q2) + (13.f / 12.f) * (r2 * r2);
+  WenoBeta o;
+  o.i0 = rcp_fast((eps + b0) * (eps + b0));
+  o.i1 = rcp_fast((eps + b1) * (eps + b1));
+  o.i2 = rcp_fast((eps + b2) * (eps + b2));
+  return o;
+}
+
+// left-biased reconstruction (weno.py:76-97) from the five points a..e centred on c, indicators `bt` of c
+__device__ __forceinline__ float weno_left(const WenoBeta& bt, float a, float b, float c, float d, float e) {
+  const float a0 = 0.1f * bt.i0, a1 = 0.6f * bt.i1, a2 = 0.3f * bt.i2;
+  const float rs = rcp_fast(a0 + a1 + a2);
+  const float w0 = a0 * rs, w1 = a1 * rs, w2 = a2 * rs;
+  constexpr float k3 = 1.f / 3.f, k6 = 1.f / 6.f;      // (the reference divides; x * (1/6) is within 1 ulp of x / 6)
+  return (w0 * k3) * a + (-(7.f * w0 + w1) * k6) * b + ((11.f * w0 + 5.f * w1 + 2.f * w2) * k6) * c +
+         ((2.f * w1 + 5.f * w2) * k6) * d + (-w2 * k6) * e;
+}
+
+// right-biased reconstruction at the cell LEFT of the centre (weno.py:100-123): points a..e centred on c
+__device__ __forceinline__ float weno_right(const WenoBeta& bt, float a, float b, float c, float d, float e) {
+  const float a0 = 0.3f * bt.i0, a1 = 0.6f * bt.i1, a2 = 0.1f * bt.i2;
+  const float rs = rcp_fast(a0 + a1 + a2);
+  const float w2 = a0 * rs, w1 = a1 * rs, w0 = a2 * rs;    // omega2, omega1, omega0 of weno.py:106-108
+  constexpr float k3 = 1.f / 3.f, k6 = 1.f / 6.f;
+  return (-w2 * k6) * a + ((5.f * w2 + 2.f * w1) * k6) * b + ((2.f * w2 + 5.f * w1 + 11.f * w0) * k6) * c +
+         (-(w1 + 7.f * w0) * k6) * d + (w0 * k3) * e;
+}
+
+constexpr int kWenoPpt = 4;              // consecutive points per thread
+constexpr int kWenoHaloL = 3, kWenoHaloR = 4;
+
+struct WenoShared {
+  float edge[2][32][2][4];               // [stage parity][warp][first lane's points 0..3 | last lane's points 1..3]
+  float amps[2][2 * kMaxModes];          // [stage parity][sine sums 0..7 | cosine sums 0..7]
+  unsigned int first_bad;
+};
+
+__global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
+                                                            const __grid_constant__ Tableau tab) {
+  constexpr int PPT = kWenoPpt;
+  __shared__ WenoShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int N = P.N;                       // == PPT * blockDim.x
+  const int p0 = tid * PPT;
+  const bool forced = eq_forced(P.eq) && P.P > 0;
+  const float4* const basis4 = reinterpret_cast<const float4*>(P.fbasis + p0);
+
+  // window-form stencils of the non-WENO derivative channels (d >= 2), in registers
+  float cf[2][kWin];
+#pragma unroll
+  for (int d = 0; d < 2; ++d)
+#pragma unroll
+    for (int j = 0; j < kWin; ++j) cf[d][j] = d + 2 < P.D ? __ldg(P.blob + P.st_off + (d + 2) * kWinPad + j) : 0.f;
+
+  uint32_t par = 0;
+  for (int row = blockIdx.x; row < W.batch; row += gridDim.x) {
+    const int sample = W.sample_offset + row;
+    const ForcingTerm fterm = warp == 0 ? load_forcing_term(P, sample, lane) : ForcingTerm{0.f, 0.f, 0.f, 0.f};
+    double y[PPT];
+    float k0[PPT], k1[PPT], k2[PPT], k3[PPT];      // stage derivatives (static indexing keeps them in registers)
+    {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(W.u + (size_t)row * N + p0));
+      y[0] = v.x; y[1] = v.y; y[2] = v.z; y[3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) k0[i] = k1[i] = k2[i] = k3[i] = 0.f;
+    if (tid == 0) sh.first_bad = 0xffffffffu;
+    int first_bad = -1;
+    int save_idx = 0;
+
+    for (int step = 0; step < W.nsteps; ++step) {
+      const double t = W.t0 + (double)step * W.dt;
+#pragma unroll 1
+      for (int s = 0; s < tab.stages; ++s) {
+        // ---- stage values, rounded to float32 (integrate.py:57-60,71); a[s][j] = 0 for j >= s ----
+        float E[PPT + kWenoHaloL + kWenoHaloR];        // E[j] = u[p0 + j - 3]
+        const double a0 = s > 0 ? tab.a[s][0] : 0.0, a1 = s > 1 ? tab.a[s][1] : 0.0, a2 = s > 2 ? tab.a[s][2] : 0.0;
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          const double acc = fma(a2, (double)k2[i], fma(a1, (double)k1[i], a0 * (double)k0[i]));
+          E[kWenoHaloL + i] = (float)(s == 0 ? y[i] : y[i] + W.dt * acc);
+        }
+        // ---- halo exchange: shuffles inside the warp, shared memory across warps ----
+        if (lane == 0) *reinterpret_cast<float4*>(sh.edge[par][warp][0]) = make_float4(E[3], E[4], E[5], E[6]);
+        if (lane == 31) *reinterpret_cast<float4*>(sh.edge[par][warp][1]) = make_float4(E[4], E[5], E[6], 0.f);
+        if (forced && warp == 0) {
+          // mode amplitudes of this stage (equations.py:214-219): one forcing term per lane, warp sums
+          const float ts = (float)(t + tab.c[s] * W.dt);
+          float sn, cs;
+          sincosf(fmaf(fterm.w, ts, fterm.phi), &sn, &cs);
+          const bool on = lane < P.P;
+          const float a_sin = on ? fterm.a * sn : 0.f;
+          const float a_cos = on ? (fterm.k < 0.f ? -fterm.a : fterm.a) * cs : 0.f;
+          const float ka = fabsf(fterm.k);
+          float mine_s = 0.f, mine_c = 0.f;
+#pragma unroll
+          for (int m = 0; m < kMaxModes; ++m) {
+            if (m >= P.M) break;
+            float a = ka == (float)(m + 1) ? a_sin : 0.f, b = ka == (float)(m + 1) ? a_cos : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (lane == m) { mine_s = a; mine_c = b; }
+          }
+          if (lane < kMaxModes) {
+            sh.amps[par][lane] = mine_s;
+            sh.amps[par][kMaxModes + lane] = mine_c;
+          }
+        }
+        {
+          // from the lane below: its points 1..3; from the lane above: its points 0..3
+          const float l1 = __shfl_up_sync(0xffffffffu, E[4], 1), l2 = __shfl_up_sync(0xffffffffu, E[5], 1),
+                      l3 = __shfl_up_sync(0xffffffffu, E[6], 1);
+          const float r0 = __shfl_down_sync(0xffffffffu, E[3], 1), r1 = __shfl_down_sync(0xffffffffu, E[4], 1),
+                      r2 = __shfl_down_sync(0xffffffffu, E[5], 1), r3 = __shfl_down_sync(0xffffffffu, E[6], 1);
+          E[0] = l1; E[1] = l2; E[2] = l3;
+          E[7] = r0; E[8] = r1; E[9] = r2; E[10] = r3;
+        }
+        __syncthreads();
+        if (lane == 0) {
+          const float4 v = *reinterpret_cast<const float4*>(sh.edge[par][warp == 0 ? nwarps - 1 : warp - 1][1]);
+          E[0] = v.x; E[1] = v.y; E[2] = v.z;
+        }
+        if (lane == 31) {
+          const float4 v = *reinterpret_cast<const float4*>(sh.edge[par][warp + 1 == nwarps ? 0 : warp + 1][0]);
+          E[7] = v.x; E[8] = v.y; E[9] = v.z; E[10] = v.w;
+        }
+        // ---- WENO5 reconstructions and the flux at points p0 .. p0 + PPT ----
+        // inverse smoothness indicators of the centres p0 - 1 .. p0 + PPT (E index 2 .. PPT + 3)
+        WenoBeta bt[PPT + 2];
+#pragma unroll
+        for (int c = 0; c < PPT + 2; ++c) bt[c] = weno_inverse_beta(E[c], E[c + 1], E[c + 2], E[c + 3], E[c + 4]);
+        float flux[PPT + 1];
+#pragma unroll
+        for (int i = 0; i <= PPT; ++i) {
+          // point p = p0 + i: u_minus = left reconstruction centred on p - 1, u_plus = right one centred on p
+          // (weno.py:92-97,118-123 and the roll by +1 of integrate.py:137-138)
+          float dv[kMaxD];
+          dv[0] = weno_left(bt[i], E[i], E[i + 1], E[i + 2], E[i + 3], E[i + 4]);
+          dv[1] = weno_right(bt[i + 1], E[i + 1], E[i + 2], E[i + 3], E[i + 4], E[i + 5]);
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float acc = 0.f;                       // constant stencil rows (model.py:99-109, 536-548)
+#pragma unroll
+            for (int j = 0; j < kWin; ++j) acc = fmaf(cf[d][j], E[i + j], acc);
+            dv[2 + d] = acc;
+          }
+          flux[i] = equation_point(P.eq, E[kWenoHaloL + i], dv, P.eta);
+        }
+        // ---- y_t = -(1/dx) (flux[x+1] - flux[x]) + forcing (equations.py:305-320, 276-277) ----
+        float f[PPT] = {0.f, 0.f, 0.f, 0.f};
+        if (forced) {
+#pragma unroll
+          for (int m = 0; m < kMaxModes; ++m) {
+            if (m >= P.M) break;
+            const float as = sh.amps[par][m], ac = sh.amps[par][kMaxModes + m];
+            const float4 bc = __ldg(basis4 + (size_t)m * (N / 4)), bs = __ldg(basis4 + (size_t)(P.M + m) * (N / 4));
+            f[0] = fmaf(as, bc.x, f[0]); f[0] = fmaf(ac, bs.x, f[0]);
+            f[1] = fmaf(as, bc.y, f[1]); f[1] = fmaf(ac, bs.y, f[1]);
+            f[2] = fmaf(as, bc.z, f[2]); f[2] = fmaf(ac, bs.z, f[2]);
+            f[3] = fmaf(as, bc.w, f[3]); f[3] = fmaf(ac, bs.w, f[3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+          float r = -__fmul_rn(P.inv_dx, __fsub_rn(flux[i + 1], flux[i]));
+          if (forced) r = __fadd_rn(r, f[i]);
+          if (s == 0) k0[i] = r;
+          else if (s == 1) k1[i] = r;
+          else if (s == 2) k2[i] = r;
+          else k3[i] = r;
+        }
+        par ^= 1u;
+      }
+      // ---- end of the step: float64 update, snapshot ----
+      const bool save = ((step + 1) % W.save_every) == 0;
+      float out[PPT];
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        double acc = tab.b[0] * (double)k0[i];
+        if (tab.stages > 1) acc = fma(tab.b[1], (double)k1[i], acc);
+        if (tab.stages > 2) acc = fma(tab.b[2], (double)k2[i], acc);
+        if (tab.stages > 3) acc = fma(tab.b[3], (double)k3[i], acc);
+        const double yn = y[i] + W.dt * acc;
+        y[i] = yn;
+        if (first_bad < 0 && !isfinite(yn)) first_bad = step;
+        out[i] = (float)yn;
+      }
+      if (save) {
+        *reinterpret_cast<float4*>(W.snaps + ((size_t)save_idx * W.batch + row) * N + p0) =
+            make_float4(out[0], out[1], out[2], out[3]);
+        ++save_idx;
+      }
+    }
+    if (W.first_bad) {
+      if (first_bad >= 0) atomicMin(&sh.first_bad, (unsigned int)first_bad);
+      __syncthreads();
+      if (tid == 0) W.first_bad[row] = sh.first_bad == 0xffffffffu ? -1 : (int)sh.first_bad;
+    }
+    __syncthreads();       // the next row reuses the shared words
+  }
+}
+
+}  // namespace ddd1d

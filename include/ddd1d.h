@@ -22,10 +22,14 @@
  *     first_bad_step[] records when (the reference NaN-pads, integrate.py:161-167);
  *   - one handle per (device, stream); handles are independent and re-entrant.
  *
- * Stencil window: every derivative channel is a 7-wide window over offsets
- * -3..+3 relative to the output point.  A stencil of `s` points applied with the
+ * Stencil window: every derivative channel is an 11-wide window over offsets
+ * -5..+5 relative to the output point.  A stencil of `s` points applied with the
  * reference's centred periodic padding (layers.py:76-79: ceil((s-1)/2) points on
- * the left) occupies window slots 3-ceil((s-1)/2) ... ; unused slots are zero.
+ * the left) occupies window slots 5-ceil((s-1)/2) ... ; unused slots are zero.
+ * Tables that use only the central 7 slots (every stencil of up to 7 points: the
+ * reference's defaults) run on 7-slot kernels; the coefficient grids of
+ * hparams.coefficient_grid_min_size = 9 (9 centred or 10 staggered points,
+ * model.py:445-448, training_test.py:56) run on the FFMA engine.
  */
 #ifndef DDD1D_H_
 #define DDD1D_H_
@@ -34,9 +38,9 @@
 extern "C" {
 #endif
 
-#define DDD1D_VERSION 1
+#define DDD1D_VERSION 2
 #define DDD1D_MAX_DERIVATIVES 4
-#define DDD1D_WINDOW 7
+#define DDD1D_WINDOW 11
 #define DDD1D_MAX_LAYERS 6
 #define DDD1D_MAX_FORCING_MODES 8
 
@@ -116,7 +120,7 @@ typedef struct ddd1d_config {
   int kernel_size;         /* K */
   int activation;          /* DDD1D_ACT_* of the hidden layers */
   int net_outputs;         /* C = channels of the last conv */
-  int stencil_size;        /* S = size of the coefficient grid (6 staggered, 7 centred) */
+  int stencil_size;        /* S = size of the coefficient grid (6 staggered, 7 centred; up to 11) */
   int projection;          /* DDD1D_PROJ_* */
   int engine;              /* DDD1D_ENGINE_*: which kernel evaluates the conv stack */
 } ddd1d_config;
@@ -131,7 +135,7 @@ int ddd1d_destroy(ddd1d_handle* handle);
 const char* ddd1d_last_error(const ddd1d_handle* handle);
 int ddd1d_version(void);
 
-/* Fixed coefficients per derivative channel in window form, host double [D][7].
+/* Fixed coefficients per derivative channel in window form, host double [D][DDD1D_WINDOW].
  * STENCIL mode: polynomials.coefficients() of each derivative (polynomials.py:280-303);
  * LEARNED mode with PROJ_NULLSPACE: PolynomialAccuracyLayer.bias (polynomials.py:237-239);
  * WENO mode: rows of u_minus/u_plus are ignored. */
@@ -143,7 +147,7 @@ int ddd1d_set_stencils(ddd1d_handle* handle, const double* window_coefficients);
 int ddd1d_set_layer(ddd1d_handle* handle, int layer, const float* kernel, const float* bias,
                     int kernel_size, int cin, int cout);
 
-/* Null-space rows in window form, host double [C][7], and the number of net
+/* Null-space rows in window form, host double [C][DDD1D_WINDOW], and the number of net
  * channels feeding each derivative, int [D] (PolynomialAccuracyLayer.nullspace /
  * input_size, polynomials.py:246-262; model.py:504-511). */
 int ddd1d_set_projection(ddd1d_handle* handle, const double* window_nullspace, const int* input_sizes);
@@ -219,7 +223,7 @@ int ddd1d_weno_reconstruct(int device, int real, const void* u, void* left, void
  * the launch shape the integrator uses (grid, block, dynamic shared bytes). */
 long long ddd1d_launch_count(const ddd1d_handle* handle);
 int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* block, int* shared_bytes);
-/* DDD1D_ENGINE_FFMA or DDD1D_ENGINE_TENSOR: the engine the next launch will use. */
+/* DDD1D_ENGINE_FFMA or one of DDD1D_ENGINE_TENSOR*: the engine the next launch will use. */
 int ddd1d_engine(const ddd1d_handle* handle);
 
 #ifdef __cplusplus

@@ -457,10 +457,37 @@ def golden_weno_parts():
   return len(out)
 
 
+def golden_grid9():
+  """hparams.coefficient_grid_min_size = 9 (training_test.py:56 runs it on the default, conservative KS):
+  9 centred points for the plain forms, 10 staggered points for the conservative / Godunov ones."""
+  out = {}
+  rs = np.random.RandomState(909)
+  for kind, variant in (('ks', 'conservative'), ('ks', 'plain'), ('burgers', 'plain'), ('burgers', 'conservative'),
+                        ('kdv', 'godunov')):
+    for n in (32, 64):
+      hp = make_hparams(kind, variant, n, coefficient_grid_min_size=9)
+      eq = equation_class(kind, variant)(n, random_seed=9)
+      weights = random_weights(conv_shapes(hp, eq), seed=500 + len(out))
+      u = (0.6 * rs.randn(3, n)).astype(np.float32)
+      key = '%s/%s/%d' % (kind, variant, n)
+      out.update(flat_weights(key, weights))
+      out[key + '/u'] = u
+      set_store(weights)
+      out[key + '/coefficients'] = model.predict_coefficients(tf.Tensor(u), hp).a
+      set_store(weights)
+      out[key + '/space_derivatives'] = model.predict_space_derivatives(tf.Tensor(u), hp).a
+      set_store(weights)
+      out[key + '/time_derivative'] = model.predict_time_derivative(tf.Tensor(u), hp).a
+      d = EagerModelDifferentiator(eq, hp, weights)
+      out[key + '/differentiator'] = d(0.23, u[0].astype(np.float64))
+  np.savez_compressed(os.path.join(HERE, 'grid9.npz'), **out)
+  return len(out)
+
+
 if __name__ == '__main__':
   only = sys.argv[1:]
   for fn in (golden_tables, golden_learned, golden_targets, golden_baseline, golden_pointwise,
-             golden_trajectories, golden_layers, golden_layers0, golden_weno_parts):
+             golden_trajectories, golden_layers, golden_layers0, golden_weno_parts, golden_grid9):
     if only and fn.__name__ not in only:
       continue
     print(fn.__name__, fn())

@@ -55,6 +55,38 @@ def test_learned_against_reference_fixture(golden, monkeypatch, kind, variant, n
   assert rel_err(got, g[key + '/differentiator']) < RHS_TOL
 
 
+@pytest.mark.parametrize('kind,variant', (('ks', 'conservative'), ('ks', 'plain'), ('burgers', 'plain'),
+                                          ('burgers', 'conservative'), ('kdv', 'godunov')))
+@pytest.mark.parametrize('n', (32, 64))
+def test_coefficient_grid_min_size_9_against_reference_fixture(golden, kind, variant, n):
+  """hparams.coefficient_grid_min_size = 9 (model.py:445-448; the reference's training_test.py:56 runs it on the
+  default conservative KS): 9 centred or 10 staggered points, the 11-slot window of the FFMA engine."""
+  from ddd1d_b200 import model, integrate
+  g = golden('grid9')
+  key = '%s/%s/%d' % (kind, variant, n)
+  hp = G.product_hparams(kind, variant, n, coefficient_grid_min_size=9)
+  w = weights_from(g, key)
+  u = g[key + '/u']
+  coefs = cpu(model.predict_coefficients(u, hp, w))
+  assert coefs.shape == g[key + '/coefficients'].shape
+  assert rel_err(coefs, g[key + '/coefficients']) < RHS_TOL
+  assert rel_err(cpu(model.predict_space_derivatives(u, hp, w)), g[key + '/space_derivatives']) < RHS_TOL
+  assert rel_err(cpu(model.predict_time_derivative(u, hp, w)), g[key + '/time_derivative']) < FLUX_TOL
+  eq = G.product_equation(kind, variant, n, seed=9)
+  d = integrate.SavedModelDifferentiator(w, eq, hp)
+  assert d.solver.engine() == 'ffma'
+  assert rel_err(d(0.23, u[0].astype(np.float64)), g[key + '/differentiator']) < FLUX_TOL
+  # and a short fused integration against the oracle
+  oeq = G.oracle_equation(kind, variant, n, seed=9)
+  net = O.NetSpec(coefficient_grid_min_size=9)
+  dt = {'burgers': 1e-3, 'kdv': 2.5e-5, 'ks': 1e-5}[kind]
+  w_small = [(k, b) for k, b in w[:-1]] + [(w[-1][0] * 0.1, w[-1][1] * 0.1)]
+  solver = integrate.BatchIntegrator.learned([eq], hp, w_small)
+  got = cpu(solver.integrate(u[:1], 0.0, dt, 6, 3))
+  want = O.fixed_step_integrate(O.batched_rhs([oeq], net, w_small, mode='learned'), u[:1], 0.0, dt, 6, 3)
+  assert rel_err(got, want) < TRAJ_TOL
+
+
 def test_learned_hparam_variants_against_reference_fixture(golden):
   from ddd1d_b200 import model
   g = golden('learned')
@@ -391,6 +423,36 @@ def test_c5_weno_shape_against_oracle():
   assert rel_err(cpu(got[pick]), want) < 2e-4
 
 
+@pytest.mark.parametrize('n', (384, 512, 1024, 2048))
+def test_weno_block_kernel(monkeypatch, n):
+  """The register-resident CTA-per-row WENO5 integrator (csrc/ddd1d_weno.cuh; rows of 4 points per thread):
+  every Godunov equation against the oracle, every scheme, snapshots, odd batch sizes and divergence
+  reporting against the shared-memory CTA-per-row kernel it replaces.  The two differ only in the
+  rounding of the WENO weights (reciprocal-and-multiply here, IEEE division there)."""
+  from ddd1d_b200 import integrate
+  for kind, dt in (('burgers', 1e-4), ('kdv', 2.5e-5), ('ks', 1e-5)):
+    _fixed_step_case(kind, 'godunov', n, 3, 12, dt, 'weno', tol=2e-4)
+  batch = 301
+  eqs = [G.product_equation('burgers', 'godunov', n, seed=s) for s in range(batch)]
+  solver = integrate.BatchIntegrator.weno(eqs)
+  u0 = G.smooth_rows(batch, n, seed=9)
+  u0[7] *= 1e20                                         # this row blows up: divergence is data
+  for scheme in ('rk3', 'midpoint', 'euler', 'rk4'):
+    monkeypatch.delenv('DDD1D_NO_WENO_BLOCK', raising=False)
+    assert solver.solver.launch_shape(batch)['block'] == n // 4
+    a, bad_a = solver.integrate(u0, 0.3, 1e-4, 12, 4, scheme, return_first_bad=True)
+    monkeypatch.setenv('DDD1D_NO_WENO_BLOCK', '1')
+    assert solver.solver.launch_shape(batch)['block'] != n // 4 or n == 2048
+    b, bad_b = solver.integrate(u0, 0.3, 1e-4, 12, 4, scheme, return_first_bad=True)
+    monkeypatch.delenv('DDD1D_NO_WENO_BLOCK', raising=False)
+    a, b = cpu(a), cpu(b)
+    np.testing.assert_array_equal(cpu(bad_a), cpu(bad_b))
+    ok = np.isfinite(b).all(axis=(0, 2))
+    assert ok.sum() == batch - 1 and not ok[7]
+    assert rel_err(a[:, ok], b[:, ok]) < 5e-6, scheme
+    np.testing.assert_array_equal(np.isfinite(a), np.isfinite(b))
+
+
 # ---------------------------------------------------------------------------------
 # edge cases and error behaviour
 # ---------------------------------------------------------------------------------
@@ -474,10 +536,10 @@ def test_argument_errors_mirror_the_reference():
   with pytest.raises(ValueError):                      # more rows than forcing samples
     integrate.BatchIntegrator.baseline([equations.BurgersEquation(32)], 1).integrate(
         np.zeros((2, 32), np.float32), 0.0, 1e-3, 1)
-  with pytest.raises(NotImplementedError):             # coefficient_grid_min_size=9 -> 9-point stencil
+  with pytest.raises(NotImplementedError):             # coefficient grids beyond the 11-slot window
     runtime.learned_solver(equations.BurgersEquation(32),
-                           G.product_hparams('burgers', 'plain', 32, coefficient_grid_min_size=9),
-                           O.glorot_weights(oeq, O.NetSpec(coefficient_grid_min_size=9), seed=0))
+                           G.product_hparams('burgers', 'plain', 32, coefficient_grid_min_size=13),
+                           O.glorot_weights(oeq, O.NetSpec(coefficient_grid_min_size=13), seed=0))
 
 
 def test_host_buffer_entry_points():

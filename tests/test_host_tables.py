@@ -89,13 +89,19 @@ def test_from_hparams_and_defaults():
 
 def test_window_alignment():
   # s points sit ceil((s-1)/2) to the left of the output (layers.py:76-79)
-  np.testing.assert_array_equal(_lib.to_window([1., 2., 3.]), [0, 0, 1, 2, 3, 0, 0])
-  np.testing.assert_array_equal(_lib.to_window([1., 2.]), [0, 0, 1, 2, 0, 0, 0])
-  np.testing.assert_array_equal(_lib.to_window([1., 2., 3., 4.]), [0, 1, 2, 3, 4, 0, 0])
-  np.testing.assert_array_equal(_lib.to_window(np.arange(6.) + 1), [1, 2, 3, 4, 5, 6, 0])
-  np.testing.assert_array_equal(_lib.to_window(np.arange(7.) + 1), np.arange(7.) + 1)
+  centre = lambda w: list(w[2:9])          # the 7 slots -3..+3 of the 11-slot window
+  assert _lib.WINDOW == 11
+  for stencil, want in (([1., 2., 3.], [0, 0, 1, 2, 3, 0, 0]), ([1., 2.], [0, 0, 1, 2, 0, 0, 0]),
+                        ([1., 2., 3., 4.], [0, 1, 2, 3, 4, 0, 0]), (np.arange(6.) + 1, [1, 2, 3, 4, 5, 6, 0]),
+                        (np.arange(7.) + 1, np.arange(7.) + 1)):
+    w = _lib.to_window(stencil)
+    np.testing.assert_array_equal(centre(w), want)
+    assert not w[:2].any() and not w[9:].any()
+  # hparams.coefficient_grid_min_size = 9: 9 centred points (-4..+4), 10 staggered ones (-5..+4)
+  np.testing.assert_array_equal(_lib.to_window(np.arange(9.) + 1), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 0])
+  np.testing.assert_array_equal(_lib.to_window(np.arange(10.) + 1), [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 0])
   with pytest.raises(NotImplementedError):
-    _lib.to_window(np.arange(9.))
+    _lib.to_window(np.arange(12.))
 
 
 def test_abi_exports_every_declared_symbol():
@@ -105,7 +111,7 @@ def test_abi_exports_every_declared_symbol():
   lib = _lib.load()   # raises loudly if the library is missing
   for name in declared:
     assert getattr(lib, name) is not None
-  assert lib.ddd1d_version() == 1
+  assert lib.ddd1d_version() == 2
   assert ctypes.sizeof(_lib.Config) == 88
 
 

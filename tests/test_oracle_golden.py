@@ -231,3 +231,27 @@ def test_num_layers_zero(golden, kind, variant):
   u = g[key + '/u']
   assert rel_err(O.predict_coefficients(u, eq, net, w), g[key + '/coefficients']) < F32_TOL
   assert rel_err(O.predict_time_derivative(u, eq, net, w), g[key + '/time_derivative']) < F32_TOL
+
+
+GRID9_CASES = (('ks', 'conservative'), ('ks', 'plain'), ('burgers', 'plain'), ('burgers', 'conservative'),
+               ('kdv', 'godunov'))
+
+
+@pytest.mark.parametrize('kind,variant', GRID9_CASES)
+@pytest.mark.parametrize('n', (32, 64))
+def test_coefficient_grid_min_size_9(golden, kind, variant, n):
+  """hparams.coefficient_grid_min_size = 9 (model.py:445-448; training_test.py:56): 9 centred / 10 staggered points."""
+  g = golden('grid9')
+  key = '%s/%s/%d' % (kind, variant, n)
+  eq = O.EquationSpec(kind, variant, num_points=n, random_seed=9)
+  net = O.NetSpec(coefficient_grid_min_size=9)
+  assert O.coefficient_grid(eq, net).size == (9 if variant == 'plain' else 10)
+  w = weights_from(g, key)
+  u = g[key + '/u']
+  coefs = O.predict_coefficients(u, eq, net, w)
+  assert coefs.shape == g[key + '/coefficients'].shape
+  assert rel_err(coefs, g[key + '/coefficients']) < F32_TOL
+  assert rel_err(O.apply_coefficients(coefs, u), g[key + '/space_derivatives']) < 5 * F32_TOL
+  assert rel_err(O.predict_time_derivative(u, eq, net, w), g[key + '/time_derivative']) < 1e-5
+  d = O.ModelDifferentiator(eq, net, w)
+  assert rel_err(d(0.23, u[0].astype(np.float64)), g[key + '/differentiator']) < 1e-5
