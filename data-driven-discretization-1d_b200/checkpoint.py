@@ -357,22 +357,27 @@ def checkpoint_dir_to_path(checkpoint_dir):
   return os.path.join(checkpoint_dir, 'model.ckpt')
 
 
-_LAYER = re.compile(r'^(?:.*/)?predict_coefficients/conv1d(?:_(\d+))?/(kernel|bias)$')
+# Only predict_coefficients opens a variable scope (model.py:442).  The direct model targets
+# ('space_derivatives' / 'time_derivative' / 'flux') build their conv stack through _multilayer_conv1d
+# (model.py:551-568) with no scope, so their Saver variables are top-level `conv1d/kernel`, `conv1d_1/kernel`, ...
+# Optimiser slots (`.../kernel/Adam`, `.../kernel/Adam_1`) do not end in kernel|bias and never match.
+_LAYER = re.compile(r'^(?:.*/)?(?:predict_coefficients/)?conv1d(?:_(\d+))?/(kernel|bias)$')
 
 
 def conv_weights(variables):
   """{name: ndarray} -> [(kernel[k, in, out], bias[out]), ...] in layer order, or
   [coefficients] for a `num_layers=0` model (model.py:497-500)."""
   layers = {}
+  scoped = any(re.match(r'^(?:.*/)?predict_coefficients/', name) for name in variables)
   for name, value in variables.items():
     m = _LAYER.match(name)
-    if m:
+    if m and (('predict_coefficients/' in name) == scoped):     # never mix a scoped stack with a stray unscoped one
       layers.setdefault(int(m.group(1) or 0), {})[m.group(2)] = np.asarray(value, np.float32)
   if not layers:
     for name, value in variables.items():
       if re.match(r'^(?:.*/)?predict_coefficients/coefficients$', name):
         return [np.asarray(value, np.float32)]
-    raise ValueError('no predict_coefficients/conv1d* variables in the checkpoint (found: %s)'
+    raise ValueError('no [predict_coefficients/]conv1d* variables in the checkpoint (found: %s)'
                      % ', '.join(sorted(variables)[:8]))
   out = []
   for i in range(len(layers)):
@@ -398,14 +403,23 @@ def load_conv_weights(checkpoint_dir, verify=True):
   return conv_weights(read_checkpoint(prefix, verify))
 
 
-def save_conv_weights(checkpoint_dir, weights):
-  """Inverse of load_conv_weights: `<dir>/model.ckpt.*` with the reference's variable names."""
+def save_conv_weights(checkpoint_dir, weights, model_target='coefficients'):
+  """Inverse of load_conv_weights: `<dir>/model.ckpt.*` with the reference's variable names -- under
+  `predict_coefficients/` for model_target='coefficients' (model.py:442), top level for the direct targets
+  (model.py:551-568); a `num_layers=0` model is the single vector `predict_coefficients/coefficients`
+  (model.py:497-500)."""
   os.makedirs(checkpoint_dir, exist_ok=True)
   tensors = {}
-  for i, (kernel, bias) in enumerate(weights):
-    scope = 'predict_coefficients/conv1d' + ('_%d' % i if i else '')
-    tensors[scope + '/kernel'] = np.asarray(kernel, np.float32)
-    tensors[scope + '/bias'] = np.asarray(bias, np.float32)
+  prefix = 'predict_coefficients/' if model_target == 'coefficients' else ''
+  if len(weights) == 1 and not isinstance(weights[0], (tuple, list)):
+    if model_target != 'coefficients':
+      raise ValueError('a num_layers=0 model has model_target="coefficients"')
+    tensors['predict_coefficients/coefficients'] = np.asarray(weights[0], np.float32)
+  else:
+    for i, (kernel, bias) in enumerate(weights):
+      scope = prefix + 'conv1d' + ('_%d' % i if i else '')
+      tensors[scope + '/kernel'] = np.asarray(kernel, np.float32)
+      tensors[scope + '/bias'] = np.asarray(bias, np.float32)
   write_checkpoint(checkpoint_dir_to_path(checkpoint_dir), tensors)
 
 
@@ -514,6 +528,9 @@ def format_hparams_pbtxt(values):
     if kind == 'bytes':
       return '"%s"' % _c_escape(v.encode('utf-8'))
     if kind == 'float':
+      # the float32 value's float64 repr: what the protobuf runtime installed here prints for a float field (pinned by
+      # tests/test_checkpoint.py against google.protobuf.text_format); newer runtimes print the shortest float32 form,
+      # which parse_hparams reads just the same
       return repr(float(np.float32(v))) if np.isfinite(v) else str(v)
     return str(v)
 

@@ -7,9 +7,13 @@ the far side of the hot path:
 * `unify_x_coords`, `calculate_mae`, `is_good`, `mostly_good`, `calculate_survival`,
   `mostly_good_survival`: analysis.py:39-90 and scripts/run_evaluation.py:189-210 as
   torch reductions over the gathered trajectories (they run where the tensors live);
-* `write_results` / `read_results`: the `results.nc` schema `{y: (sample, time, x)}` with
-  coords `time, x, num_evals, sample` (scripts/run_evaluation.py:168-174,186-187).  netCDF
-  needs xarray + netCDF4, absent here; the same variables are written as `.npz`.
+* `write_results` / `read_results`: `results.nc` as the reference writes it -- `Dataset.to_netcdf()` bytes
+  (xarray_beam.py:32-35), i.e. NetCDF-3 through xarray's SciPy backend -- with the schema
+  `{y: (sample, time, x)}` + coords `time, x, sample`, `num_evals(sample)` (scripts/run_evaluation.py:168-174,
+  186-187), written with `scipy.io.netcdf_file`; `write_metric` does the same for `mae.nc` / `survival.nc`
+  (scripts/run_evaluation.py:189-210).  A path ending in `.npz` keeps the NumPy container;
+* `run_integrate_batch(..., distributed=True)`: the per-seed map of scripts/run_evaluation.py:212-221 over
+  the GPUs of one box -- every rank integrates a contiguous block of seeds, one all-gather at the end.
 
 Arrays may be NumPy or torch (CPU or CUDA); results come back as NumPy.
 """
@@ -26,13 +30,19 @@ def _t(x, like=None):
 
 
 def run_integrate_batch(checkpoint_dir, hparams, initial_conditions, times, warmup=0.0,
-                        integrate_method='RK23', fixed_dt=None, first_seed=0):
+                        integrate_method='RK23', fixed_dt=None, first_seed=0, distributed=False, group=None):
   """Integrate the learned model from `initial_conditions[sample, x]`, sample i with
   `random_seed = first_seed + i` (scripts/run_evaluation.py:147-166).
 
   integrate_method='RK23' runs SciPy's adaptive scheme per row on the device (same
   controller and dense output as integrate.odeint); `fixed_dt` switches to the fused
-  fixed-step Bogacki-Shampine integrator.  Returns the results dict of write_results."""
+  fixed-step Bogacki-Shampine integrator.  Returns the results dict of write_results.
+
+  distributed=True (inside an initialised torch.distributed job, one rank per GPU): every rank passes the
+  SAME full `initial_conditions`, integrates its contiguous block of samples (distributed.shard_bounds) and
+  receives the results of all samples -- the reference's Beam map over seeds (scripts/run_evaluation.py:
+  212-221) with one all-gather at the end.  Rows are independent, so the result is bit-identical to the
+  single-GPU call."""
   from . import equations as equations_lib
   from . import integrate
   y0 = np.asarray(initial_conditions)
@@ -43,6 +53,8 @@ def run_integrate_batch(checkpoint_dir, hparams, initial_conditions, times, warm
   if hparams is None:
     from . import training
     hparams = training.load_hparams(checkpoint_dir)
+  if distributed:
+    return _run_sharded(checkpoint_dir, hparams, y0, times, warmup, integrate_method, fixed_dt, first_seed, group)
   coarse = [equations_lib.from_hparams(hparams, random_seed=first_seed + i)[1] for i in range(y0.shape[0])]
   weights = integrate._load_weights(checkpoint_dir)
   batch = integrate.BatchIntegrator.learned(coarse, hparams, weights)
@@ -58,19 +70,106 @@ def run_integrate_batch(checkpoint_dir, hparams, initial_conditions, times, warm
           'num_evals': np.asarray(nfev), 'sample': first_seed + np.arange(y0.shape[0])}
 
 
+def _run_sharded(checkpoint_dir, hparams, y0, times, warmup, integrate_method, fixed_dt, first_seed, group,
+                 local_runner=None):
+  """The distributed branch of run_integrate_batch.  `local_runner` (tests: the CPU plumbing under gloo)
+  replaces the CUDA integration of one block."""
+  import torch
+  import torch.distributed as dist
+  from . import distributed as D
+  if not (dist.is_available() and dist.is_initialized()):
+    raise RuntimeError('distributed=True needs an initialised torch.distributed process group')
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  total = y0.shape[0]
+  start, stop = D.shard_bounds(total, rank, world)
+  run = local_runner or (lambda block, seed0: run_integrate_batch(
+      checkpoint_dir, hparams, block, times, warmup, integrate_method, fixed_dt, seed0))
+  times = np.asarray(times, dtype=np.float64)
+  if stop > start:
+    local = run(y0[start:stop], first_seed + start)
+    y_local, evals_local = np.asarray(local['y']), np.asarray(local['num_evals'])
+    x = np.asarray(local['x'])
+  else:                                               # more ranks than samples: an empty block
+    y_local = np.zeros((0, len(times), y0.shape[1]))
+    evals_local = np.zeros((0,), dtype=np.int64)
+    x = None
+  device = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
+  y = D.gather_snapshots(torch.as_tensor(y_local, dtype=torch.float64, device=device), total, sample_axis=0, group=group)
+  evals = D.gather_snapshots(torch.as_tensor(evals_local.astype(np.int64), device=device)[:, None], total,
+                             sample_axis=0, group=group)[:, 0]
+  if x is None:                                       # the grid is a function of hparams alone
+    from . import equations as equations_lib
+    x = equations_lib.from_hparams(hparams, random_seed=first_seed)[1].grid.solution_x
+  return {'y': y.cpu().numpy(), 'time': warmup + times, 'x': x, 'num_evals': evals.cpu().numpy(),
+          'sample': first_seed + np.arange(total)}
+
+
+def _to_netcdf3(path, dims, variables, attrs=None):
+  """Write NetCDF-3 (classic, 64-bit offsets) with SciPy: `dims` {name: size}, `variables`
+  {name: (dim names, array)}.  What xarray's Dataset.to_netcdf() emits with its SciPy backend, the
+  backend the reference's bytes-in-memory writer uses (xarray_beam.py:32-35)."""
+  from scipy.io import netcdf_file
+  with netcdf_file(path, 'w', version=2) as f:
+    for name, size in dims.items():
+      f.createDimension(name, int(size))
+    for name, spec in variables.items():
+      vdims, array = spec[0], np.asarray(spec[1])
+      if array.dtype == np.int64:                     # NetCDF-3 has no 64-bit integers (xarray casts likewise)
+        array = array.astype(np.int32)
+      elif array.dtype == np.bool_:
+        array = array.astype(np.int8)
+      var = f.createVariable(name, array.dtype, tuple(vdims))
+      var[...] = array
+      for key, value in (spec[2] if len(spec) > 2 else {}).items():
+        setattr(var, key, value)
+    for key, value in (attrs or {}).items():
+      setattr(f, key, value)
+
+
 def write_results(path, results):
-  """`results.nc` variables as `.npz`: y (sample, time, x) + coords."""
+  """`results.nc`: y (sample, time, x) + coords time, x, sample and num_evals (sample), NetCDF-3; a path
+  ending in .npz keeps the NumPy container."""
   y = np.asarray(results['y'])
   if y.ndim != 3 or y.shape != (len(results['sample']), len(results['time']), len(results['x'])):
     raise ValueError('y must be (sample, time, x)')
-  np.savez_compressed(path, y=y, time=np.asarray(results['time']), x=np.asarray(results['x']),
-                      num_evals=np.asarray(results['num_evals']), sample=np.asarray(results['sample']),
-                      dims=json.dumps({'y': ['sample', 'time', 'x'], 'num_evals': ['sample']}))
+  if str(path).endswith('.npz'):
+    np.savez_compressed(path, y=y, time=np.asarray(results['time']), x=np.asarray(results['x']),
+                        num_evals=np.asarray(results['num_evals']), sample=np.asarray(results['sample']),
+                        dims=json.dumps({'y': ['sample', 'time', 'x'], 'num_evals': ['sample']}))
+    return
+  _to_netcdf3(path, {'sample': y.shape[0], 'time': y.shape[1], 'x': y.shape[2]},
+              {'y': (('sample', 'time', 'x'), y, {'coordinates': 'num_evals'}),     # xarray's encoding of a non-index coordinate
+               'time': (('time',), np.asarray(results['time'], dtype=np.float64)),
+               'x': (('x',), np.asarray(results['x'], dtype=np.float64)),
+               'sample': (('sample',), np.asarray(results['sample'])),
+               'num_evals': (('sample',), np.asarray(results['num_evals']))})
 
 
 def read_results(path):
-  with np.load(path) as f:
-    return {k: f[k] for k in ('y', 'time', 'x', 'num_evals', 'sample')}
+  if str(path).endswith('.npz'):
+    with np.load(path) as f:
+      return {k: f[k] for k in ('y', 'time', 'x', 'num_evals', 'sample')}
+  from scipy.io import netcdf_file
+  with netcdf_file(path, 'r', mmap=False) as f:
+    return {k: np.array(f.variables[k][...]) for k in ('y', 'time', 'x', 'num_evals', 'sample')}
+
+
+def write_metric(path, name, values, stop_times=None, samples=None):
+  """`mae.nc` (name='mae': values [time_max, sample], scripts/run_evaluation.py:189-198) or `survival.nc`
+  (name='survival': values [sample], :200-210) as NetCDF-3."""
+  values = np.asarray(values, dtype=np.float64)
+  if values.ndim == 2:
+    stop_times = np.arange(values.shape[0]) if stop_times is None else stop_times
+    samples = np.arange(values.shape[1]) if samples is None else samples
+    _to_netcdf3(path, {'time_max': values.shape[0], 'sample': values.shape[1]},
+                {name: (('time_max', 'sample'), values), 'time_max': (('time_max',), np.asarray(stop_times, np.float64)),
+                 'sample': (('sample',), np.asarray(samples))})
+  elif values.ndim == 1:
+    samples = np.arange(values.shape[0]) if samples is None else samples
+    _to_netcdf3(path, {'sample': values.shape[0]},
+                {name: (('sample',), values), 'sample': (('sample',), np.asarray(samples))})
+  else:
+    raise ValueError('metric must be [time_max, sample] or [sample]')
 
 
 # -------------------------------------------------------------------------------------

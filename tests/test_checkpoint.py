@@ -170,6 +170,39 @@ def test_num_layers_zero_checkpoint(tmp_path):
   got = C.load_conv_weights(str(tmp_path))
   assert len(got) == 1
   np.testing.assert_array_equal(got[0], coef)
+  # load -> save -> load is the identity for the single-vector model too
+  C.save_conv_weights(str(tmp_path / 'again'), got)
+  np.testing.assert_array_equal(C.load_conv_weights(str(tmp_path / 'again'))[0], coef)
+
+
+def test_direct_model_targets_have_unscoped_variables(tmp_path):
+  """model_target in {'space_derivatives', 'time_derivative', 'flux'} builds its conv stack without a variable
+  scope (model.py:551-568: only predict_coefficients opens one, model.py:442): `conv1d/kernel`, `conv1d_1/kernel`."""
+  rs = np.random.RandomState(0)
+  weights = [(rs.randn(5, 1, 8).astype(np.float32), rs.randn(8).astype(np.float32)),
+             (rs.randn(5, 8, 1).astype(np.float32), rs.randn(1).astype(np.float32))]
+  C.save_conv_weights(str(tmp_path / 'flux'), weights, model_target='flux')
+  names = sorted(C.read_checkpoint(str(tmp_path / 'flux' / 'model.ckpt')))
+  assert names == ['conv1d/bias', 'conv1d/kernel', 'conv1d_1/bias', 'conv1d_1/kernel']
+  got = C.load_conv_weights(str(tmp_path / 'flux'))
+  for (k, b), (k2, b2) in zip(weights, got):
+    np.testing.assert_array_equal(k, k2)
+    np.testing.assert_array_equal(b, b2)
+  # with optimiser slots and a global step next to them, as MonitoredTrainingSession saves
+  tensors = {'conv1d/kernel': weights[0][0], 'conv1d/bias': weights[0][1], 'conv1d_1/kernel': weights[1][0],
+             'conv1d_1/bias': weights[1][1], 'conv1d/kernel/Adam': weights[0][0] * 0, 'conv1d/kernel/Adam_1': weights[0][0] * 0,
+             'beta1_power': np.float32(0.9), 'global_step': np.int64(20)}
+  C.write_checkpoint(str(tmp_path / 'model.ckpt'), tensors)
+  got = C.load_conv_weights(str(tmp_path))
+  assert len(got) == 2
+  np.testing.assert_array_equal(got[1][0], weights[1][0])
+  # a scoped stack wins over stray unscoped names
+  tensors['predict_coefficients/conv1d/kernel'] = weights[0][0] + 1
+  tensors['predict_coefficients/conv1d/bias'] = weights[0][1] + 1
+  C.write_checkpoint(str(tmp_path / 'model.ckpt'), tensors)
+  got = C.load_conv_weights(str(tmp_path))
+  assert len(got) == 1
+  np.testing.assert_array_equal(got[0][0], weights[0][0] + 1)
 
 
 HPARAMS_TEXT = '''

@@ -74,3 +74,51 @@ def test_single_process_is_identity():
   x = torch.arange(24.).reshape(2, 3, 4)
   assert distributed.gather_snapshots(x, 3) is x
   assert distributed.max_over_ranks(3.5) == 3.5
+
+
+def _eval_worker(rank, world, port, total, queue):
+  """run_integrate_batch(distributed=True) plumbing with a stand-in for the CUDA integration of one block."""
+  import torch.distributed as dist
+  from ddd1d_b200 import evaluation
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                    WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+  distributed.init_from_env(backend='gloo')
+  times = np.array([0.0, 0.5, 1.0])
+  y0 = np.arange(total * 4, dtype=np.float64).reshape(total, 4)
+
+  def local_runner(block, seed0):          # "integrates" sample s: y(t) = y0 * (1 + t) + seed
+    seeds = seed0 + np.arange(block.shape[0])
+    y = block[:, None, :] * (1.0 + times)[None, :, None] + seeds[:, None, None]
+    return {'y': y, 'num_evals': 100 + seeds, 'x': np.arange(4) * 0.25}
+
+  class HP(object):                        # only reached when a rank holds no sample
+    pass
+  res = evaluation._run_sharded(None, HP(), y0, times, 2.0, 'RK23', None, 7, None, local_runner=local_runner)
+  queue.put((rank, res))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('total', (5, 8))
+def test_sharded_evaluation_two_ranks(total):
+  """Every rank integrates its block of seeds and receives all samples: equal to the unsharded result."""
+  import torch.multiprocessing as mp
+  ctx = mp.get_context('spawn')
+  queue = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, total, queue)) for r in range(2)]
+  for p in procs:
+    p.start()
+  results = [queue.get(timeout=120) for _ in procs]
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  times = np.array([0.0, 0.5, 1.0])
+  y0 = np.arange(total * 4, dtype=np.float64).reshape(total, 4)
+  seeds = 7 + np.arange(total)
+  want = y0[:, None, :] * (1.0 + times)[None, :, None] + seeds[:, None, None]
+  for rank, res in results:
+    np.testing.assert_array_equal(res['y'], want)
+    np.testing.assert_array_equal(res['num_evals'], 100 + seeds)
+    np.testing.assert_array_equal(res['sample'], seeds)
+    np.testing.assert_array_equal(res['time'], 2.0 + times)

@@ -64,13 +64,43 @@ def test_mostly_good_survival_matches_numpy():
   np.testing.assert_array_equal(got, np.where(good.all(1), t.max(), t[np.argmin(good, axis=1)]))
 
 
-def test_results_round_trip(tmp_path):
+@pytest.mark.parametrize('name', ('results.nc', 'results.npz'))
+def test_results_round_trip(tmp_path, name):
   res = {'y': np.random.RandomState(2).randn(2, 3, 8), 'time': np.array([10.0, 10.5, 11.0]),
          'x': np.arange(8) * 0.1, 'num_evals': np.array([100, 103]), 'sample': np.array([0, 1])}
-  path = str(tmp_path / 'results.npz')
+  res['y'][1, 2:] = np.nan                               # a diverged sample is NaN padded (integrate.py:161-167)
+  path = str(tmp_path / name)
   E.write_results(path, res)
   back = E.read_results(path)
   for k in res:
     np.testing.assert_array_equal(back[k], res[k])
   with pytest.raises(ValueError):
     E.write_results(path, dict(res, y=res['y'][0]))
+
+
+def test_results_nc_is_netcdf3_with_the_reference_schema(tmp_path):
+  """scripts/run_evaluation.py:168-174: {y: (sample, time, x)}, coords time, x, sample, num_evals(sample), as the
+  NetCDF-3 bytes Dataset.to_netcdf() yields (xarray_beam.py:32-35); read back with SciPy's own reader."""
+  from scipy.io import netcdf_file
+  res = {'y': np.random.RandomState(3).randn(4, 5, 16), 'time': np.linspace(0, 1, 5), 'x': np.arange(16) * 0.5,
+         'num_evals': np.array([31, 32, 33, 34]), 'sample': np.arange(4) + 10}
+  path = str(tmp_path / 'results.nc')
+  E.write_results(path, res)
+  with open(path, 'rb') as f:
+    assert f.read(3) == b'CDF'                            # the classic format, not HDF5
+  with netcdf_file(path, 'r', mmap=False) as f:
+    assert {k: v for k, v in f.dimensions.items()} == {'sample': 4, 'time': 5, 'x': 16}
+    assert f.variables['y'].dimensions == ('sample', 'time', 'x')
+    assert f.variables['num_evals'].dimensions == ('sample',)
+    assert f.variables['y'].coordinates == b'num_evals'
+    np.testing.assert_array_equal(f.variables['y'][...], res['y'])
+    np.testing.assert_array_equal(f.variables['sample'][...], res['sample'])
+  mae = np.abs(np.random.RandomState(4).randn(3, 4))
+  E.write_metric(str(tmp_path / 'mae.nc'), 'mae', mae, stop_times=[5, 10, 15], samples=res['sample'])
+  E.write_metric(str(tmp_path / 'survival.nc'), 'survival', mae[0], samples=res['sample'])
+  with netcdf_file(str(tmp_path / 'mae.nc'), 'r', mmap=False) as f:
+    assert f.variables['mae'].dimensions == ('time_max', 'sample')
+    np.testing.assert_array_equal(f.variables['mae'][...], mae)
+    np.testing.assert_array_equal(f.variables['time_max'][...], [5, 10, 15])
+  with netcdf_file(str(tmp_path / 'survival.nc'), 'r', mmap=False) as f:
+    np.testing.assert_array_equal(f.variables['survival'][...], mae[0])
