@@ -18,6 +18,7 @@ PROJ_NULLSPACE, PROJ_RAW, PROJ_RAW_UNBIASED = 0, 1, 2
 PROJ_DERIVATIVES, PROJ_TIME_DERIVATIVE, PROJ_FLUX = 3, 4, 5
 SCHEMES = {'rk3': 0, 'RK23': 0, 'bogacki_shampine': 0, 'midpoint': 1, 'euler': 2, 'rk4': 3}
 REAL_F32, REAL_F64 = 0, 1
+STATE_F32 = 0x100     # OR into a scheme: float32 carry between steps (model.integrate_ode semantics)
 ENGINES = {'auto': 0, 'ffma': 1, 'tensor': 2, 'tensor_f16x2': 3, 'tensor_f16': 4}
 ENGINE_NAMES = {v: k for k, v in ENGINES.items() if v}
 WINDOW = 11         # DDD1D_WINDOW: offsets -5..+5

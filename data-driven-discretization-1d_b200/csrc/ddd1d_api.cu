@@ -884,8 +884,11 @@ int ddd1d_integrate(ddd1d_handle* h, double t0, double dt, int num_steps, int sa
   if (num_steps < 0 || save_every < 1) return fail(h, DDD1D_EINVAL, "bad step counts");
   if (batch == 0) return DDD1D_OK;
   if (!u0 || (!snapshots && num_steps / save_every > 0)) return fail(h, DDD1D_EINVAL, "null argument");
+  const int state_f32 = (scheme & DDD1D_STATE_F32) != 0;
+  scheme &= ~DDD1D_STATE_F32;
   if (scheme < 0 || scheme > DDD1D_RK4) return fail(h, DDD1D_EINVAL, "unknown scheme %d", scheme);
   Work W = blank_work();
+  W.state_f32 = state_f32;
   W.op = OP_INTEGRATE; W.batch = batch; W.sample_offset = sample_offset; W.u = u0; W.snaps = snapshots;
   W.first_bad = first_bad_step; W.t0 = t0; W.dt = dt; W.nsteps = num_steps; W.save_every = save_every;
   W.scheme = scheme;

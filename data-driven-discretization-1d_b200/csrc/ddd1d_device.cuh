@@ -78,6 +78,7 @@ struct Work {
   double* out64;
   double t0, dt;
   int nsteps, save_every, scheme;
+  int state_f32;       // carry the solution in float32 between steps (tf odeint_fixed, model.py:138-159) instead of float64 (SciPy)
   float* snaps;        // [nsteps/save_every][batch][N]
   int* first_bad;      // [batch] or null
   // OP_ADAPTIVE (scipy RK23 twin): output times, tolerances, float64 record
@@ -1063,6 +1064,7 @@ __global__ void __launch_bounds__(MODE == MODE_LEARNED ? 512 : 1024, 1)
         for (int j = 0; j < kMaxStages; ++j)
           if (j < tab.stages && tab.b[j] != 0.0) acc += tab.b[j] * (double)K[j * N + p];
         double yn = S.ydbl[p] + W.dt * acc;
+        if (W.state_f32) yn = (double)(float)yn;
         S.ydbl[p] = yn;
         if (first_bad < 0 && !isfinite(yn)) first_bad = step;
         if (save) snap[p] = (float)yn;

@@ -636,7 +636,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         if (nstages > 1) accd = fma(tab.b[1], (double)S.k1, accd);
         if (nstages > 2) accd = fma(tab.b[2], (double)S.k2, accd);
         if (nstages > 3) accd = fma(tab.b[3], (double)S.k3, accd);
-        const double y = S.y + W.dt * accd;
+        double y = S.y + W.dt * accd;
+        if (W.state_f32) y = (double)(float)y;        // float32 carry (tf odeint_fixed, model.py:138-159)
         S.y = y;
         if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
           atomicMin(reinterpret_cast<unsigned int*>(sc + G::SC_BAD) + rr, (unsigned int)fstep);

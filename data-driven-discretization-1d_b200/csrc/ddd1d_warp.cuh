@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
 #pragma unroll
         for (int j = 0; j < kMaxStages; ++j)
           if (j < tab.stages && tab.b[j] != 0.0) acc += tab.b[j] * (double)k[j][i];
-        const double yn = y[i] + W.dt * acc;
+        double yn = y[i] + W.dt * acc;
+        if (W.state_f32) yn = (double)(float)yn;     // float32 carry (tf odeint_fixed, model.py:138-159)
         y[i] = yn;
         if (!bad_seen && !isfinite(yn)) { bad_seen = true; first_bad = step; }
         if (save) snap[i] = (float)yn;

@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
         if (tab.stages > 1) acc = fma(tab.b[1], (double)k1[i], acc);
         if (tab.stages > 2) acc = fma(tab.b[2], (double)k2[i], acc);
         if (tab.stages > 3) acc = fma(tab.b[3], (double)k3[i], acc);
-        const double yn = y[i] + W.dt * acc;
+        double yn = y[i] + W.dt * acc;
+        if (W.state_f32) yn = (double)(float)yn;     // float32 carry (tf odeint_fixed, model.py:138-159)
         y[i] = yn;
         if (first_bad < 0 && !isfinite(yn)) first_bad = step;
         out[i] = (float)yn;

@@ -201,7 +201,8 @@ def predict_time_evolution(inputs, hparams, weights=None):
   rule (model.py:643-661), all steps in one persistent kernel launch."""
   equation, solver = _learned(hparams, weights)
   assert_consistent_solution(equation, inputs)
-  snaps = solver.integrate(inputs, 0.0, equation.time_step, hparams.num_time_steps, 1, 'midpoint')
+  # float32 carry between steps, as tf.contrib.integrate.odeint_fixed on the float32 graph (model.py:156-157)
+  snaps = solver.integrate(inputs, 0.0, equation.time_step, hparams.num_time_steps, 1, 'midpoint', float32_state=True)
   return snaps.permute(1, 2, 0)
 
 
@@ -253,7 +254,7 @@ def baseline_time_evolution(inputs, num_time_steps, equation):
   grid = equation.grid
   tag = (type(equation).__name__, grid.solution_num_points, grid.period, getattr(equation, 'eta', None))
   solver = _cached(('fd', 1) + tag, lambda: runtime.stencil_solver(equation, 1, forcing=False))
-  snaps = solver.integrate(inputs, 0.0, equation.time_step, num_time_steps, 1, 'midpoint')
+  snaps = solver.integrate(inputs, 0.0, equation.time_step, num_time_steps, 1, 'midpoint', float32_state=True)
   return snaps.permute(1, 2, 0)
 
 

@@ -283,8 +283,10 @@ class RowSolver(object):
     return out
 
   def integrate(self, u0, t0, dt, num_steps, save_every=1, scheme='rk3', sample_offset=0,
-                return_first_bad=False):
-    """Fused fixed-step integration; returns snapshots [num_steps // save_every, batch, N]."""
+                return_first_bad=False, float32_state=False):
+    """Fused fixed-step integration; returns snapshots [num_steps // save_every, batch, N].
+    float32_state=True rounds the carried solution to float32 after every step (the reference's TF-graph
+    unroll, model.py:138-159); the default carries it in float64 like SciPy (integrate.py:154)."""
     torch = _torch()
     rows = self._rows(u0)
     self._offset_ok(rows.shape[0], sample_offset)
@@ -292,7 +294,8 @@ class RowSolver(object):
     snaps = torch.empty((nsave,) + tuple(rows.shape), device=self.device, dtype=torch.float32)
     bad = torch.empty(rows.shape[0], device=self.device, dtype=torch.int32)
     self._check(self._lib.ddd1d_integrate(
-        self._handle, float(t0), float(dt), int(num_steps), int(save_every), _lib.SCHEMES[scheme],
+        self._handle, float(t0), float(dt), int(num_steps), int(save_every),
+        _lib.SCHEMES[scheme] | (_lib.STATE_F32 if float32_state else 0),
         rows.data_ptr(), snaps.data_ptr(), bad.data_ptr(), rows.shape[0], sample_offset, self._stream()))
     return (snaps, bad) if return_first_bad else snaps
 

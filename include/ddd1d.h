@@ -84,6 +84,10 @@ enum {
   DDD1D_EULER = 2,
   DDD1D_RK4 = 3
 };
+/* OR into `scheme`: round the carried solution to float32 after every step, as the reference's TF-graph unroll
+ * does (tf.contrib.integrate.odeint_fixed on a float32 tensor, model.py:138-159).  Without it the state is
+ * carried in float64 between steps, as SciPy carries it (integrate.py:154; the RHS is float32 either way). */
+#define DDD1D_STATE_F32 0x100
 
 /* conv-stack engine (learned mode).  AUTO picks the tcgen05 kernel in its FP32-faithful form (TENSOR) when
  * the net is the shape it is built for (kernel_size 5, filter_size 32, relu, 2 or 3 layers, N in

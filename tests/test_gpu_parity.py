@@ -454,6 +454,26 @@ def test_weno_block_kernel(monkeypatch, n):
     np.testing.assert_array_equal(np.isfinite(a), np.isfinite(b))
 
 
+def test_float32_state_carry():
+  """model.integrate_ode (model.py:138-159) unrolls the midpoint rule on a float32 tensor: the solution is rounded
+  to float32 after every step.  DDD1D_STATE_F32 reproduces that carry (predict_time_evolution /
+  baseline_time_evolution use it); the default float64 carry is SciPy's (integrate.py:154).  Over 400 steps the two
+  differ measurably, and each matches the oracle run with the same state dtype."""
+  from ddd1d_b200 import integrate
+  n, steps = 64, 400
+  eqs = [G.product_equation('burgers', 'plain', n, seed=s) for s in range(3)]
+  oeqs = [G.oracle_equation('burgers', 'plain', n, seed=s) for s in range(3)]
+  u0 = G.smooth_rows(3, n, seed=2)
+  rhs = O.batched_rhs(oeqs, mode='fd', accuracy_order=1)
+  for engine_solver in (integrate.BatchIntegrator.baseline(eqs, 1),):
+    got32 = cpu(engine_solver.solver.integrate(u0, 0.0, 1e-3, steps, steps, 'midpoint', float32_state=True))
+    got64 = cpu(engine_solver.solver.integrate(u0, 0.0, 1e-3, steps, steps, 'midpoint'))
+    want32 = O.fixed_step_integrate(rhs, u0, 0.0, 1e-3, steps, steps, scheme='midpoint', state_dtype=np.float32)
+    want64 = O.fixed_step_integrate(rhs, u0, 0.0, 1e-3, steps, steps, scheme='midpoint')
+    assert rel_err(got32, want32) < 2e-5 and rel_err(got64, want64) < 2e-5
+    assert rel_err(got32, got64) > 0                      # the carry matters (and is not silently ignored)
+
+
 # ---------------------------------------------------------------------------------
 # edge cases and error behaviour
 # ---------------------------------------------------------------------------------
