@@ -573,7 +573,14 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
   CUDA_TRY(h, cudaSetDevice(c.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_tc(h) && W.op != OP_ADAPTIVE) {
-    h->tc_entry.launch(h->Ptc, W, make_tableau(W.scheme), tc_grid(h, W.batch), st);
+    const Tableau tab = make_tableau(W.scheme);
+    for (int s = 0; s < kMaxStages; ++s) {
+      for (int j = 0; j < kMaxStages; ++j) W.adt[s][j] = (float)(W.dt * tab.a[s][j]);
+      const double b = W.dt * tab.b[s];
+      W.bdt_hi[s] = (float)b;
+      W.bdt_lo[s] = (float)(b - (double)W.bdt_hi[s]);
+    }
+    h->tc_entry.launch(h->Ptc, W, tab, tc_grid(h, W.batch), st);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;

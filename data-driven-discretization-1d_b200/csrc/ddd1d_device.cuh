@@ -78,6 +78,10 @@ struct Work {
   double* out64;
   double t0, dt;
   int nsteps, save_every, scheme;
+  // dt * tableau as float32 / float-float constants, filled by the host per launch (the tensor engine carries its
+  // float64-equivalent state as an unevaluated float pair: conversions to and from float64 run at 16 lanes/clk/SM)
+  float adt[kMaxStages][kMaxStages];     // float(dt * a[s][j])
+  float bdt_hi[kMaxStages], bdt_lo[kMaxStages];     // dt * b[j] = hi + lo
   int state_f32;       // carry the solution in float32 between steps (tf odeint_fixed, model.py:138-159) instead of float64 (SciPy)
   float* snaps;        // [nsteps/save_every][batch][N]
   int* first_bad;      // [batch] or null

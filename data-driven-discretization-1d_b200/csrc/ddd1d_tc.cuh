@@ -389,8 +389,18 @@ __device__ __forceinline__ void tmem_read(uint32_t taddr, float (&v)[NB]) {
 }
 
 // per-thread state of one slot that outlives a phase; slots are unrolled, so this lives in registers
+// a + b = s + e exactly (Knuth's TwoSum)
+__device__ __forceinline__ void two_sum(float a, float b, float& s, float& e) {
+  s = a + b;
+  const float bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+
 struct SlotState {
-  double y;
+  // The solution, float64-equivalent (integrate.py:154: SciPy carries y in float64), as an unevaluated sum of two
+  // floats yh + yl with yh = float(yh + yl): ~48 significant bits and no float64 instruction in the loop
+  // (conversions to / from float64 run at 16 lanes per clock per SM).
+  float yh, yl;
   float k0, k1, k2, k3;
   float umax;        // verified bound on the slot's max |u / sigma|; < 0: not calibrated yet
   float bound1;      // bound on the first layer's activations
@@ -532,7 +542,16 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         if (sl >= nslots) continue;
         const int row = (unit0 + sl * total_teams) * RPT + rr;
         const bool live = row < W.batch;
-        st[sl].y = !live ? 0.0 : W.u64 ? W.u64[(size_t)row * N + x] : (double)__ldg(W.u + (size_t)row * N + x);
+        if (!live) {
+          st[sl].yh = st[sl].yl = 0.f;
+        } else if (W.u64) {
+          const double v = W.u64[(size_t)row * N + x];
+          st[sl].yh = (float)v;
+          st[sl].yl = (float)(v - (double)st[sl].yh);
+        } else {
+          st[sl].yh = __ldg(W.u + (size_t)row * N + x);
+          st[sl].yl = 0.f;
+        }
         st[sl].k0 = st[sl].k1 = st[sl].k2 = st[sl].k3 = 0.f;
         st[sl].umax = -1.f;                              // no bound yet: the first stage calibrates
         st[sl].bound1 = 0.f;
@@ -632,28 +651,42 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         set_k(S, fs, r);
         if (fs != nstages - 1) return;
         // ---- the step is complete: y += dt * sum b k ----
-        double accd = tab.b[0] * (double)S.k0;
-        if (nstages > 1) accd = fma(tab.b[1], (double)S.k1, accd);
-        if (nstages > 2) accd = fma(tab.b[2], (double)S.k2, accd);
-        if (nstages > 3) accd = fma(tab.b[3], (double)S.k3, accd);
-        double y = S.y + W.dt * accd;
-        if (W.state_f32) y = (double)(float)y;        // float32 carry (tf odeint_fixed, model.py:138-159)
-        S.y = y;
+        // increment dt * b_j * k_j as a float pair: exact products (FMA residual) of the float-float constants,
+        // highs summed with TwoSum -- the float64 sum of the reference to ~2^-48
+        float ih = 0.f, il = 0.f;
+        const float kk[kMaxStages] = {S.k0, S.k1, S.k2, S.k3};
+#pragma unroll
+        for (int j = 0; j < kMaxStages; ++j) {
+          if (j >= nstages) break;
+          const float ph = W.bdt_hi[j] * kk[j];
+          const float pl = fmaf(W.bdt_hi[j], kk[j], -ph) + W.bdt_lo[j] * kk[j];
+          float sh, e;
+          two_sum(ih, ph, sh, e);
+          ih = sh;
+          il += e + pl;
+        }
+        float yh, e;
+        two_sum(S.yh, ih, yh, e);
+        const float yl = S.yl + (e + il);
+        const float y = yh + yl;                       // renormalise: y = float(yh + yl)
+        S.yl = W.state_f32 ? 0.f : yl - (y - yh);      // (float32 carry: tf odeint_fixed, model.py:138-159)
+        S.yh = y;
         if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
           atomicMin(reinterpret_cast<unsigned int*>(sc + G::SC_BAD) + rr, (unsigned int)fstep);
         if (((fstep + 1) % W.save_every) == 0 && live)
-          W.snaps[((size_t)((fstep + 1) / W.save_every - 1) * W.batch + row) * N + x] = (float)y;
+          W.snaps[((size_t)((fstep + 1) / W.save_every - 1) * W.batch + row) * N + x] = y;
       };
 
       // ---- phase 0 of right-hand side (step, s): stage value, exchange, first layer, planes, request ----
-      auto start = [&](auto slc, int step, int s, double a0, double a1, double a2) {
+      auto start = [&](auto slc, int step, int s, float a0, float a1, float a2) {
         constexpr int sl = decltype(slc)::value;
         SlotState& S = st[sl];
         float* const sc = sc0 + sl * G::SC_STRIDE;
         float* const rowbuf = sc + G::SC_ROWS + (stage_par * 2u * RPT + rr) * G::ROWBUF;   // raw; normalised at + RPT * ROWBUF
-        // stage value, rounded to float32 (integrate.py:57-60,71); a_j = 0 beyond the stage
-        const double accd = fma(a2, (double)S.k2, fma(a1, (double)S.k1, a0 * (double)S.k0));
-        const float us = (float)(s == 0 ? S.y : S.y + W.dt * accd);
+        // stage value y + dt * sum a_j k_j rounded to float32 (integrate.py:57-60,71): the increment in float32
+        // (its rounding is 1e-7 of an increment that is itself far below half an ulp of y), added low part first
+        const float inc = fmaf(a2, S.k2, fmaf(a1, S.k1, a0 * S.k0));      // a_j = float(dt * a[s][j]), 0 beyond the stage
+        const float us = s == 0 ? S.yh : S.yh + (S.yl + inc);
         const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
         rowbuf[x + kHalo] = us;
         rowbuf[RPT * G::ROWBUF + x + kHalo] = usn;
@@ -763,7 +796,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       for (int step = 0; step < nsteps; ++step) {
         for (int s = 0; s < nstages; ++s) {
           // this stage's row of the tableau, fetched once for both slots
-          const double a0 = s > 0 ? tab.a[s][0] : 0.0, a1 = s > 1 ? tab.a[s][1] : 0.0, a2 = s > 2 ? tab.a[s][2] : 0.0;
+          const float a0 = s > 0 ? W.adt[s][0] : 0.f, a1 = s > 1 ? W.adt[s][1] : 0.f, a2 = s > 2 ? W.adt[s][2] : 0.f;
           if (have_prev) finish(std::integral_constant<int, 0>{}, prev_step, prev_s, stage_par ^ 1u);
           start(std::integral_constant<int, 0>{}, step, s, a0, a1, a2);
           if (nslots > 1) {
