@@ -58,6 +58,8 @@ def gather_snapshots(local, total_samples, sample_axis=1, group=None):
     x = torch.cat([x, pad], dim=0)
   out = torch.empty((world * largest,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
   dist.all_gather_into_tensor(out, x, group=group)
+  if min(counts) == largest:                    # even shards: the gathered buffer is the result, no second copy
+    return out.movedim(0, sample_axis)
   pieces = [out[r * largest:r * largest + counts[r]] for r in range(world)]
   return torch.cat(pieces, dim=0).movedim(0, sample_axis)
 

@@ -1,22 +1,24 @@
 #!/bin/bash
-# Evidence pass for the current tensor engine: parity tests -> smoke -> bench -> launch list -> ncu full -> reference arm.
-cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
-nproc > gpurun_out/nproc.txt
-timeout -k 10 1200 python -m pytest tests -m gpu -q --timeout 400 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-timeout -k 5 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-echo "smoke exit $?" >> gpurun_out/smoke.log
-timeout -k 10 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-echo "bench exit $?" >> gpurun_out/bench_n1.err
-timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
-    --log-file gpurun_out/launches_c2_tensor.csv python bench.py --steps 3 --warmup 3 --no-cpu \
-    > gpurun_out/ncu_launches.log 2>&1
-timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:tc_row_kernel -s 3 -c 1 \
-    -f -o gpurun_out/prof_tc_f16 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
-for w in c3 c4; do
-  timeout -k 10 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
-done
-timeout -k 10 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-echo done
+# Round evidence on one B200: the driver's bench command, the reference arm, the ncu launch list of the same command
+# and one `ncu --set full` capture per top kernel.  Usage: gpurun -- bash scripts/gpu_evidence.sh <tag>
+tag=${1:-evidence}
+out=gpurun_out/$tag
+mkdir -p $out
+python bench.py --gpus 1 --steps 20 --warmup 5 > $out/bench_n1.json 2> $out/bench_n1.err
+python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err
+python bench.py --engine tensor_f16x2 --steps 20 --warmup 5 --no-cpu --extra '' > $out/bench_n1_f16x2.json 2> $out/bench_n1_f16x2.err
+python bench.py --engine ffma --steps 4 --warmup 3 --rk-steps 100 --no-cpu --extra '' > $out/bench_n1_ffma.json 2> $out/bench_n1_ffma.err
+# every launch of the bench command with its device time (cold-cache, serialised: compare shares)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/launches_c2.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu --extra '' > $out/launches_c2.log 2>&1
+prof() {   # name, kernel regex, bench args...
+  name=$1; regex=$2; shift 2
+  ncu --set full --clock-control none --import-source on -k regex:$regex -s 3 -c 1 -o $out/prof_$name \
+      python bench.py --steps 2 --warmup 3 --no-cpu --extra '' "$@" > $out/prof_$name.log 2>&1
+}
+prof tc_c2 tc_row_kernel --workload c2 --rk-steps 20
+prof tc_c3 tc_row_kernel --workload c3 --rk-steps 20
+prof tc_c2s tc_row_kernel --workload c2s --rk-steps 20
+prof weno_c5 weno_block_kernel --workload c5 --rk-steps 5
+prof warp_c1b warp_row_kernel --workload c1b --rk-steps 20
+ls -la $out
