@@ -423,6 +423,12 @@ static __device__ __noinline__ void export_coefficients(const TcParams& P, const
   }
 }
 
+// OP_DERIV export (per-call parity hook): out of line, the integration loop has to stay small
+static __device__ __noinline__ void export_derivatives(const TcParams& P, const Work& W, const float (&dv)[kMaxD],
+                                                       size_t point) {
+  for (int d = 0; d < P.D; ++d) W.out[point * P.D + d] = dv[d];
+}
+
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
@@ -478,14 +484,14 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       const int nslots = unit0 + total_teams < units ? 2 : 1;
       for (int it = 0; it < nsteps * nstages; ++it) {
         for (int layer = 0; layer <= nhid; ++layer) {
-#pragma unroll
-          for (int q = 0; q < G::SPI; ++q) {
+#pragma unroll 1
+          for (int q = 0; q < G::SPI; ++q) {              // rolled: one copy of the issue code per layer kind
             const int ts = ts0 + q;
             if ((ts & 1) >= nslots) continue;
             if (!(P.debug & 64)) mbar_wait_guarded(&bars[1 + ts], parity);
             fence_after();
             const uint32_t slot16 = (smem_s + G::OFF_SLOTS + (uint32_t)ts * G::SLOT_BYTES) >> 4;
-#pragma unroll
+#pragma unroll 1
             for (int m = 0; m < TILES; ++m) {
               const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
               const uint32_t d = tmem_u + (uint32_t)((ts * TILES + m) * G::COLS);
@@ -531,34 +537,37 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((ts_a * TILES + tile) * G::COLS);
     const float* const fbasis_x = P.fbasis + x;         // this point's column of the forcing basis (L1 resident)
 
-    SlotState st[2];
+    // The two slots of the team share ONE copy of the phase code (the steady-state loop has to stay inside the
+    // instruction cache: two unrolled copies were 80 KB): `cur` is the slot whose turn it is, `oth` the other
+    // one, and they change places after every turn (eight register moves).
+    SlotState cur, oth;
     const int g = blockIdx.x * R + team;
 
     for (int unit0 = g; unit0 < units; unit0 += 2 * total_teams) {
       const int nslots = unit0 + total_teams < units ? 2 : 1;
       // ---- load the rows ----
-#pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        if (sl >= nslots) continue;
+      auto load_slot = [&](int sl, SlotState& S) {
         const int row = (unit0 + sl * total_teams) * RPT + rr;
         const bool live = row < W.batch;
         if (!live) {
-          st[sl].yh = st[sl].yl = 0.f;
+          S.yh = S.yl = 0.f;
         } else if (W.u64) {
           const double v = W.u64[(size_t)row * N + x];
-          st[sl].yh = (float)v;
-          st[sl].yl = (float)(v - (double)st[sl].yh);
+          S.yh = (float)v;
+          S.yl = (float)(v - (double)S.yh);
         } else {
-          st[sl].yh = __ldg(W.u + (size_t)row * N + x);
-          st[sl].yl = 0.f;
+          S.yh = __ldg(W.u + (size_t)row * N + x);
+          S.yl = 0.f;
         }
-        st[sl].k0 = st[sl].k1 = st[sl].k2 = st[sl].k3 = 0.f;
-        st[sl].umax = -1.f;                              // no bound yet: the first stage calibrates
-        st[sl].bound1 = 0.f;
+        S.k0 = S.k1 = S.k2 = S.k3 = 0.f;
+        S.umax = -1.f;                                   // no bound yet: the first stage calibrates
+        S.bound1 = 0.f;
         float* sc = sc0 + sl * G::SC_STRIDE;
         if (p < RPT) reinterpret_cast<unsigned int*>(sc + G::SC_BAD)[p] = 0xffffffffu;
         if (p == 0) *reinterpret_cast<unsigned int*>(sc + G::SC_UMAX) = 0u;
-      }
+      };
+      load_slot(0, cur);
+      if (nslots > 1) load_slot(1, oth);
       team_sync(team, TEAM);
 
       // A right-hand side is "started" (phase 0) and "finished" (phase 2) in different turns: a slot's turn is
@@ -569,9 +578,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       int prev_step = 0, prev_s = 0;
 
       // ---- phase 2 (+ the Runge-Kutta update after the last stage) of right-hand side (fstep, fs) ----
-      auto finish = [&](auto slc, int fstep, int fs, uint32_t fpar) {
-        constexpr int sl = decltype(slc)::value;
-        SlotState& S = st[sl];
+      auto finish = [&](int sl, SlotState& S, int fstep, int fs, uint32_t fpar) {
         float* const sc = sc0 + sl * G::SC_STRIDE;
         const float* const rowbuf = sc + G::SC_ROWS + (fpar * 2u * RPT + rr) * G::ROWBUF;
         const int row = (unit0 + sl * total_teams) * RPT + rr;
@@ -595,6 +602,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             f = fmaf(a.z, c[2], f); f = fmaf(b.z, d[2], f);
             f = fmaf(a.w, c[3], f); f = fmaf(b.w, d[3], f);
           } else {
+#pragma unroll 1
             for (int m = 0; m < P.M; ++m) {
               f = fmaf(amp[m], __ldg(fbasis_x + (size_t)m * N), f);
               f = fmaf(amp[kMaxModes + m], __ldg(fbasis_x + (size_t)(P.M + m) * N), f);
@@ -628,8 +636,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
         fence_before();
         if (!fast_op) {
-          if (W.op == OP_DERIV && live)
-            for (int d = 0; d < P.D; ++d) W.out[((size_t)row * N + x) * P.D + d] = dv[d];
+          if (W.op == OP_DERIV && live) export_derivatives(P, W, dv, (size_t)row * N + x);
           return;
         }
         float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
@@ -678,9 +685,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       };
 
       // ---- phase 0 of right-hand side (step, s): stage value, exchange, first layer, planes, request ----
-      auto start = [&](auto slc, int step, int s, float a0, float a1, float a2) {
-        constexpr int sl = decltype(slc)::value;
-        SlotState& S = st[sl];
+      auto start = [&](int sl, SlotState& S, int step, int s, float a0, float a1, float a2) {
         float* const sc = sc0 + sl * G::SC_STRIDE;
         float* const rowbuf = sc + G::SC_ROWS + (stage_par * 2u * RPT + rr) * G::ROWBUF;   // raw; normalised at + RPT * ROWBUF
         // stage value y + dt * sum a_j k_j rounded to float32 (integrate.py:57-60,71): the increment in float32
@@ -759,9 +764,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       };
 
       // ---- phase 1: epilogue of a hidden tensor layer, planes rewritten in place, next layer requested ----
-      auto hidden = [&](auto slc) {
-        constexpr int sl = decltype(slc)::value;
-        SlotState& S = st[sl];
+      auto hidden = [&](int sl, SlotState& S) {
         const float bound1 = S.bound1;
         // accumulators carry (activation scale x filter scale); the next planes get their own scale
         const float inv = pow2_inverse(scale_for(bound1)) * P.inv_sw_hid;
@@ -793,20 +796,30 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         if (lane == 0) mbar_arrive(req0 + sl);
       };
 
+      auto change_places = [&]() {
+        if (nslots > 1) {
+          const SlotState t = cur;
+          cur = oth;
+          oth = t;
+        }
+      };
       for (int step = 0; step < nsteps; ++step) {
         for (int s = 0; s < nstages; ++s) {
           // this stage's row of the tableau, fetched once for both slots
           const float a0 = s > 0 ? W.adt[s][0] : 0.f, a1 = s > 1 ? W.adt[s][1] : 0.f, a2 = s > 2 ? W.adt[s][2] : 0.f;
-          if (have_prev) finish(std::integral_constant<int, 0>{}, prev_step, prev_s, stage_par ^ 1u);
-          start(std::integral_constant<int, 0>{}, step, s, a0, a1, a2);
-          if (nslots > 1) {
-            if (have_prev) finish(std::integral_constant<int, 1>{}, prev_step, prev_s, stage_par ^ 1u);
-            start(std::integral_constant<int, 1>{}, step, s, a0, a1, a2);
+#pragma unroll 1
+          for (int sl = 0; sl < nslots; ++sl) {
+            if (have_prev) finish(sl, cur, prev_step, prev_s, stage_par ^ 1u);
+            start(sl, cur, step, s, a0, a1, a2);
+            change_places();
           }
           if (have_prev) done_parity ^= 1u;
           for (int l = 0; l < nhid; ++l) {
-            hidden(std::integral_constant<int, 0>{});
-            if (nslots > 1) hidden(std::integral_constant<int, 1>{});
+#pragma unroll 1
+            for (int sl = 0; sl < nslots; ++sl) {
+              hidden(sl, cur);
+              change_places();
+            }
             done_parity ^= 1u;
           }
           have_prev = true;
@@ -815,8 +828,11 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           stage_par ^= 1u;
         }
       }
-      finish(std::integral_constant<int, 0>{}, prev_step, prev_s, stage_par ^ 1u);
-      if (nslots > 1) finish(std::integral_constant<int, 1>{}, prev_step, prev_s, stage_par ^ 1u);
+#pragma unroll 1
+      for (int sl = 0; sl < nslots; ++sl) {
+        finish(sl, cur, prev_step, prev_s, stage_par ^ 1u);
+        change_places();
+      }
       if (W.op == OP_INTEGRATE && W.first_bad) {
         team_sync(team, TEAM);
 #pragma unroll
