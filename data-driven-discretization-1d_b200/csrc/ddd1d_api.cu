@@ -44,6 +44,8 @@ struct ddd1d_handle {
   std::string error;
   bool dirty = true;
   bool have_stencils = false, have_projection = false;
+  const void* warp_kernel = nullptr;   // the warp_row_kernel instantiation last launched, and its resident CTAs per SM
+  int warp_occ = 0;
   std::vector<double> stencils;      // [D][7]
   std::vector<double> nullspace;     // [C][7]
   std::vector<int> input_sizes;      // [D]
@@ -572,7 +574,8 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
                 W.sample_offset + W.batch, P.fcap);
   CUDA_TRY(h, cudaSetDevice(c.device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (use_tc(h) && W.op != OP_ADAPTIVE) {
+  {
+    // dt * tableau as float32 / float-float constants (the float-pair state of the tensor and warp-row kernels)
     const Tableau tab = make_tableau(W.scheme);
     for (int s = 0; s < kMaxStages; ++s) {
       for (int j = 0; j < kMaxStages; ++j) W.adt[s][j] = (float)(W.dt * tab.a[s][j]);
@@ -580,7 +583,9 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
       W.bdt_hi[s] = (float)b;
       W.bdt_lo[s] = (float)(b - (double)W.bdt_hi[s]);
     }
-    h->tc_entry.launch(h->Ptc, W, tab, tc_grid(h, W.batch), st);
+  }
+  if (use_tc(h) && W.op != OP_ADAPTIVE) {
+    h->tc_entry.launch(h->Ptc, W, make_tableau(W.scheme), tc_grid(h, W.batch), st);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;
@@ -588,24 +593,41 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
   if (use_warp_rows(h, W.op)) {
     // one warp per row, everything in registers (ddd1d_warp.cuh): the fixed-step integrator of the
     // fixed-stencil / float32 WENO modes for rows of 32 * {1, 2, 4, 8} points
-    const int blocks = std::min((W.batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * 8);
     const Tableau tab = make_tableau(W.scheme);
     const bool weno = c.mode == DDD1D_MODE_WENO;
     const bool few = P.M <= 4;                 // forcing modes (the reference's k_max = 3)
-#define DDD1D_WARP_LAUNCH(PPL)                                                                        \
+    // how far the stencil table reaches from a point (WENO5 reads three points either side)
+    int halo = 1;
+    if (weno) halo = kHalo;
+    else
+      for (int d = 0; d < c.num_derivatives; ++d)
+        for (int j = 0; j < kWin; ++j)
+          if (h->stencils[(size_t)d * kWinHost + kCentre + j] != 0.0) halo = std::max(halo, std::abs(j - kHalo));
+    const void* kernel = nullptr;
+#define DDD1D_WARP_PICK(PPL)                                                                          \
   do {                                                                                                \
-    if (weno && few) warp_row_kernel<PPL, true, 4><<<blocks, 256, 0, st>>>(P, W, tab);              \
-    else if (weno) warp_row_kernel<PPL, true, kMaxModes><<<blocks, 256, 0, st>>>(P, W, tab);        \
-    else if (few) warp_row_kernel<PPL, false, 4><<<blocks, 256, 0, st>>>(P, W, tab);                \
-    else warp_row_kernel<PPL, false, kMaxModes><<<blocks, 256, 0, st>>>(P, W, tab);                 \
+    if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 4, 3> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3>;   \
+    else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 4, 1> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1>;   \
+    else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 4, 2> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2>;   \
+    else kernel = few ? (const void*)warp_row_kernel<PPL, false, 4, 3> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3>;   \
   } while (0)
     switch (c.num_points / 32) {
-      case 1: DDD1D_WARP_LAUNCH(1); break;
-      case 2: DDD1D_WARP_LAUNCH(2); break;
-      case 4: DDD1D_WARP_LAUNCH(4); break;
-      default: DDD1D_WARP_LAUNCH(8); break;
+      case 1: DDD1D_WARP_PICK(1); break;
+      case 2: DDD1D_WARP_PICK(2); break;
+      case 4: DDD1D_WARP_PICK(4); break;
+      default: DDD1D_WARP_PICK(8); break;
     }
-#undef DDD1D_WARP_LAUNCH
+#undef DDD1D_WARP_PICK
+    // persistent warps: exactly the CTAs that are resident at once, so that no CTA waits for a slot
+    if (h->warp_kernel != kernel) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * kWarpRowsPerBlock, 0) != cudaSuccess || occ < 1) occ = 1;
+      h->warp_kernel = kernel;
+      h->warp_occ = occ;
+    }
+    const int blocks = std::min((W.batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * h->warp_occ);
+    void* args[] = {(void*)&P, (void*)&W, (void*)&tab};
+    CUDA_TRY(h, cudaLaunchKernel(kernel, dim3(blocks), dim3(32 * kWarpRowsPerBlock), args, 0, st));
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;

@@ -3,15 +3,21 @@
 // The CTA-per-row kernel (row_kernel) needs five block barriers and a shared-memory round trip per
 // Runge-Kutta stage; for the short rows of the baseline configurations (N = 64 in BASELINE config 1 and its
 // batched twin) that is nearly all it does.  Here ONE WARP owns a row for the whole launch:
-//   * lane l holds the PPL = N / 32 consecutive points l*PPL .. l*PPL + PPL-1: float64 solution, float32
-//     stage derivatives and the stage row all live in registers;
-//   * the three halo points on either side come from the neighbouring lanes by shuffles (the row is periodic
-//     and exactly one warp wide, so lane -1 is lane 31);
-//   * forcing: lane q evaluates term q of the sample's RandomForcing (one sincosf per stage), the amplitude of
-//     every spatial mode is a warp sum (xor shuffles), and the spatial basis is read from L1;
+//   * lane l holds the PPL = N / 32 consecutive points l*PPL .. l*PPL + PPL-1: the float64-equivalent solution
+//     as an unevaluated float pair (no FP64 instruction and no float64 conversion in the loop: conversions
+//     run at 16 lanes per clock per SM), float32 stage derivatives and the stage row all live in registers;
+//   * the HALO (1..3) points the stencils actually reach on either side come from the neighbouring lanes by
+//     shuffles (the row is periodic and exactly one warp wide, so lane -1 is lane 31); the host picks HALO
+//     from the stencil table, so first-order rows do 3 taps and 2 shuffles instead of 7 and 6;
+//   * forcing: lane q owns term q of the sample's RandomForcing.  ONE sincosf per Runge-Kutta STEP; the later
+//     stages rotate it by the per-term constant angle w c_s dt (angle addition, 4 FMAs).  The amplitude of
+//     every spatial mode is a warp sum done by the integer adder of REDUX (redux.sync.add.s32): the terms are
+//     scaled to 2^25 / (largest amplitude of the row) and rounded, so the sum is exact in fixed point and its
+//     error (<= 2^-26 of the largest amplitude per term) is below that of a float32 summation -- 3
+//     instructions per mode instead of 10 shuffles and adds.  Short rows keep their forcing basis in registers;
 //   * the flux difference of the conservative forms needs the flux of the next point: one more shuffle.
-// No shared memory, no block barriers.  Arithmetic follows row_kernel operation by operation (same helpers:
-// equation_point, weno_pair, the stage / update formulas in float64), so both satisfy the same tolerances.
+// No shared memory, no block barriers.  The arithmetic of a right-hand side follows row_kernel operation by
+// operation (same helpers: equation_point, weno_pair), so both satisfy the same tolerances.
 //
 // Reference: model.baseline_space_derivatives (model.py:59-112), polynomials.reconstruct
 // (polynomials.py:280-303), equations.*.equation_of_motion, RandomForcing (equations.py:196-227),
@@ -21,84 +27,142 @@
 
 namespace ddd1d {
 
+// a + b = s + e exactly (Knuth's TwoSum)
+__device__ __forceinline__ void warp_two_sum(float a, float b, float& s, float& e) {
+  s = a + b;
+  const float bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+
+constexpr int warp_rows_min_blocks(int ppl) { return ppl <= 2 ? 3 : ppl == 4 ? 2 : 1; }
+
 // MM: compile-time bound on the number of forcing modes (4 covers the reference's k_max = 3)
-template <int PPL, bool WENO, int MM>
-__global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
-                                                       const __grid_constant__ Tableau tab) {
+// HALO: points the stencil table reaches on either side of a point (WENO: 3)
+template <int PPL, bool WENO, int MM, int HALO>
+__global__ void __launch_bounds__(256, warp_rows_min_blocks(PPL))
+warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W, const __grid_constant__ Tableau tab) {
+  static_assert(!WENO || HALO == kHalo, "WENO5 reads three points on either side");
+  constexpr int N = 32 * PPL;                         // == P.N
+  constexpr int TAPS = 2 * HALO + 1;
+  constexpr bool KEEP_BASIS = PPL * 2 * MM <= 16;     // the lane's forcing basis stays in registers
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int total_warps = gridDim.x * warps_per_block;
-  const int N = P.N;                       // == 32 * PPL
   const bool cons = eq_conservative(P.eq);
   const bool forced = eq_forced(P.eq) && P.P > 0;
+  const int nstages = tab.stages;
 
-  // window-form stencils of the derivative channels (ddd1d_set_stencils), in registers
-  float cf[kMaxD][kWin];
+  // window-form stencils of the derivative channels (ddd1d_set_stencils), offsets -HALO..+HALO, in registers
+  float cf[kMaxD][TAPS];
 #pragma unroll
   for (int d = 0; d < kMaxD; ++d)
 #pragma unroll
-    for (int j = 0; j < kWin; ++j) cf[d][j] = d < P.D ? __ldg(P.blob + P.st_off + d * kWinPad + j) : 0.f;
+    for (int j = 0; j < TAPS; ++j) cf[d][j] = d < P.D ? __ldg(P.blob + P.st_off + d * kWinPad + (kHalo - HALO) + j) : 0.f;
+
+  // the spatial basis of this lane's points: [sine-amplitude factors 0..MM) | cosine-amplitude factors 0..MM)]
+  float basis[KEEP_BASIS ? 2 * MM : 1][KEEP_BASIS ? PPL : 1];
+  if constexpr (KEEP_BASIS) {
+#pragma unroll
+    for (int m = 0; m < MM; ++m)
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const bool have = forced && m < P.M;
+        basis[m][i] = have ? __ldg(P.fbasis + (size_t)m * N + lane * PPL + i) : 0.f;
+        basis[MM + m][i] = have ? __ldg(P.fbasis + (size_t)(P.M + m) * N + lane * PPL + i) : 0.f;
+      }
+  }
 
   for (int row = gwarp; row < W.batch; row += total_warps) {
     const int sample = W.sample_offset + row;
+    // ---- per-row forcing constants (equations.py:196-219) ----
     const ForcingTerm fterm = load_forcing_term(P, sample, lane);
-    double y[PPL];
+    float a_s = 0.f, a_c = 0.f, inv_scale = 0.f;        // term amplitude in fixed-point units, cosine copy signed by k
+    float rot_c[kMaxStages], rot_s[kMaxStages];         // cos / sin of w c_s dt
+    unsigned int in_mode[MM];                           // all ones where this lane's term belongs to mode m + 1
+#pragma unroll
+    for (int m = 0; m < MM; ++m) in_mode[m] = 0u;
+#pragma unroll
+    for (int s = 0; s < kMaxStages; ++s) { rot_c[s] = 1.f; rot_s[s] = 0.f; }
+    if (forced) {
+      const bool on = lane < P.P;
+      const unsigned int amax_bits = __reduce_max_sync(0xffffffffu, on ? __float_as_uint(fabsf(fterm.a)) : 0u);
+      // 2^e >= largest |a| > 2^(e-1): terms scaled by 2^(25 - e) stay below 2^25, 32 of them below 2^30
+      const int eb = (int)(amax_bits >> 23) + ((amax_bits & 0x7fffffu) ? 1 : 0);      // biased exponent of 2^e
+      const int es = min(max(25 + 127 - (eb - 127), 1), 254);
+      const float scale = amax_bits == 0u ? 1.f : __uint_as_float((unsigned int)es << 23);
+      inv_scale = __uint_as_float((254u << 23) - __float_as_uint(scale));             // exact: powers of two
+      a_s = on ? fterm.a * scale : 0.f;
+      a_c = fterm.k < 0.f ? -a_s : a_s;
+      const float ka = fabsf(fterm.k);
+#pragma unroll
+      for (int m = 0; m < MM; ++m) in_mode[m] = (on && m < P.M && ka == (float)(m + 1)) ? 0xffffffffu : 0u;
+#pragma unroll
+      for (int s = 1; s < kMaxStages; ++s)
+        if (s < nstages) sincosf(fterm.w * (float)(tab.c[s] * W.dt), &rot_s[s], &rot_c[s]);
+    }
+
+    float yh[PPL], yl[PPL];                              // solution = yh + yl, yh = float(yh + yl)
     float k[kMaxStages][PPL];
 #pragma unroll
-    for (int i = 0; i < PPL; ++i)
-      y[i] = W.u64 ? W.u64[(size_t)row * N + lane * PPL + i] : (double)__ldg(W.u + (size_t)row * N + lane * PPL + i);
-    bool bad_seen = false;
+    for (int i = 0; i < PPL; ++i) {
+      if (W.u64) {
+        const double v = W.u64[(size_t)row * N + lane * PPL + i];
+        yh[i] = (float)v;
+        yl[i] = (float)(v - (double)yh[i]);
+      } else {
+        yh[i] = __ldg(W.u + (size_t)row * N + lane * PPL + i);
+        yl[i] = 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < kMaxStages; ++s) k[s][i] = 0.f;
+    }
     int first_bad = -1;
     int save_idx = 0;
+    int until_save = W.save_every;
 
     for (int step = 0; step < W.nsteps; ++step) {
-      const double t = W.t0 + (double)step * W.dt;
+      float sn0 = 0.f, cs0 = 0.f;
+      if (forced) {
+        const float t = (float)(W.t0 + (double)step * W.dt);
+        sincosf(fmaf(fterm.w, t, fterm.phi), &sn0, &cs0);
+      }
 #pragma unroll
       for (int s = 0; s < kMaxStages; ++s) {
-        if (s >= tab.stages) break;
-        // ---- stage row y + dt * sum_j a[s][j] k_j, rounded to float32 (integrate.py:57-60,71) ----
-        float e[PPL + 2 * kHalo];            // e[kHalo + i] = u[point i of this lane]
+        if (s >= nstages) break;
+        // ---- stage row y + dt * sum_j a[s][j] k_j, rounded to float32 (integrate.py:57-60,71): the increment in
+        //      float32, added low part first ----
+        float e[PPL + 2 * HALO];             // e[HALO + i] = u[point i of this lane]
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          double acc = 0.0;
+          float inc = 0.f;
 #pragma unroll
           for (int j = 0; j < kMaxStages; ++j)
-            if (j < s && tab.a[s][j] != 0.0) acc += tab.a[s][j] * (double)k[j][i];
-          e[kHalo + i] = (float)(s == 0 ? y[i] : y[i] + W.dt * acc);
+            if (j < s) inc = fmaf(W.adt[s][j], k[j][i], inc);
+          e[HALO + i] = s == 0 ? yh[i] : yh[i] + (yl[i] + inc);
         }
         // ---- periodic halo from the neighbouring lanes ----
 #pragma unroll
-        for (int h = 1; h <= kHalo; ++h) {
+        for (int h = 1; h <= HALO; ++h) {
           const int dl = (h + PPL - 1) / PPL;                  // lanes to the left
           const int il = (PPL - (h % PPL)) % PPL;              // its point index
-          e[kHalo - h] = __shfl_sync(0xffffffffu, e[kHalo + il], (lane - dl) & 31);
+          e[HALO - h] = __shfl_sync(0xffffffffu, e[HALO + il], (lane - dl) & 31);
           const int dr = (PPL - 1 + h) / PPL;                  // lanes to the right
           const int ir = (PPL - 1 + h) % PPL;
-          e[kHalo + PPL - 1 + h] = __shfl_sync(0xffffffffu, e[kHalo + ir], (lane + dr) & 31);
+          e[HALO + PPL - 1 + h] = __shfl_sync(0xffffffffu, e[HALO + ir], (lane + dr) & 31);
         }
-        // ---- forcing amplitudes of this stage (equations.py:214-219) ----
+        // ---- forcing amplitudes of this stage: rotate the step's sine / cosine, fixed-point warp sums ----
         float amp[2 * MM];
         if (forced) {
-          const float ts = (float)(t + tab.c[s] * W.dt);
-          float sn, cs;
-          sincosf(fmaf(fterm.w, ts, fterm.phi), &sn, &cs);
-          const bool on = lane < P.P;
-          const float a_sin = on ? fterm.a * sn : 0.f;
-          const float a_cos = on ? (fterm.k < 0.f ? -fterm.a : fterm.a) * cs : 0.f;
-          const float ka = fabsf(fterm.k);
+          const float sn = s == 0 ? sn0 : fmaf(sn0, rot_c[s], cs0 * rot_s[s]);
+          const float cs = s == 0 ? cs0 : fmaf(cs0, rot_c[s], -(sn0 * rot_s[s]));
+          const int is = __float2int_rn(a_s * sn), ic = __float2int_rn(a_c * cs);
 #pragma unroll
           for (int m = 0; m < MM; ++m) {
             amp[m] = amp[MM + m] = 0.f;
             if (m >= P.M) continue;
-            float a = ka == (float)(m + 1) ? a_sin : 0.f, b = ka == (float)(m + 1) ? a_cos : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, o);
-              b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            amp[m] = a;
-            amp[MM + m] = b;
+            amp[m] = (float)__reduce_add_sync(0xffffffffu, (int)((unsigned int)is & in_mode[m])) * inv_scale;
+            amp[MM + m] = (float)__reduce_add_sync(0xffffffffu, (int)((unsigned int)ic & in_mode[m])) * inv_scale;
           }
         }
         // ---- derivatives, equation of motion ----
@@ -111,17 +175,17 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
             float acc = 0.f;                 // einsum('bxdi,bxi->bxd') with constant rows (model.py:536-548)
             if (d < P.D && !(WENO && d < 2)) {      // (warp-uniform; WENO overwrites channels 0 and 1 below)
 #pragma unroll
-              for (int j = 0; j < kWin; ++j) acc = fmaf(cf[d][j], e[i + j], acc);
+              for (int j = 0; j < TAPS; ++j) acc = fmaf(cf[d][j], e[i + j], acc);
             }
             dv[d] = acc;
           }
           if (WENO) {                        // u_minus / u_plus replaced by WENO5 (integrate.py:134-138)
             float um, up;
-            weno_pair<float>(&e[kHalo + i], um, up);
+            weno_pair<float>(&e[HALO + i], um, up);
             dv[0] = um;
             dv[1] = up;
           }
-          r[i] = equation_point(P.eq, e[kHalo + i], dv, P.eta);
+          r[i] = equation_point(P.eq, e[HALO + i], dv, P.eta);
         }
         if (cons) {
           // y_t = -(1/dx) (flux[x+1] - flux[x])  (equations.py:305-320)
@@ -135,13 +199,20 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
         if (forced) {
 #pragma unroll
           for (int i = 0; i < PPL; ++i) {
-            const float* basis = P.fbasis + lane * PPL + i;
             float f = 0.f;
 #pragma unroll
             for (int m = 0; m < MM; ++m)
               if (m < P.M) {
-                f = fmaf(amp[m], __ldg(basis + (size_t)m * N), f);
-                f = fmaf(amp[MM + m], __ldg(basis + (size_t)(P.M + m) * N), f);
+                float bs, bc;
+                if constexpr (KEEP_BASIS) {
+                  bs = basis[m][i];
+                  bc = basis[MM + m][i];
+                } else {
+                  bs = __ldg(P.fbasis + (size_t)m * N + lane * PPL + i);
+                  bc = __ldg(P.fbasis + (size_t)(P.M + m) * N + lane * PPL + i);
+                }
+                f = fmaf(amp[m], bs, f);
+                f = fmaf(amp[MM + m], bc, f);
               }
             r[i] = __fadd_rn(r[i], f);
           }
@@ -149,22 +220,33 @@ __global__ void __launch_bounds__(256, PPL <= 2 ? 4 : PPL == 4 ? 2 : 1) warp_row
 #pragma unroll
         for (int i = 0; i < PPL; ++i) k[s][i] = r[i];
       }
-      // ---- end of the step: float64 update, snapshot ----
-      const bool save = ((step + 1) % W.save_every) == 0;
+      // ---- end of the step: y += dt * sum b k in float-float (the float64 sum of the reference to ~2^-48):
+      //      exact products of the float-float constants dt * b_j, highs summed with TwoSum ----
+      const bool save = --until_save == 0;
       float* snap = save ? W.snaps + ((size_t)save_idx * W.batch + row) * N + lane * PPL : nullptr;
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
-        double acc = 0.0;
+        float ih = 0.f, il = 0.f;
 #pragma unroll
-        for (int j = 0; j < kMaxStages; ++j)
-          if (j < tab.stages && tab.b[j] != 0.0) acc += tab.b[j] * (double)k[j][i];
-        double yn = y[i] + W.dt * acc;
-        if (W.state_f32) yn = (double)(float)yn;     // float32 carry (tf odeint_fixed, model.py:138-159)
-        y[i] = yn;
-        if (!bad_seen && !isfinite(yn)) { bad_seen = true; first_bad = step; }
-        if (save) snap[i] = (float)yn;
+        for (int j = 0; j < kMaxStages; ++j) {
+          if (j >= nstages) break;
+          const float ph = W.bdt_hi[j] * k[j][i];
+          const float pl = fmaf(W.bdt_hi[j], k[j][i], -ph) + W.bdt_lo[j] * k[j][i];
+          float sh, er;
+          warp_two_sum(ih, ph, sh, er);
+          ih = sh;
+          il += er + pl;
+        }
+        float nh, er;
+        warp_two_sum(yh[i], ih, nh, er);
+        const float nl = yl[i] + (er + il);
+        const float y = nh + nl;                       // renormalise: y = float(yh + yl)
+        yl[i] = W.state_f32 ? 0.f : nl - (y - nh);     // (float32 carry: tf odeint_fixed, model.py:138-159)
+        yh[i] = y;
+        if (first_bad < 0 && !isfinite(y)) first_bad = step;
+        if (save) snap[i] = y;
       }
-      if (save) ++save_idx;
+      if (save) { ++save_idx; until_save = W.save_every; }
     }
     if (W.first_bad) {
       unsigned int key = first_bad < 0 ? 0xffffffffu : (unsigned int)first_bad;
