@@ -595,7 +595,7 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     // fixed-stencil / float32 WENO modes for rows of 32 * {1, 2, 4, 8} points
     const Tableau tab = make_tableau(W.scheme);
     const bool weno = c.mode == DDD1D_MODE_WENO;
-    const bool few = P.M <= 4;                 // forcing modes (the reference's k_max = 3)
+    const bool few = P.M <= 3;                 // forcing modes (the reference's k_max = 3)
     // how far the stencil table reaches from a point (WENO5 reads three points either side)
     int halo = 1;
     if (weno) halo = kHalo;
@@ -606,10 +606,10 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     const void* kernel = nullptr;
 #define DDD1D_WARP_PICK(PPL)                                                                          \
   do {                                                                                                \
-    if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 4, 3> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3>;   \
-    else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 4, 1> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1>;   \
-    else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 4, 2> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2>;   \
-    else kernel = few ? (const void*)warp_row_kernel<PPL, false, 4, 3> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3>;   \
+    if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 3, 3> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3>;   \
+    else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 1> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1>;   \
+    else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 2> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2>;   \
+    else kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 3> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3>;   \
   } while (0)
     switch (c.num_points / 32) {
       case 1: DDD1D_WARP_PICK(1); break;

@@ -307,30 +307,60 @@ __device__ __forceinline__ void tmem_read_pairs(uint32_t t_main, uint32_t t_cros
   }
 }
 
-// x = hi + lo with hi = fp16(x) and lo = fp16(x - hi): F2FP, two HADD2.F32, one FADD2, F2FP per pair
-__device__ __forceinline__ void split_pair(float2 v, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(v.x, v.y);
-  const float2 d = fsub2(v, __half22float2(h));
-  const __half2 l = __floats2half2_rn(d.x, d.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+// relu(x) = hi + lo as two fp16 pairs, ReLU included.
+//   DDD1D_SPLIT_RZ (4 instructions per pair): hi = fp16(x) rounded TOWARDS ZERO and clamped at zero
+//     (F2FP.RELU.RZ), the exact remainders x - hi by the mixed-precision FMA (FHFMA: f16 * f16 + f32), lo =
+//     fp16(remainder) clamped at zero (F2FP.RELU): with hi rounded towards zero the remainder of a positive x is
+//     never negative, so the second clamp only acts where x < 0.  The remainder spans a whole ulp of hi: 2^-23.
+//   default (6 per pair): hi = fp16(x) rounded to nearest, clamped (F2FP.RELU); remainders max(x, 0) - hi (two
+//     FMNMX, two FHFMA), lo = fp16(remainder): 2^-24, the float32 operand precision.
+__device__ __forceinline__ void split_pair_relu(float2 v, uint32_t& hi, uint32_t& lo) {
+#ifdef DDD1D_SPLIT_RZ
+  asm("{\n\t.reg .b16 h0, h1, m1;\n\t.reg .f32 d0, d1;\n\t"
+      "cvt.rz.relu.f16x2.f32 %0, %3, %2;\n\t"
+      "mov.b32 {h0, h1}, %0;\n\t"
+      "mov.b16 m1, 0xBC00;\n\t"                       // -1.0
+      "fma.rn.f32.f16 d0, h0, m1, %2;\n\t"
+      "fma.rn.f32.f16 d1, h1, m1, %3;\n\t"
+      "cvt.rn.relu.f16x2.f32 %1, d1, d0;\n\t}"
+      : "=&r"(hi), "=&r"(lo)
+      : "f"(v.x), "f"(v.y));
+#else
+  const float rx = fmaxf(v.x, 0.f), ry = fmaxf(v.y, 0.f);
+  asm("{\n\t.reg .b16 h0, h1, m1;\n\t.reg .f32 d0, d1;\n\t"
+      "cvt.rn.f16x2.f32 %0, %3, %2;\n\t"
+      "mov.b32 {h0, h1}, %0;\n\t"
+      "mov.b16 m1, 0xBC00;\n\t"                       // -1.0
+      "fma.rn.f32.f16 d0, h0, m1, %2;\n\t"
+      "fma.rn.f32.f16 d1, h1, m1, %3;\n\t"
+      "cvt.rn.f16x2.f32 %1, d1, d0;\n\t}"
+      : "=&r"(hi), "=&r"(lo)
+      : "f"(rx), "f"(ry));
+#endif
+}
+// relu(x) rounded to one fp16 pair (PREC < 3)
+__device__ __forceinline__ uint32_t pack_half2_relu(float2 v) {
+  uint32_t h;
+  asm("cvt.rn.relu.f16x2.f32 %0, %2, %1;" : "=r"(h) : "f"(v.x), "f"(v.y));
+  return h;
 }
 
-// eight consecutive channels of one position (four pairs) -> one 16-byte chunk of the hi plane (and of the lo plane)
+// relu of eight consecutive channels of one position (four pairs) -> one 16-byte chunk of the hi plane (and of the
+// lo plane)
 template <class G>
 __device__ __forceinline__ void store_chunk8(unsigned char* mine, int c8, int copy_off, bool has_copy,
                                              const float2 (&v)[4]) {
   uint4 h, l;
   if (G::PREC == 3) {
-    split_pair(v[0], h.x, l.x);
-    split_pair(v[1], h.y, l.y);
-    split_pair(v[2], h.z, l.z);
-    split_pair(v[3], h.w, l.w);
+    split_pair_relu(v[0], h.x, l.x);
+    split_pair_relu(v[1], h.y, l.y);
+    split_pair_relu(v[2], h.z, l.z);
+    split_pair_relu(v[3], h.w, l.w);
   } else {
-    h.x = pack_half2(v[0].x, v[0].y);
-    h.y = pack_half2(v[1].x, v[1].y);
-    h.z = pack_half2(v[2].x, v[2].y);
-    h.w = pack_half2(v[3].x, v[3].y);
+    h.x = pack_half2_relu(v[0]);
+    h.y = pack_half2_relu(v[1]);
+    h.z = pack_half2_relu(v[2]);
+    h.w = pack_half2_relu(v[3]);
   }
   unsigned char* hp = mine + (uint32_t)c8 * G::PLANE;
   *reinterpret_cast<uint4*>(hp) = h;
@@ -438,7 +468,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
   using G = Geo<TILES, RPT, NL, PREC>;
   constexpr int N = G::N, TEAM = G::TEAM, R = G::R, TS = G::TS;
   unsigned char* const smem_raw = dyn_smem;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler (role branches, uniform registers)
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw + G::OFF_BAR);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + G::OFF_TMEM);
   // bars[0] blob copy | [1 + ts] "planes stored" (one arrival per team warp) | [1 + TS + ts * TILES + m] "tile's MMAs done"
@@ -740,9 +771,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
 #pragma unroll
             for (int i = 0; i < 4; ++i) h[i] = ffma2(u2, pair_at(P.w1, k * kF + 8 * c8 + 2 * i), h[i]);
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = make_float2(fmaxf(h[i].x, 0.f), fmaxf(h[i].y, 0.f));   // ReLU
-          store_chunk8<G>(my, c8, copy_off, has_copy, h);
+          store_chunk8<G>(my, c8, copy_off, has_copy, h);        // (ReLU inside the conversion)
         }
         fence_async_smem();
         __syncwarp();
@@ -785,7 +814,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 v = ffma2(acc[4 * c + i], inv2, pair_at(P.bh, 16 * half + 8 * c + 2 * i));
-              h[i] = fmul2(make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)), s2);
+              h[i] = fmul2(v, s2);                    // relu(v) * s = relu(v * s); the conversion clamps
             }
             store_chunk8<G>(my, 2 * half + c, copy_off, has_copy, h);
           }

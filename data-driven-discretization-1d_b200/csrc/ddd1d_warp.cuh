@@ -36,7 +36,7 @@ __device__ __forceinline__ void warp_two_sum(float a, float b, float& s, float& 
 
 constexpr int warp_rows_min_blocks(int ppl) { return ppl <= 2 ? 3 : ppl == 4 ? 2 : 1; }
 
-// MM: compile-time bound on the number of forcing modes (4 covers the reference's k_max = 3)
+// MM: compile-time bound on the number of forcing modes (3 is the reference's k_max)
 // HALO: points the stencil table reaches on either side of a point (WENO: 3)
 template <int PPL, bool WENO, int MM, int HALO>
 __global__ void __launch_bounds__(256, warp_rows_min_blocks(PPL))
@@ -44,7 +44,7 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
   static_assert(!WENO || HALO == kHalo, "WENO5 reads three points on either side");
   constexpr int N = 32 * PPL;                         // == P.N
   constexpr int TAPS = 2 * HALO + 1;
-  constexpr bool KEEP_BASIS = PPL * 2 * MM <= 16;     // the lane's forcing basis stays in registers
+  constexpr bool KEEP_BASIS = PPL * 2 * MM <= 24;     // the lane's forcing basis stays in registers
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -60,24 +60,14 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
 #pragma unroll
     for (int j = 0; j < TAPS; ++j) cf[d][j] = d < P.D ? __ldg(P.blob + P.st_off + d * kWinPad + (kHalo - HALO) + j) : 0.f;
 
-  // the spatial basis of this lane's points: [sine-amplitude factors 0..MM) | cosine-amplitude factors 0..MM)]
-  float basis[KEEP_BASIS ? 2 * MM : 1][KEEP_BASIS ? PPL : 1];
-  if constexpr (KEEP_BASIS) {
-#pragma unroll
-    for (int m = 0; m < MM; ++m)
-#pragma unroll
-      for (int i = 0; i < PPL; ++i) {
-        const bool have = forced && m < P.M;
-        basis[m][i] = have ? __ldg(P.fbasis + (size_t)m * N + lane * PPL + i) : 0.f;
-        basis[MM + m][i] = have ? __ldg(P.fbasis + (size_t)(P.M + m) * N + lane * PPL + i) : 0.f;
-      }
-  }
-
   for (int row = gwarp; row < W.batch; row += total_warps) {
     const int sample = W.sample_offset + row;
     // ---- per-row forcing constants (equations.py:196-219) ----
     const ForcingTerm fterm = load_forcing_term(P, sample, lane);
     float a_s = 0.f, a_c = 0.f, inv_scale = 0.f;        // term amplitude in fixed-point units, cosine copy signed by k
+    // the spatial basis of this lane's points over the row's fixed-point scale:
+    // [sine-amplitude factors 0..MM) | cosine-amplitude factors 0..MM)]
+    float sbasis[KEEP_BASIS ? 2 * MM : 1][KEEP_BASIS ? PPL : 1];
     float rot_c[kMaxStages], rot_s[kMaxStages];         // cos / sin of w c_s dt
     unsigned int in_mode[MM];                           // all ones where this lane's term belongs to mode m + 1
 #pragma unroll
@@ -100,6 +90,16 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
 #pragma unroll
       for (int s = 1; s < kMaxStages; ++s)
         if (s < nstages) sincosf(fterm.w * (float)(tab.c[s] * W.dt), &rot_s[s], &rot_c[s]);
+    }
+    if constexpr (KEEP_BASIS) {
+#pragma unroll
+      for (int m = 0; m < 2 * MM; ++m)
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const int mode = m < MM ? m : m - MM;
+          const bool have = forced && mode < P.M;
+          sbasis[m][i] = have ? __ldg(P.fbasis + (size_t)(m < MM ? mode : P.M + mode) * N + lane * PPL + i) * inv_scale : 0.f;
+        }
     }
 
     float yh[PPL], yl[PPL];                              // solution = yh + yl, yh = float(yh + yl)
@@ -157,12 +157,12 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
           const float sn = s == 0 ? sn0 : fmaf(sn0, rot_c[s], cs0 * rot_s[s]);
           const float cs = s == 0 ? cs0 : fmaf(cs0, rot_c[s], -(sn0 * rot_s[s]));
           const int is = __float2int_rn(a_s * sn), ic = __float2int_rn(a_c * cs);
+          // (modes beyond P.M have an empty mask: their sums are zero, no branch needed)
 #pragma unroll
           for (int m = 0; m < MM; ++m) {
-            amp[m] = amp[MM + m] = 0.f;
-            if (m >= P.M) continue;
-            amp[m] = (float)__reduce_add_sync(0xffffffffu, (int)((unsigned int)is & in_mode[m])) * inv_scale;
-            amp[MM + m] = (float)__reduce_add_sync(0xffffffffu, (int)((unsigned int)ic & in_mode[m])) * inv_scale;
+            amp[m] = (float)__reduce_add_sync(0xffffffffu, (int)((unsigned int)is & in_mode[m]));
+            amp[MM + m] = (float)__reduce_add_sync(0xffffffffu, (int)((unsigned int)ic & in_mode[m]));
+            if constexpr (!KEEP_BASIS) { amp[m] *= inv_scale; amp[MM + m] *= inv_scale; }
           }
         }
         // ---- derivatives, equation of motion ----
@@ -173,7 +173,7 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
 #pragma unroll
           for (int d = 0; d < kMaxD; ++d) {
             float acc = 0.f;                 // einsum('bxdi,bxi->bxd') with constant rows (model.py:536-548)
-            if (d < P.D && !(WENO && d < 2)) {      // (warp-uniform; WENO overwrites channels 0 and 1 below)
+            if (!(WENO && d < 2)) {          // (rows beyond P.D are zero; WENO overwrites channels 0 and 1 below)
 #pragma unroll
               for (int j = 0; j < TAPS; ++j) acc = fmaf(cf[d][j], e[i + j], acc);
             }
@@ -201,19 +201,18 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
           for (int i = 0; i < PPL; ++i) {
             float f = 0.f;
 #pragma unroll
-            for (int m = 0; m < MM; ++m)
-              if (m < P.M) {
-                float bs, bc;
-                if constexpr (KEEP_BASIS) {
-                  bs = basis[m][i];
-                  bc = basis[MM + m][i];
-                } else {
-                  bs = __ldg(P.fbasis + (size_t)m * N + lane * PPL + i);
-                  bc = __ldg(P.fbasis + (size_t)(P.M + m) * N + lane * PPL + i);
-                }
-                f = fmaf(amp[m], bs, f);
-                f = fmaf(amp[MM + m], bc, f);
+            for (int m = 0; m < MM; ++m) {
+              float bs, bc;
+              if constexpr (KEEP_BASIS) {
+                bs = sbasis[m][i];
+                bc = sbasis[MM + m][i];
+              } else {
+                bs = m < P.M ? __ldg(P.fbasis + (size_t)m * N + lane * PPL + i) : 0.f;
+                bc = m < P.M ? __ldg(P.fbasis + (size_t)(P.M + m) * N + lane * PPL + i) : 0.f;
               }
+              f = fmaf(amp[m], bs, f);
+              f = fmaf(amp[MM + m], bc, f);
+            }
             r[i] = __fadd_rn(r[i], f);
           }
         }
@@ -226,9 +225,10 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
       float* snap = save ? W.snaps + ((size_t)save_idx * W.batch + row) * N + lane * PPL : nullptr;
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
-        float ih = 0.f, il = 0.f;
+        float ih = W.bdt_hi[0] * k[0][i];
+        float il = fmaf(W.bdt_hi[0], k[0][i], -ih) + W.bdt_lo[0] * k[0][i];
 #pragma unroll
-        for (int j = 0; j < kMaxStages; ++j) {
+        for (int j = 1; j < kMaxStages; ++j) {
           if (j >= nstages) break;
           const float ph = W.bdt_hi[j] * k[j][i];
           const float pl = fmaf(W.bdt_hi[j], k[j][i], -ph) + W.bdt_lo[j] * k[j][i];

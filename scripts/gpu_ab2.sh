@@ -15,7 +15,7 @@ for v in "$@"; do
     echo "$v pytest: $(tail -1 $out/pytest_$v.log)"
   fi
   for w in ${WLS:-c2 c3 c4 c2s}; do
-    timeout -k 10 200 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/ab_${v}_${w}_$rep.json 2> $out/ab_${v}_${w}_$rep.err
+    timeout -k 10 200 python bench.py --workload $w --steps 5 --warmup 3 --rk-steps ${RK:-100} --no-cpu --extra "" > $out/ab_${v}_${w}_$rep.json 2> $out/ab_${v}_${w}_$rep.err
     python -c "
 import json; d=json.loads(open('$out/ab_${v}_${w}_$rep.json').read().strip().splitlines()[-1]); print('$v', '$w', '%.3f ms'%d['ms_per_step'], '%.3e'%d['value'], d.get('parity_check',{}).get('rel_err'))"
   done
