@@ -433,15 +433,22 @@ struct SlotState {
   float yh, yl;
   float k0, k1, k2, k3;
   float umax;        // verified bound on the slot's max |u / sigma|; < 0: not calibrated yet
-  float bound1;      // bound on the first layer's activations
 };
 
-__device__ __forceinline__ void set_k(SlotState& st, int s, float r) {
-  if (s == 0) st.k0 = r;
-  else if (s == 1) st.k1 = r;
-  else if (s == 2) st.k2 = r;
-  else st.k3 = r;
-}
+// The two slots of a team share ONE copy of the phase code (the steady-state loop has to stay inside the
+// instruction cache: two unrolled copies were 80 KB), selected by the run-time slot index: a field of the slot
+// in turn is one SEL to read and two predicated moves to write (exchanging the two register sets after every
+// turn cost ~40 moves).
+struct SlotPair {
+  SlotState a, b;
+};
+#define DDD1D_SLOT_GET(SS, sl, f) ((sl) ? (SS).b.f : (SS).a.f)
+#define DDD1D_SLOT_PUT(SS, sl, f, v) \
+  do {                               \
+    const float v_ = (v);            \
+    if (sl) (SS).b.f = v_;           \
+    else (SS).a.f = v_;              \
+  } while (0)
 
 // OP_COEF export of the last epilogue (per-call parity hook, not on the integration path): sixteen window
 // columns starting at column q0 of one grid point
@@ -568,10 +575,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((ts_a * TILES + tile) * G::COLS);
     const float* const fbasis_x = P.fbasis + x;         // this point's column of the forcing basis (L1 resident)
 
-    // The two slots of the team share ONE copy of the phase code (the steady-state loop has to stay inside the
-    // instruction cache: two unrolled copies were 80 KB): `cur` is the slot whose turn it is, `oth` the other
-    // one, and they change places after every turn (eight register moves).
-    SlotState cur, oth;
+    SlotPair SS;
     const int g = blockIdx.x * R + team;
 
     for (int unit0 = g; unit0 < units; unit0 += 2 * total_teams) {
@@ -579,7 +583,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       // ---- load the rows ----
       auto load_slot = [&](int sl, SlotState& S) {
         const int row = (unit0 + sl * total_teams) * RPT + rr;
-        const bool live = row < W.batch;
+        const bool live = sl < nslots && row < W.batch;
         if (!live) {
           S.yh = S.yl = 0.f;
         } else if (W.u64) {
@@ -592,13 +596,13 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
         S.k0 = S.k1 = S.k2 = S.k3 = 0.f;
         S.umax = -1.f;                                   // no bound yet: the first stage calibrates
-        S.bound1 = 0.f;
+        if (sl >= nslots) return;
         float* sc = sc0 + sl * G::SC_STRIDE;
         if (p < RPT) reinterpret_cast<unsigned int*>(sc + G::SC_BAD)[p] = 0xffffffffu;
         if (p == 0) *reinterpret_cast<unsigned int*>(sc + G::SC_UMAX) = 0u;
       };
-      load_slot(0, cur);
-      if (nslots > 1) load_slot(1, oth);
+      load_slot(0, SS.a);
+      load_slot(1, SS.b);
       team_sync(team, TEAM);
 
       // A right-hand side is "started" (phase 0) and "finished" (phase 2) in different turns: a slot's turn is
@@ -609,7 +613,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       int prev_step = 0, prev_s = 0;
 
       // ---- phase 2 (+ the Runge-Kutta update after the last stage) of right-hand side (fstep, fs) ----
-      auto finish = [&](int sl, SlotState& S, int fstep, int fs, uint32_t fpar) {
+      auto finish = [&](int sl, int fstep, int fs, uint32_t fpar) {
         float* const sc = sc0 + sl * G::SC_STRIDE;
         const float* const rowbuf = sc + G::SC_ROWS + (fpar * 2u * RPT + rr) * G::ROWBUF;
         const int row = (unit0 + sl * total_teams) * RPT + rr;
@@ -640,7 +644,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             }
           }
         }
-        const float bound1 = S.bound1;
+        const float bound1 = fmaf(P.w1abs, DDD1D_SLOT_GET(SS, sl, umax), P.b1abs);
         const float s_last = nhid > 0 ? scale_for(fmaf(P.whabs, bound1, P.bhabs)) : scale_for(bound1);
         const float inv_last = pow2_inverse(s_last) * P.inv_sw_last;
         if (!nowait) mbar_wait_spin(done0 + sl * TILES, done_parity);
@@ -686,13 +690,17 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           }
           return;
         }
-        set_k(S, fs, r);
+        if (fs == 0) DDD1D_SLOT_PUT(SS, sl, k0, r);
+        else if (fs == 1) DDD1D_SLOT_PUT(SS, sl, k1, r);
+        else if (fs == 2) DDD1D_SLOT_PUT(SS, sl, k2, r);
+        else DDD1D_SLOT_PUT(SS, sl, k3, r);
         if (fs != nstages - 1) return;
         // ---- the step is complete: y += dt * sum b k ----
         // increment dt * b_j * k_j as a float pair: exact products (FMA residual) of the float-float constants,
         // highs summed with TwoSum -- the float64 sum of the reference to ~2^-48
         float ih = 0.f, il = 0.f;
-        const float kk[kMaxStages] = {S.k0, S.k1, S.k2, S.k3};
+        const float kk[kMaxStages] = {DDD1D_SLOT_GET(SS, sl, k0), DDD1D_SLOT_GET(SS, sl, k1), DDD1D_SLOT_GET(SS, sl, k2),
+                                      DDD1D_SLOT_GET(SS, sl, k3)};
 #pragma unroll
         for (int j = 0; j < kMaxStages; ++j) {
           if (j >= nstages) break;
@@ -704,11 +712,11 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           il += e + pl;
         }
         float yh, e;
-        two_sum(S.yh, ih, yh, e);
-        const float yl = S.yl + (e + il);
+        two_sum(DDD1D_SLOT_GET(SS, sl, yh), ih, yh, e);
+        const float yl = DDD1D_SLOT_GET(SS, sl, yl) + (e + il);
         const float y = yh + yl;                       // renormalise: y = float(yh + yl)
-        S.yl = W.state_f32 ? 0.f : yl - (y - yh);      // (float32 carry: tf odeint_fixed, model.py:138-159)
-        S.yh = y;
+        DDD1D_SLOT_PUT(SS, sl, yl, W.state_f32 ? 0.f : yl - (y - yh));      // (float32 carry: tf odeint_fixed, model.py:138-159)
+        DDD1D_SLOT_PUT(SS, sl, yh, y);
         if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
           atomicMin(reinterpret_cast<unsigned int*>(sc + G::SC_BAD) + rr, (unsigned int)fstep);
         if (((fstep + 1) % W.save_every) == 0 && live)
@@ -716,13 +724,14 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       };
 
       // ---- phase 0 of right-hand side (step, s): stage value, exchange, first layer, planes, request ----
-      auto start = [&](int sl, SlotState& S, int step, int s, float a0, float a1, float a2) {
+      auto start = [&](int sl, int step, int s, float a0, float a1, float a2) {
         float* const sc = sc0 + sl * G::SC_STRIDE;
         float* const rowbuf = sc + G::SC_ROWS + (stage_par * 2u * RPT + rr) * G::ROWBUF;   // raw; normalised at + RPT * ROWBUF
         // stage value y + dt * sum a_j k_j rounded to float32 (integrate.py:57-60,71): the increment in float32
         // (its rounding is 1e-7 of an increment that is itself far below half an ulp of y), added low part first
-        const float inc = fmaf(a2, S.k2, fmaf(a1, S.k1, a0 * S.k0));      // a_j = float(dt * a[s][j]), 0 beyond the stage
-        const float us = s == 0 ? S.yh : S.yh + (S.yl + inc);
+        const float inc = fmaf(a2, DDD1D_SLOT_GET(SS, sl, k2), fmaf(a1, DDD1D_SLOT_GET(SS, sl, k1), a0 * DDD1D_SLOT_GET(SS, sl, k0)));      // a_j = float(dt * a[s][j]), 0 beyond the stage
+        const float yh0 = DDD1D_SLOT_GET(SS, sl, yh);
+        const float us = s == 0 ? yh0 : yh0 + (DDD1D_SLOT_GET(SS, sl, yl) + inc);
         const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
         rowbuf[x + kHalo] = us;
         rowbuf[RPT * G::ROWBUF + x + kHalo] = usn;
@@ -741,16 +750,15 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
               forcing_amplitudes_t(P, sc + G::SC_FS + fr * kFsWords + sq * kFsStride, W.sample_offset + frow, tq, lane);
           }
         }
-        float umax = S.umax;
+        float umax = DDD1D_SLOT_GET(SS, sl, umax);
         bool keep = team_sync_all(team, TEAM, fabsf(usn) <= umax);    // team-uniform; NaN rows fail every stage
         if (keep && s == 0 && (step & 15) == 15)                      // now and then: has the slot decayed far below
           keep = !team_sync_all(team, TEAM, fabsf(usn) < umax * (1.f / 256.f));   // its bound (lo planes would thin out)?
         if (!keep) {
           umax = recalibrate(reinterpret_cast<unsigned int*>(sc + G::SC_UMAX), usn, team, TEAM, lane, p == 0);
-          S.umax = umax;
+          DDD1D_SLOT_PUT(SS, sl, umax, umax);
         }
         const float bound1 = fmaf(P.w1abs, umax, P.b1abs);   // |h1| <= |b1| + sum|W1| * max|u/sigma|
-        S.bound1 = bound1;
         const float s_act = scale_for(bound1);
 
         // ---- first layer 1 -> 32 on the CUDA cores: relu(s * (W u + b)) = s * relu(W u + b), s a power of two;
@@ -793,8 +801,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       };
 
       // ---- phase 1: epilogue of a hidden tensor layer, planes rewritten in place, next layer requested ----
-      auto hidden = [&](int sl, SlotState& S) {
-        const float bound1 = S.bound1;
+      auto hidden = [&](int sl) {
+        const float bound1 = fmaf(P.w1abs, DDD1D_SLOT_GET(SS, sl, umax), P.b1abs);
         // accumulators carry (activation scale x filter scale); the next planes get their own scale
         const float inv = pow2_inverse(scale_for(bound1)) * P.inv_sw_hid;
         const float s_act = scale_for(fmaf(P.whabs, bound1, P.bhabs));   // |h2| <= |b2| + sum|W2| max|h1|
@@ -825,29 +833,20 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         if (lane == 0) mbar_arrive(req0 + sl);
       };
 
-      auto change_places = [&]() {
-        if (nslots > 1) {
-          const SlotState t = cur;
-          cur = oth;
-          oth = t;
-        }
-      };
       for (int step = 0; step < nsteps; ++step) {
         for (int s = 0; s < nstages; ++s) {
           // this stage's row of the tableau, fetched once for both slots
           const float a0 = s > 0 ? W.adt[s][0] : 0.f, a1 = s > 1 ? W.adt[s][1] : 0.f, a2 = s > 2 ? W.adt[s][2] : 0.f;
 #pragma unroll 1
           for (int sl = 0; sl < nslots; ++sl) {
-            if (have_prev) finish(sl, cur, prev_step, prev_s, stage_par ^ 1u);
-            start(sl, cur, step, s, a0, a1, a2);
-            change_places();
+            if (have_prev) finish(sl, prev_step, prev_s, stage_par ^ 1u);
+            start(sl, step, s, a0, a1, a2);
           }
           if (have_prev) done_parity ^= 1u;
           for (int l = 0; l < nhid; ++l) {
 #pragma unroll 1
             for (int sl = 0; sl < nslots; ++sl) {
-              hidden(sl, cur);
-              change_places();
+              hidden(sl);
             }
             done_parity ^= 1u;
           }
@@ -859,8 +858,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       }
 #pragma unroll 1
       for (int sl = 0; sl < nslots; ++sl) {
-        finish(sl, cur, prev_step, prev_s, stage_par ^ 1u);
-        change_places();
+        finish(sl, prev_step, prev_s, stage_par ^ 1u);
       }
       if (W.op == OP_INTEGRATE && W.first_bad) {
         team_sync(team, TEAM);
