@@ -94,6 +94,13 @@ struct Work {
   int* status;         // [batch]: 0 reached the end, -1 step size underflow
 };
 
+// a + b = s + e exactly (Knuth's TwoSum): the float-pair state of the fused integrators
+__device__ __forceinline__ void warp_two_sum(float a, float b, float& s, float& e) {
+  s = a + b;
+  const float bb = s - a;
+  e = (a - (s - bb)) + (b - bb);
+}
+
 // The one dynamic shared-memory window of every kernel in this library.  Device functions that
 // are not inlined re-derive their pointers from this symbol so loads stay LDS/STS.
 extern __shared__ __align__(128) unsigned char dyn_smem[];

@@ -27,13 +27,6 @@
 
 namespace ddd1d {
 
-// a + b = s + e exactly (Knuth's TwoSum)
-__device__ __forceinline__ void warp_two_sum(float a, float b, float& s, float& e) {
-  s = a + b;
-  const float bb = s - a;
-  e = (a - (s - bb)) + (b - bb);
-}
-
 constexpr int warp_rows_min_blocks(int ppl) { return ppl <= 2 ? 3 : ppl == 4 ? 2 : 1; }
 
 // MM: compile-time bound on the number of forcing modes (3 is the reference's k_max)

@@ -4,8 +4,9 @@
 // row_kernel<MODE_WENO> keeps the stage row, the stage derivatives and the flux in shared memory and walks
 // the points with a strided loop: 576 thread instructions per point-stage, of which 35 % are IEEE divisions
 // and 9 % the forcing basis loads (profiles/r01/row_kernel_weno_c5_ncu_full.json).  Here a thread owns PPT = 4
-// CONSECUTIVE points for the whole launch -- float64 solution, float32 stage derivatives and the stage values
-// in registers -- so that
+// CONSECUTIVE points for the whole launch -- the float64-equivalent solution as an unevaluated float pair (no
+// FP64 instruction or float64 conversion in the loop), float32 stage derivatives and the stage values in
+// registers -- so that
 //   * the smoothness indicators (weno.py:46-57) are computed once per stencil centre and shared by the right
 //     reconstruction of point p and the left reconstruction of point p + 1 (the reference computes them twice);
 //   * 1 / (eps + beta)^2 is one MUFU.RCP (1 ulp) per indicator, shared by both sides, the weight normalisation
@@ -15,8 +16,10 @@
 //   * the flux is evaluated at PPT + 1 points per thread, so the flux difference needs no second exchange;
 //   * halos (3 left, 4 right) come from the neighbouring lanes by shuffles; only the first / last lane of a warp
 //     goes through shared memory (one block barrier per stage, double buffered);
-//   * the forcing basis of the thread's 4 points is 6 LDG.128 per stage from L1, the mode amplitudes are
-//     computed by warp 0 (one forcing term per lane) ahead of the same barrier.
+//   * the forcing basis of the thread's 4 points is 6 LDG.128 per stage from L1; the mode amplitudes are
+//     computed by warp 0 (one forcing term per lane) ahead of the same barrier: one sincosf per STEP rotated to
+//     the later stages by angle addition, fixed-point warp sums on REDUX's integer adder (see ddd1d_warp.cuh),
+//     so that warp 0 is not the warp everybody waits for.
 // Reference: weno.py:43-123, integrate.WENODifferentiator (integrate.py:124-140), model.py:81-97 (float32
 // form), equations.py:341-370 (Godunov flux), :196-227 (forcing), integrate.odeint's Bogacki-Shampine steps.
 #pragma once
@@ -75,6 +78,8 @@ constexpr int kWenoHaloL = 3, kWenoHaloR = 4;
 struct WenoShared {
   float edge[2][32][2][4];               // [stage parity][warp][first lane's points 0..3 | last lane's points 1..3]
   float amps[2][2 * kMaxModes];          // [stage parity][sine sums 0..7 | cosine sums 0..7]
+  float rot[kMaxStages][32][2];          // [stage][lane of warp 0]: cos, sin of w c_s dt (rotation to stage s)
+  float term[32][4];                     // [lane of warp 0]: fixed-point amplitude, its copy signed by k, mode index
   unsigned int first_bad;
 };
 
@@ -99,11 +104,32 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
   for (int row = blockIdx.x; row < W.batch; row += gridDim.x) {
     const int sample = W.sample_offset + row;
     const ForcingTerm fterm = warp == 0 ? load_forcing_term(P, sample, lane) : ForcingTerm{0.f, 0.f, 0.f, 0.f};
-    double y[PPT];
+    // warp 0: term amplitude in fixed-point units (2^25 / largest amplitude of the row), cosine copy signed by k,
+    // mode |k| of this lane's term, cos / sin of w c_s dt (the rotation from the step's angle to stage s)
+    float inv_scale = 0.f;
+    if (forced && warp == 0) {
+      const bool on = lane < P.P;
+      const unsigned int amax_bits = __reduce_max_sync(0xffffffffu, on ? __float_as_uint(fabsf(fterm.a)) : 0u);
+      const int eb = (int)(amax_bits >> 23) + ((amax_bits & 0x7fffffu) ? 1 : 0);
+      const int es = min(max(279 - eb, 1), 254);                 // 2^(25 - e), 2^e >= the largest |a|
+      const float scale = amax_bits == 0u ? 1.f : __uint_as_float((unsigned int)es << 23);
+      inv_scale = __uint_as_float((254u << 23) - __float_as_uint(scale));
+      const float a_s = on ? fterm.a * scale : 0.f;
+      *reinterpret_cast<float4*>(sh.term[lane]) =
+          make_float4(a_s, fterm.k < 0.f ? -a_s : a_s, __int_as_float(on ? (int)fabsf(fterm.k) - 1 : -1), 0.f);
+      for (int q = 0; q < tab.stages; ++q) {       // (read back by the same lane only)
+        float rs, rc;
+        sincosf(fterm.w * (float)(tab.c[q] * W.dt), &rs, &rc);
+        sh.rot[q][lane][0] = rc;
+        sh.rot[q][lane][1] = rs;
+      }
+    }
+    float yh[PPT], yl[PPT];                        // solution = yh + yl, yh = float(yh + yl)
     float k0[PPT], k1[PPT], k2[PPT], k3[PPT];      // stage derivatives (static indexing keeps them in registers)
     {
       const float4 v = __ldg(reinterpret_cast<const float4*>(W.u + (size_t)row * N + p0));
-      y[0] = v.x; y[1] = v.y; y[2] = v.z; y[3] = v.w;
+      yh[0] = v.x; yh[1] = v.y; yh[2] = v.z; yh[3] = v.w;
+      yl[0] = yl[1] = yl[2] = yl[3] = 0.f;
     }
 #pragma unroll
     for (int i = 0; i < PPT; ++i) k0[i] = k1[i] = k2[i] = k3[i] = 0.f;
@@ -112,39 +138,37 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
     int save_idx = 0;
 
     for (int step = 0; step < W.nsteps; ++step) {
-      const double t = W.t0 + (double)step * W.dt;
+      float sn0 = 0.f, cs0 = 0.f;
+      if (forced && warp == 0) sincosf(fmaf(fterm.w, (float)(W.t0 + (double)step * W.dt), fterm.phi), &sn0, &cs0);
 #pragma unroll 1
       for (int s = 0; s < tab.stages; ++s) {
         // ---- stage values, rounded to float32 (integrate.py:57-60,71); a[s][j] = 0 for j >= s ----
         float E[PPT + kWenoHaloL + kWenoHaloR];        // E[j] = u[p0 + j - 3]
-        const double a0 = s > 0 ? tab.a[s][0] : 0.0, a1 = s > 1 ? tab.a[s][1] : 0.0, a2 = s > 2 ? tab.a[s][2] : 0.0;
+        // (the increment in float32, a_j = float(dt * a[s][j]), added low part first: as the tensor engine does)
+        const float a0 = s > 0 ? W.adt[s][0] : 0.f, a1 = s > 1 ? W.adt[s][1] : 0.f, a2 = s > 2 ? W.adt[s][2] : 0.f;
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
-          const double acc = fma(a2, (double)k2[i], fma(a1, (double)k1[i], a0 * (double)k0[i]));
-          E[kWenoHaloL + i] = (float)(s == 0 ? y[i] : y[i] + W.dt * acc);
+          const float inc = fmaf(a2, k2[i], fmaf(a1, k1[i], a0 * k0[i]));
+          E[kWenoHaloL + i] = s == 0 ? yh[i] : yh[i] + (yl[i] + inc);
         }
         // ---- halo exchange: shuffles inside the warp, shared memory across warps ----
         if (lane == 0) *reinterpret_cast<float4*>(sh.edge[par][warp][0]) = make_float4(E[3], E[4], E[5], E[6]);
         if (lane == 31) *reinterpret_cast<float4*>(sh.edge[par][warp][1]) = make_float4(E[4], E[5], E[6], 0.f);
         if (forced && warp == 0) {
-          // mode amplitudes of this stage (equations.py:214-219): one forcing term per lane, warp sums
-          const float ts = (float)(t + tab.c[s] * W.dt);
-          float sn, cs;
-          sincosf(fmaf(fterm.w, ts, fterm.phi), &sn, &cs);
-          const bool on = lane < P.P;
-          const float a_sin = on ? fterm.a * sn : 0.f;
-          const float a_cos = on ? (fterm.k < 0.f ? -fterm.a : fterm.a) * cs : 0.f;
-          const float ka = fabsf(fterm.k);
+          // mode amplitudes of this stage (equations.py:214-219): the step's sine / cosine rotated by w c_s dt,
+          // one forcing term per lane, exact fixed-point warp sums
+          const float2 rot = *reinterpret_cast<const float2*>(sh.rot[s][lane]);
+          const float rc = rot.x, rs = rot.y;
+          const float sn = fmaf(sn0, rc, cs0 * rs), cs = fmaf(cs0, rc, -(sn0 * rs));
+          const float4 term = *reinterpret_cast<const float4*>(sh.term[lane]);
+          const int my_mode = __float_as_int(term.z);
+          const int is = __float2int_rn(term.x * sn), ic = __float2int_rn(term.y * cs);
           float mine_s = 0.f, mine_c = 0.f;
 #pragma unroll
           for (int m = 0; m < kMaxModes; ++m) {
             if (m >= P.M) break;
-            float a = ka == (float)(m + 1) ? a_sin : 0.f, b = ka == (float)(m + 1) ? a_cos : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, o);
-              b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
+            const float a = (float)__reduce_add_sync(0xffffffffu, my_mode == m ? is : 0) * inv_scale;
+            const float b = (float)__reduce_add_sync(0xffffffffu, my_mode == m ? ic : 0) * inv_scale;
             if (lane == m) { mine_s = a; mine_c = b; }
           }
           if (lane < kMaxModes) {
@@ -217,20 +241,32 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
         }
         par ^= 1u;
       }
-      // ---- end of the step: float64 update, snapshot ----
+      // ---- end of the step: y += dt * sum b k in float-float (the float64 sum of the reference to ~2^-48) ----
       const bool save = ((step + 1) % W.save_every) == 0;
       float out[PPT];
 #pragma unroll
       for (int i = 0; i < PPT; ++i) {
-        double acc = tab.b[0] * (double)k0[i];
-        if (tab.stages > 1) acc = fma(tab.b[1], (double)k1[i], acc);
-        if (tab.stages > 2) acc = fma(tab.b[2], (double)k2[i], acc);
-        if (tab.stages > 3) acc = fma(tab.b[3], (double)k3[i], acc);
-        double yn = y[i] + W.dt * acc;
-        if (W.state_f32) yn = (double)(float)yn;     // float32 carry (tf odeint_fixed, model.py:138-159)
-        y[i] = yn;
+        const float kk[kMaxStages] = {k0[i], k1[i], k2[i], k3[i]};
+        float ih = W.bdt_hi[0] * kk[0];
+        float il = fmaf(W.bdt_hi[0], kk[0], -ih) + W.bdt_lo[0] * kk[0];
+#pragma unroll
+        for (int j = 1; j < kMaxStages; ++j) {
+          if (j >= tab.stages) break;
+          const float ph = W.bdt_hi[j] * kk[j];
+          const float pl = fmaf(W.bdt_hi[j], kk[j], -ph) + W.bdt_lo[j] * kk[j];
+          float sh_, er;
+          warp_two_sum(ih, ph, sh_, er);
+          ih = sh_;
+          il += er + pl;
+        }
+        float nh, er;
+        warp_two_sum(yh[i], ih, nh, er);
+        const float nl = yl[i] + (er + il);
+        const float yn = nh + nl;
+        yl[i] = W.state_f32 ? 0.f : nl - (yn - nh);     // float32 carry (tf odeint_fixed, model.py:138-159)
+        yh[i] = yn;
         if (first_bad < 0 && !isfinite(yn)) first_bad = step;
-        out[i] = (float)yn;
+        out[i] = yn;
       }
       if (save) {
         *reinterpret_cast<float4*>(W.snaps + ((size_t)save_idx * W.batch + row) * N + p0) =
