@@ -541,6 +541,51 @@ bool use_warp_rows(const ddd1d_handle* h, int op) {
   return getenv("DDD1D_NO_WARP_ROWS") == nullptr;
 }
 
+// The warp_row_kernel instantiation of a handle (points per lane x WENO x forcing modes x stencil reach) and,
+// cached on the handle, how many of its CTAs are resident per SM: the grid is exactly the resident CTAs
+// (persistent warps), so that no CTA waits for a slot.
+const void* pick_warp_kernel(ddd1d_handle* h) {
+  const ddd1d_config& c = h->cfg;
+  const Params& P = h->P;
+  const bool weno = c.mode == DDD1D_MODE_WENO;
+  const bool few = P.M <= 3;                 // forcing modes (the reference's k_max = 3)
+  // how far the stencil table reaches from a point (WENO5 reads three points either side)
+  int halo = 1;
+  if (weno) halo = kHalo;
+  else
+    for (int d = 0; d < c.num_derivatives; ++d)
+      for (int j = 0; j < kWin; ++j)
+        if (h->stencils[(size_t)d * kWinHost + kCentre + j] != 0.0) halo = std::max(halo, std::abs(j - kHalo));
+  const void* kernel = nullptr;
+#define DDD1D_WARP_PICK(PPL)                                                                          \
+  do {                                                                                                \
+  if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 3, 3> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3>;   \
+  else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 1> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1>;   \
+  else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 2> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2>;   \
+  else kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 3> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3>;   \
+  } while (0)
+  switch (c.num_points / 32) {
+    case 1: DDD1D_WARP_PICK(1); break;
+    case 2: DDD1D_WARP_PICK(2); break;
+    case 4: DDD1D_WARP_PICK(4); break;
+    default: DDD1D_WARP_PICK(8); break;
+  }
+#undef DDD1D_WARP_PICK
+  // persistent warps: exactly the CTAs that are resident at once, so that no CTA waits for a slot
+  if (h->warp_kernel != kernel) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * kWarpRowsPerBlock, 0) != cudaSuccess || occ < 1) occ = 1;
+    h->warp_kernel = kernel;
+    h->warp_occ = occ;
+  }
+  return kernel;
+}
+
+int warp_rows_grid(ddd1d_handle* h, int batch) {
+  pick_warp_kernel(h);
+  return std::max(1, std::min((batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * h->warp_occ));
+}
+
 // The register-resident CTA-per-row WENO5 integrator (ddd1d_weno.cuh) takes the fused fixed-step integration of
 // float32 WENO rows of 4 points per thread: N a multiple of 128 up to 2048 (BASELINE config 5).
 bool use_weno_block(const ddd1d_handle* h, int op) {
@@ -594,38 +639,8 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     // one warp per row, everything in registers (ddd1d_warp.cuh): the fixed-step integrator of the
     // fixed-stencil / float32 WENO modes for rows of 32 * {1, 2, 4, 8} points
     const Tableau tab = make_tableau(W.scheme);
-    const bool weno = c.mode == DDD1D_MODE_WENO;
-    const bool few = P.M <= 3;                 // forcing modes (the reference's k_max = 3)
-    // how far the stencil table reaches from a point (WENO5 reads three points either side)
-    int halo = 1;
-    if (weno) halo = kHalo;
-    else
-      for (int d = 0; d < c.num_derivatives; ++d)
-        for (int j = 0; j < kWin; ++j)
-          if (h->stencils[(size_t)d * kWinHost + kCentre + j] != 0.0) halo = std::max(halo, std::abs(j - kHalo));
-    const void* kernel = nullptr;
-#define DDD1D_WARP_PICK(PPL)                                                                          \
-  do {                                                                                                \
-    if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 3, 3> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3>;   \
-    else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 1> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1>;   \
-    else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 2> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2>;   \
-    else kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 3> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3>;   \
-  } while (0)
-    switch (c.num_points / 32) {
-      case 1: DDD1D_WARP_PICK(1); break;
-      case 2: DDD1D_WARP_PICK(2); break;
-      case 4: DDD1D_WARP_PICK(4); break;
-      default: DDD1D_WARP_PICK(8); break;
-    }
-#undef DDD1D_WARP_PICK
-    // persistent warps: exactly the CTAs that are resident at once, so that no CTA waits for a slot
-    if (h->warp_kernel != kernel) {
-      int occ = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * kWarpRowsPerBlock, 0) != cudaSuccess || occ < 1) occ = 1;
-      h->warp_kernel = kernel;
-      h->warp_occ = occ;
-    }
-    const int blocks = std::min((W.batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * h->warp_occ);
+    const void* kernel = pick_warp_kernel(h);
+    const int blocks = warp_rows_grid(h, W.batch);
     void* args[] = {(void*)&P, (void*)&W, (void*)&tab};
     CUDA_TRY(h, cudaLaunchKernel(kernel, dim3(blocks), dim3(32 * kWarpRowsPerBlock), args, 0, st));
     CUDA_TRY(h, cudaGetLastError());
@@ -1049,7 +1064,7 @@ int ddd1d_launch_shape(const ddd1d_handle* handle, int batch, int* grid, int* bl
     return DDD1D_OK;
   }
   if (use_warp_rows(h, OP_INTEGRATE)) {     // (the shape of ddd1d_integrate launches)
-    if (grid) *grid = std::min((batch + kWarpRowsPerBlock - 1) / kWarpRowsPerBlock, h->num_sms * 8);
+    if (grid) *grid = warp_rows_grid(h, batch);
     if (block) *block = 256;
     if (shared_bytes) *shared_bytes = 0;
     return DDD1D_OK;
