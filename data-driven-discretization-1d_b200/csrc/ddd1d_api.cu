@@ -557,12 +557,19 @@ const void* pick_warp_kernel(ddd1d_handle* h) {
       for (int j = 0; j < kWin; ++j)
         if (h->stencils[(size_t)d * kWinHost + kCentre + j] != 0.0) halo = std::max(halo, std::abs(j - kHalo));
   const void* kernel = nullptr;
+  // (the Burgers forms of the baseline configurations get instantiations with the equation folded in)
+#define DDD1D_WARP_PICK_EQ(PPL, EQ)                                                                   \
+  do {                                                                                                \
+    if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 3, 3, EQ> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3, EQ>;   \
+    else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 1, EQ> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1, EQ>;   \
+    else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 2, EQ> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2, EQ>;   \
+    else kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 3, EQ> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3, EQ>;   \
+  } while (0)
 #define DDD1D_WARP_PICK(PPL)                                                                          \
   do {                                                                                                \
-  if (weno) kernel = few ? (const void*)warp_row_kernel<PPL, true, 3, 3> : (const void*)warp_row_kernel<PPL, true, kMaxModes, 3>;   \
-  else if (halo == 1) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 1> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 1>;   \
-  else if (halo == 2) kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 2> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 2>;   \
-  else kernel = few ? (const void*)warp_row_kernel<PPL, false, 3, 3> : (const void*)warp_row_kernel<PPL, false, kMaxModes, 3>;   \
+    if (P.eq == EQ_BURGERS) DDD1D_WARP_PICK_EQ(PPL, EQ_BURGERS);                                      \
+    else if (P.eq == EQ_BURGERS_GOD) DDD1D_WARP_PICK_EQ(PPL, EQ_BURGERS_GOD);                         \
+    else DDD1D_WARP_PICK_EQ(PPL, -1);                                                                 \
   } while (0)
   switch (c.num_points / 32) {
     case 1: DDD1D_WARP_PICK(1); break;
@@ -570,6 +577,7 @@ const void* pick_warp_kernel(ddd1d_handle* h) {
     case 4: DDD1D_WARP_PICK(4); break;
     default: DDD1D_WARP_PICK(8); break;
   }
+#undef DDD1D_WARP_PICK_EQ
 #undef DDD1D_WARP_PICK
   // persistent warps: exactly the CTAs that are resident at once, so that no CTA waits for a slot
   if (h->warp_kernel != kernel) {
@@ -600,7 +608,7 @@ bool use_weno_block(const ddd1d_handle* h, int op) {
 int weno_block_grid(ddd1d_handle* h, int batch) {
   if (h->weno_block_occ == 0) {
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weno_block_kernel, h->cfg.num_points / kWenoPpt, 0) != cudaSuccess || occ < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, weno_block_kernel<-1>, h->cfg.num_points / kWenoPpt, 0) != cudaSuccess || occ < 1)
       occ = 1;
     h->weno_block_occ = occ;
   }
@@ -648,7 +656,10 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     return DDD1D_OK;
   }
   if (use_weno_block(h, W.op) && W.u) {
-    weno_block_kernel<<<weno_block_grid(h, W.batch), c.num_points / kWenoPpt, 0, st>>>(P, W, make_tableau(W.scheme));
+    if (P.eq == EQ_BURGERS_GOD)
+      weno_block_kernel<EQ_BURGERS_GOD><<<weno_block_grid(h, W.batch), c.num_points / kWenoPpt, 0, st>>>(P, W, make_tableau(W.scheme));
+    else
+      weno_block_kernel<-1><<<weno_block_grid(h, W.batch), c.num_points / kWenoPpt, 0, st>>>(P, W, make_tableau(W.scheme));
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return DDD1D_OK;

@@ -31,7 +31,10 @@ constexpr int warp_rows_min_blocks(int ppl) { return ppl <= 2 ? 3 : ppl == 4 ? 2
 
 // MM: compile-time bound on the number of forcing modes (3 is the reference's k_max)
 // HALO: points the stencil table reaches on either side of a point (WENO: 3)
-template <int PPL, bool WENO, int MM, int HALO>
+// EQ: the equation (EQ_* of ddd1d_device.cuh) when the instantiation is specialised for it, -1 = read P.eq.  The
+//     Burgers forms the baselines are quoted on get their own instantiation: equation_point's switch is an
+//     indirect branch per point and stage (17 % of the warp samples of the c1b launch before it was folded).
+template <int PPL, bool WENO, int MM, int HALO, int EQ>
 __global__ void __launch_bounds__(256, warp_rows_min_blocks(PPL))
 warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W, const __grid_constant__ Tableau tab) {
   static_assert(!WENO || HALO == kHalo, "WENO5 reads three points on either side");
@@ -42,8 +45,9 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
   const int warps_per_block = blockDim.x >> 5;
   const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int total_warps = gridDim.x * warps_per_block;
-  const bool cons = eq_conservative(P.eq);
-  const bool forced = eq_forced(P.eq) && P.P > 0;
+  const int eq = EQ >= 0 ? EQ : P.eq;
+  const bool cons = eq_conservative(eq);
+  const bool forced = eq_forced(eq) && P.P > 0;
   const int nstages = tab.stages;
 
   // window-form stencils of the derivative channels (ddd1d_set_stencils), offsets -HALO..+HALO, in registers
@@ -178,7 +182,7 @@ warp_row_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W
             dv[0] = um;
             dv[1] = up;
           }
-          r[i] = equation_point(P.eq, e[HALO + i], dv, P.eta);
+          r[i] = equation_point(eq, e[HALO + i], dv, P.eta);
         }
         if (cons) {
           // y_t = -(1/dx) (flux[x+1] - flux[x])  (equations.py:305-320)

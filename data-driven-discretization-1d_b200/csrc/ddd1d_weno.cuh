@@ -83,6 +83,9 @@ struct WenoShared {
   unsigned int first_bad;
 };
 
+// EQ: EQ_BURGERS_GOD for the instantiation specialised for BASELINE config 5 (folds equation_point's switch, an
+// indirect branch per point and stage), -1 = read P.eq
+template <int EQ>
 __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
                                                             const __grid_constant__ Tableau tab) {
   constexpr int PPT = kWenoPpt;
@@ -90,7 +93,8 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int N = P.N;                       // == PPT * blockDim.x
   const int p0 = tid * PPT;
-  const bool forced = eq_forced(P.eq) && P.P > 0;
+  const int eq = EQ >= 0 ? EQ : P.eq;
+  const bool forced = eq_forced(eq) && P.P > 0;
   const float4* const basis4 = reinterpret_cast<const float4*>(P.fbasis + p0);
 
   // window-form stencils of the non-WENO derivative channels (d >= 2), in registers
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
             for (int j = 0; j < kWin; ++j) acc = fmaf(cf[d][j], E[i + j], acc);
             dv[2 + d] = acc;
           }
-          flux[i] = equation_point(P.eq, E[kWenoHaloL + i], dv, P.eta);
+          flux[i] = equation_point(eq, E[kWenoHaloL + i], dv, P.eta);
         }
         // ---- y_t = -(1/dx) (flux[x+1] - flux[x]) + forcing (equations.py:305-320, 276-277) ----
         float f[PPT] = {0.f, 0.f, 0.f, 0.f};
