@@ -187,7 +187,10 @@ int finalize_tc(ddd1d_handle* h) {
   const int NL = (D * kWin <= 16) ? 16 : 32;
   const int K = 5, F = tc::kF;
   tc::TcEntry entry;
-  if (!tc::lookup(tiles, rpt, NL, prec, &entry)) {
+  // DDD1D_TC_SLOTS=3: three rows per team on the TMEM block pool where it is compiled (N = 256, NL = 16)
+  const bool pool = getenv("DDD1D_TC_SLOTS") && atoi(getenv("DDD1D_TC_SLOTS")) == 3 && tiles == 2 && rpt == 1 &&
+                    tc::lookup_t2_pool(NL, prec, &entry);
+  if (!pool && !tc::lookup(tiles, rpt, NL, prec, &entry)) {
     h->tc_why = "this (num_points, precision) combination is not compiled";
     if (wants_tensor(want)) return fail(h, DDD1D_EUNSUPPORTED, "tensor engine unavailable: %s", h->tc_why.c_str());
     return DDD1D_OK;
@@ -326,8 +329,7 @@ int finalize_tc(ddd1d_handle* h) {
 int tc_grid(const ddd1d_handle* h, int batch) {
   const tc::TcEntry& e = h->tc_entry;
   const int units = (batch + e.rows_per_slot - 1) / e.rows_per_slot;
-  const int teams = e.slots_per_cta / 2;
-  return std::max(1, std::min((units + teams - 1) / teams, h->num_sms));
+  return std::max(1, std::min((units + e.teams - 1) / e.teams, h->num_sms));
 }
 
 bool use_tc(const ddd1d_handle* h) {

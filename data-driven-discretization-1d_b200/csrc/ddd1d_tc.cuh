@@ -74,17 +74,23 @@ struct TcParams {
   alignas(16) float bl[kF];         //         folded last layer
 };
 
-template <int TILES_, int RPT_, int NL_, int PREC_>
+// SL_: rows ("slots") a team keeps in flight.  2: every slot owns a TMEM accumulator block.  3: the team's slots
+// share its TWO blocks as a pool (a block is only needed from a layer's request to the tcgen05.ld of its epilogue),
+// so a slot has two turns of the other slots between a request and the need for its result instead of one.
+template <int TILES_, int RPT_, int NL_, int PREC_, int SL_ = 2>
 struct Geo {
-  static constexpr int TILES = TILES_, RPT = RPT_, NL = NL_, PREC = PREC_;
+  static constexpr int TILES = TILES_, RPT = RPT_, NL = NL_, PREC = PREC_, SL = SL_;
+  static_assert(SL == 2 || SL == 3, "two or three slots per team");
   static_assert(TILES == 1 || RPT == 1, "packed rows live in one tile");
   static constexpr int TEAM = 128 * TILES;            // threads of a team = positions of a slot
   static constexpr int N = TEAM / RPT;                // points of a row
   // row teams per CTA (packed rows with NL = 32 at full precision: three, to fit shared memory)
   static constexpr int R = (RPT > 1 && NL == 32 && PREC == 3) ? 3 : 4 / TILES;
-  static constexpr int TS = 2 * R;                    // slots per CTA
+  static constexpr int TS = SL * R;                   // slots per CTA
+  static constexpr int BLOCKS = 2 * R;                // TMEM accumulator blocks (of TILES tiles) per CTA
+  static_assert(SL == 2 || R == 2, "the block pool is written for one issuer per team");
   static constexpr int ISSUERS = R > 2 ? R : 2;
-  static constexpr int SPI = TS / ISSUERS;            // slots per issuer (consecutive: one team's, or one)
+  static constexpr int SPI = 2 * R / ISSUERS;         // slots per issuer with SL = 2 (consecutive: one team's, or one)
   static constexpr int TEAM_WARPS = TEAM / 32;
   static constexpr int THREADS = R * TEAM + 32 * ISSUERS;
   static constexpr int GROUP = RPT == 1 ? 8 : 12;     // plane positions stored per 8 positions of a tile
@@ -98,7 +104,7 @@ struct Geo {
   static constexpr uint32_t OFF_SLOTS = OFF_BLOB + BH_BYTES + BL_BYTES;
   static constexpr uint32_t SMEM = OFF_SLOTS + TS * SLOT_BYTES;
   static constexpr int COLS = PREC == 1 ? 32 : 64;    // TMEM columns of one tile's accumulator block
-  static constexpr int TMEM_USED = TS * TILES * COLS;  // 512 (PREC >= 2) or 256 (384 with three teams)
+  static constexpr int TMEM_USED = BLOCKS * TILES * COLS;  // 512 (PREC >= 2) or 256 (384 with three teams)
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;     // allocations are powers of two
   // global scratch of one slot, in floats
   static constexpr int ROWBUF = N + 2 * kHalo + 2;    // one row with its halo
@@ -439,16 +445,31 @@ struct SlotState {
 // instruction cache: two unrolled copies were 80 KB), selected by the run-time slot index: a field of the slot
 // in turn is one SEL to read and two predicated moves to write (exchanging the two register sets after every
 // turn cost ~40 moves).
-struct SlotPair {
+template <int SL>
+struct SlotSet;
+template <>
+struct SlotSet<2> {
   SlotState a, b;
 };
-#define DDD1D_SLOT_GET(SS, sl, f) ((sl) ? (SS).b.f : (SS).a.f)
-#define DDD1D_SLOT_PUT(SS, sl, f, v) \
-  do {                               \
-    const float v_ = (v);            \
-    if (sl) (SS).b.f = v_;           \
-    else (SS).a.f = v_;              \
-  } while (0)
+template <>
+struct SlotSet<3> {
+  SlotState a, b, c;
+};
+__device__ __forceinline__ float slot_get(const SlotSet<2>& s, int sl, float SlotState::*f) { return sl ? s.b.*f : s.a.*f; }
+__device__ __forceinline__ float slot_get(const SlotSet<3>& s, int sl, float SlotState::*f) {
+  return sl == 0 ? s.a.*f : sl == 1 ? s.b.*f : s.c.*f;
+}
+__device__ __forceinline__ void slot_put(SlotSet<2>& s, int sl, float SlotState::*f, float v) {
+  if (sl) s.b.*f = v;
+  else s.a.*f = v;
+}
+__device__ __forceinline__ void slot_put(SlotSet<3>& s, int sl, float SlotState::*f, float v) {
+  if (sl == 0) s.a.*f = v;
+  else if (sl == 1) s.b.*f = v;
+  else s.c.*f = v;
+}
+#define DDD1D_SLOT_GET(SS, sl, f) slot_get(SS, sl, &SlotState::f)
+#define DDD1D_SLOT_PUT(SS, sl, f, v) slot_put(SS, sl, &SlotState::f, v)
 
 // OP_COEF export of the last epilogue (per-call parity hook, not on the integration path): sixteen window
 // columns starting at column q0 of one grid point
@@ -469,22 +490,27 @@ static __device__ __noinline__ void export_derivatives(const TcParams& P, const 
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int TILES, int RPT, int NL, int PREC>
-__global__ void __launch_bounds__(Geo<TILES, RPT, NL, PREC>::THREADS, 1)
+template <int TILES, int RPT, int NL, int PREC, int SL = 2>
+__global__ void __launch_bounds__(Geo<TILES, RPT, NL, PREC, SL>::THREADS, 1)
 tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W, const __grid_constant__ Tableau tab) {
-  using G = Geo<TILES, RPT, NL, PREC>;
-  constexpr int N = G::N, TEAM = G::TEAM, R = G::R, TS = G::TS;
+  using G = Geo<TILES, RPT, NL, PREC, SL>;
+  constexpr int N = G::N, TEAM = G::TEAM, R = G::R, TS = G::TS, BLOCKS = G::BLOCKS;
+  constexpr bool POOL = SL == 3;
   unsigned char* const smem_raw = dyn_smem;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler (role branches, uniform registers)
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw + G::OFF_BAR);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + G::OFF_TMEM);
-  // bars[0] blob copy | [1 + ts] "planes stored" (one arrival per team warp) | [1 + TS + ts * TILES + m] "tile's MMAs done"
+  // bars[0] blob copy | [1 + ts] "planes stored" (one arrival per team warp) | [1 + TS + blk * TILES + m] "tile's
+  // MMAs done" (blk = ts with two slots per team) | pool only: [1 + TS + BLOCKS * TILES + blk] "block read"
+  // (one arrival per team warp: the epilogue has its accumulators in registers, the block may be overwritten)
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     for (int t = 0; t < TS; ++t) mbar_init(&bars[1 + t], (uint32_t)G::TEAM_WARPS);
-    for (int t = 0; t < TS * TILES; ++t) mbar_init(&bars[1 + TS + t], 1);
+    for (int t = 0; t < BLOCKS * TILES; ++t) mbar_init(&bars[1 + TS + t], 1);
+    if (POOL)
+      for (int t = 0; t < BLOCKS; ++t) mbar_init(&bars[1 + TS + BLOCKS * TILES + t], (uint32_t)G::TEAM_WARPS);
     mbar_fence_init();
   }
   __syncthreads();
@@ -512,11 +538,49 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     // Issuer i serves slots [i * SPI, (i + 1) * SPI): both slots of one team (or one slot).  A team requests
     // its slots' layers in a fixed order, which this loop mirrors, so every wait is a blocking try_wait.
     const int issuer = warp - R * G::TEAM_WARPS;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t bh16 = (smem_s + G::OFF_BLOB) >> 4, bl16 = (smem_s + G::OFF_BLOB + G::BH_BYTES) >> 4;
+    if constexpr (POOL) {
+      // Block pool: issuer = team.  The team's requests are served in the order it makes them; request number rq
+      // goes to block rq & 1 of the team, which the epilogue of request rq - 2 must have read ("block read").
+      const int team = issuer;
+      uint32_t parity = 0, rq = 0;
+      for (int unit0 = blockIdx.x * R + team; unit0 < units; unit0 += SL * total_teams) {
+        const int nslots = min(SL, (units - unit0 + total_teams - 1) / total_teams);
+        for (int it = 0; it < nsteps * nstages; ++it) {
+          for (int layer = 0; layer <= nhid; ++layer) {
+#pragma unroll 1
+            for (int q = 0; q < nslots; ++q) {
+              const int ts = team * SL + q;
+              const int blk = team * 2 + (int)(rq & 1u);
+              const uint32_t use = rq >> 1;
+              if (!(P.debug & 64)) {
+                mbar_wait_guarded(&bars[1 + ts], parity);
+                if (use >= 1u) mbar_wait_guarded(&bars[1 + TS + BLOCKS * TILES + blk], (use - 1u) & 1u);
+              }
+              fence_after();
+              const uint32_t slot16 = (smem_s + G::OFF_SLOTS + (uint32_t)ts * G::SLOT_BYTES) >> 4;
+#pragma unroll 1
+              for (int m = 0; m < TILES; ++m) {
+                const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
+                const uint32_t d = tmem_u + (uint32_t)((blk * TILES + m) * G::COLS);
+                if (!(P.debug & 1)) {
+                  if (layer < nhid) issue_tile<G, 32>(a_hi, a_lo, bh16, d);
+                  else issue_tile<G, NL>(a_hi, a_lo, bl16, d);
+                }
+                if (elect_one()) mma_commit(&bars[1 + TS + blk * TILES + m]);
+                __syncwarp();
+              }
+              ++rq;
+            }
+            parity ^= 1u;
+          }
+        }
+      }
+    } else {
     const int ts0 = issuer * G::SPI;
     const int team = ts0 >> 1;
     const int g = blockIdx.x * R + team;
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t bh16 = (smem_s + G::OFF_BLOB) >> 4, bl16 = (smem_s + G::OFF_BLOB + G::BH_BYTES) >> 4;
     uint32_t parity = 0;                                       // all served slots flip together
     for (int unit0 = g; unit0 < units; unit0 += 2 * total_teams) {
       const int nslots = unit0 + total_teams < units ? 2 : 1;
@@ -545,6 +609,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
       }
     }
+    }
   } else if (!(P.debug & 64)) {
     // ---------------- row teams ----------------
     const int team = warp / G::TEAM_WARPS;
@@ -566,20 +631,23 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     const int wit = warp_in_team & 3;
     const int nb_tile = TILES == 1 ? -1 : wit == 0 ? (tile + TILES - 1) % TILES : wit == 3 ? (tile + 1) % TILES : -1;
 
-    const int ts_a = team * 2;                          // the team's first slot
+    const int ts_a = team * SL;                         // the team's first slot
+    const int blk_a = team * 2;                         // ... and first accumulator block (= slot with two slots per team)
     unsigned char* const mine = smem_raw + G::OFF_SLOTS + (uint32_t)ts_a * G::SLOT_BYTES + plane_pos<G>(p);
     float* const sc0 = P.scratch + ((size_t)blockIdx.x * TS + ts_a) * G::SC_STRIDE;
     uint64_t* const req0 = &bars[1 + ts_a];
-    uint64_t* const done0 = &bars[1 + TS + ts_a * TILES + tile];
-    uint64_t* const done_nb0 = &bars[1 + TS + ts_a * TILES + (nb_tile < 0 ? tile : nb_tile)];
-    const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((ts_a * TILES + tile) * G::COLS);
+    uint64_t* const done0 = &bars[1 + TS + blk_a * TILES + tile];
+    uint64_t* const done_nb0 = &bars[1 + TS + blk_a * TILES + (nb_tile < 0 ? tile : nb_tile)];
+    uint64_t* const read0 = &bars[1 + TS + BLOCKS * TILES + blk_a];      // pool: "block read"
+    const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((blk_a * TILES + tile) * G::COLS);
+    uint32_t cq = 0;      // pool: requests of this team consumed so far; request cq sits in block cq & 1, use cq >> 1
     const float* const fbasis_x = P.fbasis + x;         // this point's column of the forcing basis (L1 resident)
 
-    SlotPair SS;
+    SlotSet<SL> SS;
     const int g = blockIdx.x * R + team;
 
-    for (int unit0 = g; unit0 < units; unit0 += 2 * total_teams) {
-      const int nslots = unit0 + total_teams < units ? 2 : 1;
+    for (int unit0 = g; unit0 < units; unit0 += SL * total_teams) {
+      const int nslots = min(SL, (units - unit0 + total_teams - 1) / total_teams);
       // ---- load the rows ----
       auto load_slot = [&](int sl, SlotState& S) {
         const int row = (unit0 + sl * total_teams) * RPT + rr;
@@ -603,6 +671,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       };
       load_slot(0, SS.a);
       load_slot(1, SS.b);
+      if constexpr (SL == 3) load_slot(2, SS.c);
       team_sync(team, TEAM);
 
       // A right-hand side is "started" (phase 0) and "finished" (phase 2) in different turns: a slot's turn is
@@ -647,15 +716,18 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         const float bound1 = fmaf(P.w1abs, DDD1D_SLOT_GET(SS, sl, umax), P.b1abs);
         const float s_last = nhid > 0 ? scale_for(fmaf(P.whabs, bound1, P.bhabs)) : scale_for(bound1);
         const float inv_last = pow2_inverse(s_last) * P.inv_sw_last;
-        if (!nowait) mbar_wait_spin(done0 + sl * TILES, done_parity);
-        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + sl * TILES, done_parity);     // before the next stage rewrites the planes
+        // where the slot's accumulators are: its own block, or (pool) the block its request was dealt
+        const int blk = POOL ? (int)(cq & 1u) : sl;
+        const uint32_t dpar = POOL ? ((cq >> 1) & 1u) : done_parity;
+        if (!nowait) mbar_wait_spin(done0 + blk * TILES, dpar);
+        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + blk * TILES, dpar);     // before the next stage rewrites the planes
         fence_after();
         // window coefficients = accumulators + folded bias, then the stencil dot products (model.py:536-548);
         // sixteen columns at a time keeps the register peak low
         float dv[kMaxD];
 #pragma unroll
         for (int d = 0; d < kMaxD; ++d) dv[d] = 0.f;
-        const uint32_t taddr = taddr0 + (uint32_t)(sl * TILES * G::COLS);
+        const uint32_t taddr = taddr0 + (uint32_t)(blk * TILES * G::COLS);
 #pragma unroll
         for (int half = 0; half < NL / 16; ++half) {
           float2 v[8];
@@ -670,6 +742,11 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           if (W.op == OP_COEF && live) export_coefficients(P, W, c16, 16 * half, (size_t)row * N + x);
         }
         fence_before();
+        if constexpr (POOL) {                     // the block may be overwritten: its next request can be served
+          __syncwarp();
+          if (lane == 0) mbar_arrive(read0 + blk);
+          ++cq;
+        }
         if (!fast_op) {
           if (W.op == OP_DERIV && live) export_derivatives(P, W, dv, (size_t)row * N + x);
           return;
@@ -808,14 +885,22 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         const float s_act = scale_for(fmaf(P.whabs, bound1, P.bhabs));   // |h2| <= |b2| + sum|W2| max|h1|
         const float2 inv2 = make_float2(inv, inv), s2 = make_float2(s_act, s_act);
         unsigned char* const my = mine + sl * G::SLOT_BYTES;
-        const uint32_t taddr = taddr0 + (uint32_t)(sl * TILES * G::COLS);
-        if (!nowait) mbar_wait_spin(done0 + sl * TILES, done_parity);
+        const int blk = POOL ? (int)(cq & 1u) : sl;
+        const uint32_t dpar = POOL ? ((cq >> 1) & 1u) : done_parity;
+        const uint32_t taddr = taddr0 + (uint32_t)(blk * TILES * G::COLS);
+        if (!nowait) mbar_wait_spin(done0 + blk * TILES, dpar);
         fence_after();
-        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + sl * TILES, done_parity);
+        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + blk * TILES, dpar);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {            // 16 channels at a time keeps the register peak low
           float2 acc[8];
           tmem_read_pairs<PREC>(taddr + 16 * half, taddr + 32 + 16 * half, acc);
+          if (POOL && half == 1) {                        // all accumulators are in registers: release the block early
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(read0 + blk);
+            ++cq;
+          }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             float2 h[4];
@@ -863,7 +948,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       if (W.op == OP_INTEGRATE && W.first_bad) {
         team_sync(team, TEAM);
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int sl = 0; sl < SL; ++sl) {
           if (sl >= nslots) continue;
           const int row = (unit0 + sl * total_teams) * RPT + rr;
           const unsigned int fb = reinterpret_cast<unsigned int*>(sc0 + sl * G::SC_STRIDE + G::SC_BAD)[rr];

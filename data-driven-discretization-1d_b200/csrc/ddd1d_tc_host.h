@@ -14,6 +14,7 @@ struct TcEntry {
   const void* kernel;      // for cudaFuncSetAttribute / occupancy queries
   void (*launch)(const TcParams&, const Work&, const Tableau&, int grid, cudaStream_t);
   int tiles, rpt, nl, prec;
+  int teams, slots_per_team;   // row teams per CTA; rows a team keeps in flight (3: TMEM block pool)
   int num_points;          // N of a row
   int threads, smem_bytes, tmem_cols;
   int slots_per_cta, rows_per_slot, sc_stride;   // scratch: grid * slots_per_cta * sc_stride floats
@@ -24,6 +25,7 @@ struct TcEntry {
 bool lookup(int tiles, int rpt, int nl, int prec, TcEntry* out);
 bool lookup_t1(int nl, int prec, TcEntry* out);
 bool lookup_t2(int nl, int prec, TcEntry* out);
+bool lookup_t2_pool(int nl, int prec, TcEntry* out);
 bool lookup_t4(int nl, int prec, TcEntry* out);
 bool lookup_p2(int nl, int prec, TcEntry* out);
 bool lookup_p4(int nl, int prec, TcEntry* out);

@@ -2,4 +2,5 @@
 #define DDD1D_TC_TILES 2
 #define DDD1D_TC_RPT 1
 #define DDD1D_TC_NAME t2
+#define DDD1D_TC_POOL 1
 #include "ddd1d_tc_inst.inc"
