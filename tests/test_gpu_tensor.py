@@ -217,3 +217,33 @@ def test_reduced_precision_engines(engine, tol):
     faithful = runtime.learned_solver(eq, G.product_hparams('burgers', 'plain', n), w, engine='tensor')
     assert rel_err(cpu(faithful.coefficients(u)), c64) < err      # and the faithful form is closer
     solver.close(), faithful.close()
+
+
+def test_block_pool_three_slots_is_bit_equal(monkeypatch):
+  """DDD1D_TC_SLOTS=3 (opt-in): three rows per team on the TMEM accumulator block pool.  Same arithmetic, another
+  schedule: results must be bit-identical to the two-slot kernel, for batch sizes that leave teams with three, two,
+  one and no rows in their last round, per call and over a trajectory with snapshots."""
+  import torch
+  from ddd1d_b200 import runtime
+  n, kind, dt = 256, 'burgers', 1e-3
+  oeq0 = G.oracle_equation(kind, 'plain', n)
+  w = O.glorot_weights(oeq0, O.NetSpec(), seed=1, last_layer_scale=0.01)
+  sms = torch.cuda.get_device_properties(0).multi_processor_count
+  for batch in (2, 2 * sms * 3 + 2 * sms + 5, 2 * sms * 2 - 3):
+    eqs = [G.product_equation(kind, 'plain', n, seed=s) for s in range(batch)]
+    u0 = G.smooth_rows(batch, n, seed=batch)
+    out = {}
+    for slots in (2, 3):
+      if slots == 3:
+        monkeypatch.setenv('DDD1D_TC_SLOTS', '3')
+      else:
+        monkeypatch.delenv('DDD1D_TC_SLOTS', raising=False)
+      solver = runtime.learned_solver(eqs, G.product_hparams(kind, 'plain', n), w, engine='tensor')
+      shape = solver.launch_shape(batch)
+      assert shape['shared_bytes'] == (230656 if slots == 3 else 164096), shape
+      snaps, bad = solver.integrate(u0, 0.05, dt, 7, 3, return_first_bad=True)
+      out[slots] = (snaps.clone(), bad.clone(), solver.rhs(0.3, u0).clone())
+      solver.close()
+    monkeypatch.delenv('DDD1D_TC_SLOTS', raising=False)
+    for a, b in zip(out[2], out[3]):
+      assert torch.equal(a, b)
