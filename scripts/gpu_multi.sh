@@ -1,16 +1,16 @@
 #!/bin/bash
-# 2-GPU pass: torchrun bench (ours + reference arm), then the non-headline workloads on GPU 0.
+# 2-GPU pass (gpurun --gpus 2): the sharded-evaluation test, then torchrun bench lines: weak, strong, reference arm.
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus 2 --steps 8 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo "n2 exit $?" >> gpurun_out/bench_n2.err
-timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-    bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
-echo "ref n2 exit $?" >> gpurun_out/bench_ref_n2.err
-for w in c5 c1b; do
-  timeout -k 10 600 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
-  echo "$w exit $?" >> gpurun_out/bench_$w.err
-done
-DDD1D_ENGINE=ffma timeout -k 10 600 python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_ffma.json 2> gpurun_out/bench_ffma.err
-echo done
+out=gpurun_out/${1:-multi}; mkdir -p $out
+timeout -k 10 600 python -m pytest tests/test_gpu_multi.py -q -x --timeout 300 -p no:cacheprovider > $out/pytest_multi.log 2>&1
+echo "pytest exit $?" >> $out/pytest_multi.log; tail -2 $out/pytest_multi.log
+run() { name=$1; port=$2; shift 2
+  timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $port \
+      bench.py --gpus 2 "$@" > $out/$name.json 2> $out/$name.err
+  echo "$name exit $?" >> $out/$name.err
+  python -c "
+import json; d=json.loads(open('$out/$name.json').read().strip().splitlines()[-1]); print('$name', d.get('value'), (d.get('e2e') or {}).get('value'), d.get('scaling'), d.get('gather'))"
+}
+run bench_n2_weak 29511 --steps 20 --warmup 5 --no-cpu --extra ''
+run bench_n2_strong 29512 --steps 20 --warmup 5 --scaling strong --no-cpu --extra ''
+run bench_ref_n2 29513 --impl reference --steps 2 --warmup 1
