@@ -121,6 +121,288 @@ __global__ void __launch_bounds__(160, 1) tc_probe_kernel(const float* __restric
   if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Probe of the TMEM-resident A operand: tcgen05.cp (128x256b, 4x256b), tcgen05.shift.down, tcgen05.mma with A in
+// TMEM (+ .ashift).  Dumps raw TMEM contents after every step so that the host can read off the semantics.
+//   out  uint32 [10][128][16]
+// Planes: raw 16-bit pattern  p | ((chunk * 8 + j) << 8)  at (chunk, position p, half j); a second plane set holds
+// small integers as fp16 for the MMA checks: A2[p][k] = ((p * 3 + k) % 7) - 3,  B[n][k] = ((n + 2 * k) % 5) - 2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_cp(uint32_t taddr, uint64_t desc, int shape) {
+  if (shape == 0) asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+  else asm volatile("tcgen05.cp.cta_group::1.4x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
+__device__ __forceinline__ void tc_shift(uint32_t taddr) {
+  asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ta(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                           bool ashift) {
+  if (ashift)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16.ashift [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+__global__ void __launch_bounds__(160, 1) tc_shift_probe_kernel(uint32_t* __restrict__ out) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int P = 160;
+  constexpr uint32_t plane = P * 16;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  unsigned short* raw = reinterpret_cast<unsigned short*>(smem_raw + 128);            // [2][P][8]
+  __half* a2 = reinterpret_cast<__half*>(smem_raw + 128 + 2 * plane);                 // [2][P][8]
+  __half* b = reinterpret_cast<__half*>(smem_raw + 128 + 4 * plane);                  // [2][16][8]
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(slot, 64);
+  for (int i = tid; i < 2 * P * 8; i += blockDim.x) {
+    const int c = i / (P * 8), p = (i / 8) % P, j = i % 8, k = c * 8 + j;
+    raw[i] = (unsigned short)(p | (k << 8));
+    a2[i] = __float2half((float)(((p * 3 + k) % 7) - 3));
+  }
+  for (int i = tid; i < 2 * 16 * 8; i += blockDim.x) {
+    const int c = i / 128, n = (i / 8) % 16, j = i % 8, k = c * 8 + j;
+    b[i] = __float2half((float)(((n + 2 * k) % 5) - 2));
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  const uint32_t raw_s = smem_u32(raw), a2_s = smem_u32(a2), b_s = smem_u32(b);
+  const uint64_t bdesc = smem_desc(b_s, 256, 128);
+  const uint32_t idesc = instr_desc_f16(128, 16);
+  uint32_t parity = 0;
+  // one step: the issuer runs `what`, commits; everybody waits and dumps columns [col, col + 16)
+  auto dump = [&](int step, uint32_t col) {
+    mbar_wait_guarded(bar, parity);
+    parity ^= 1u;
+    fence_after();
+    if (warp < 4) {
+      uint32_t r[16];
+      tmem_ld16_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + col, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) out[((size_t)step * 128 + tid) * 16 + i] = r[i];
+      fence_before();
+    }
+    __syncthreads();
+    fence_after();
+  };
+  const bool issuer = warp == 4 && elect_one();
+  // 0: 128x256b copy of positions 2..129
+  if (issuer) { tc_cp(tmem_base, smem_desc(raw_s + 2 * 16, plane, 128), 0); mma_commit(bar); }
+  dump(0, 0);
+  // 1: one shift
+  if (issuer) { tc_shift(tmem_base); mma_commit(bar); }
+  dump(1, 0);
+  // 2: 4x256b copy from position 100
+  if (issuer) { tc_cp(tmem_base, smem_desc(raw_s + 100 * 16, plane, 128), 1); mma_commit(bar); }
+  dump(2, 0);
+  // 3: shift, then 4x256b (position 120) back to back (pipeline order)
+  if (issuer) { tc_shift(tmem_base); tc_cp(tmem_base, smem_desc(raw_s + 120 * 16, plane, 128), 1); mma_commit(bar); }
+  dump(3, 0);
+  // 4: 4x256b with lane 31 (and 16, at columns 8..15 so that both show) in the address
+  if (issuer) {
+    tc_cp(tmem_base + (31u << 16), smem_desc(raw_s + 140 * 16, plane, 128), 1);
+    tc_cp(tmem_base + (16u << 16) + 8, smem_desc(raw_s + 150 * 16, plane, 128), 1);
+    mma_commit(bar);
+  }
+  dump(4, 0);
+  // 5: fresh copy of the fp16 integers, plain MMA with A in TMEM -> D at column 16
+  if (issuer) {
+    tc_cp(tmem_base, smem_desc(a2_s, plane, 128), 0);
+    mma_f16_ta(tmem_base + 16, tmem_base, bdesc, idesc, 0u, false);
+    mma_commit(bar);
+  }
+  dump(5, 16);
+  // 6: MMA.ashift -> D at column 32; 7: plain MMA afterwards -> D at column 48; 8: the A columns afterwards
+  if (issuer) {
+    mma_f16_ta(tmem_base + 32, tmem_base, bdesc, idesc, 0u, true);
+    mma_f16_ta(tmem_base + 48, tmem_base, bdesc, idesc, 0u, false);
+    mma_commit(bar);
+  }
+  dump(6, 32);
+  if (issuer) mma_commit(bar);
+  dump(7, 48);
+  if (issuer) mma_commit(bar);
+  dump(8, 0);
+  // 9: explicit shift then MMA back to back (pipeline order) -> D at column 16
+  if (issuer) {
+    tc_shift(tmem_base);
+    mma_f16_ta(tmem_base + 16, tmem_base, bdesc, idesc, 0u, false);
+    mma_commit(bar);
+  }
+  dump(9, 16);
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 64);
+}
+
+
+// WAR stress: does a tcgen05.cp that overwrites an A operand in TMEM wait for earlier MMAs that still read it?
+// `chain` MMAs (N = 256, accumulating) read A = rows of set 0, then a cp overwrites A with set 1 and one more
+// MMA (N = 16) reads it into other columns.  out[0][lane][0..15] = first 16 columns of the chain's D (expected:
+// chain * A0 B^T), out[1] = the second MMA's D (expected A1 B^T).  Repeated `rounds` times, mismatches counted.
+__global__ void __launch_bounds__(160, 1) tc_war_probe_kernel(uint32_t* __restrict__ out, int chain, int rounds) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int P = 128;
+  constexpr uint32_t plane = P * 16;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  __half* a0 = reinterpret_cast<__half*>(smem_raw + 128);                    // [2][P][8]
+  __half* a1 = reinterpret_cast<__half*>(smem_raw + 128 + 2 * plane);
+  __half* b = reinterpret_cast<__half*>(smem_raw + 128 + 4 * plane);          // [2][256][8]
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (warp == 4) tmem_alloc(slot, 512);
+  for (int i = tid; i < 2 * P * 8; i += blockDim.x) {
+    const int c = i / (P * 8), p = (i / 8) % P, j = i % 8, k = c * 8 + j;
+    a0[i] = __float2half((float)(((p * 3 + k) % 7) - 3));
+    a1[i] = __float2half((float)(((p * 5 + 2 * k) % 9) - 4));
+  }
+  for (int i = tid; i < 2 * 256 * 8; i += blockDim.x) {
+    const int c = i / 2048, n = (i / 8) % 256, j = i % 8, k = c * 8 + j;
+    b[i] = __float2half((float)(((n + 2 * k) % 5) - 2));
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  const uint64_t bdesc = smem_desc(smem_u32(b), 256 * 16, 128);
+  const uint32_t idesc_big = instr_desc_f16(128, 256), idesc_small = instr_desc_f16(128, 16);
+  const bool issuer = warp == 4 && elect_one();
+  uint32_t parity = 0;
+  uint32_t bad = 0;
+  for (int r = 0; r < rounds; ++r) {
+    if (issuer) {
+      tc_cp(tmem_base + 480, smem_desc(smem_u32(a0), plane, 128), 0);
+      for (int i = 0; i < chain; ++i) mma_f16_ta(tmem_base, tmem_base + 480, bdesc, idesc_big, i ? 1u : 0u, false);
+      tc_cp(tmem_base + 480, smem_desc(smem_u32(a1), plane, 128), 0);          // WAR on the A columns
+      mma_f16_ta(tmem_base + 256, tmem_base + 480, bdesc, idesc_small, 0u, false);
+      mma_commit(bar);
+    }
+    mbar_wait_guarded(bar, parity);
+    parity ^= 1u;
+    fence_after();
+    if (warp < 4) {
+      uint32_t d0[16], d1[16];
+      tmem_ld16_issue(tmem_base + ((uint32_t)(warp * 32) << 16), d0);
+      tmem_ld16_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + 256, d1);
+      tmem_wait_ld();
+      for (int n = 0; n < 16; ++n) {
+        float e0 = 0.f, e1 = 0.f;
+        for (int k = 0; k < 16; ++k) {
+          const float bb = (float)(((n + 2 * k) % 5) - 2);
+          e0 += (float)(((tid * 3 + k) % 7) - 3) * bb;
+          e1 += (float)(((tid * 5 + 2 * k) % 9) - 4) * bb;
+        }
+        if (__uint_as_float(d0[n]) != e0 * (float)chain) ++bad;
+        if (__uint_as_float(d1[n]) != e1) ++bad;
+        if (r == rounds - 1) { out[tid * 16 + n] = d0[n]; out[128 * 16 + tid * 16 + n] = d1[n]; }
+      }
+      fence_before();
+    }
+    __syncthreads();
+    fence_after();
+  }
+  if (warp < 4) atomicAdd(out + 2 * 128 * 16, bad);
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+
+// Rate of the TMEM-resident-A tile-layer pattern: per repetition one 128-position tile of one layer =
+//   cross pass: 4 x cp.128x256b (hi kb0, hi kb1, lo kb0, lo kb1), 5 taps x 4 MMAs (N = NB, .ashift) + 4 x cp.4x256b
+//   main pass : 2 x cp.128x256b (hi again), 5 taps x 2 MMAs + 2 x cp.4x256b
+// all into ONE accumulator block of NB columns (cross terms first).  `issuers` warps run the pattern concurrently
+// on their own staging / accumulator columns.  flags bit 0: issue the patches; bit 1: .ashift.
+template <int NB>
+__global__ void __launch_bounds__(128, 1) tc_ta_rate_kernel(int reps, int issuers, int flags, long long* __restrict__ cycles) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t plane = 260u * 16u, bplane = 2u * NB * 16u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 64);
+  unsigned char* a_hi = smem_raw + 128;                         // [4 chunks][260][16 B]
+  unsigned char* a_lo = a_hi + 4 * plane;
+  unsigned char* bw = a_lo + 4 * plane;                         // [5 taps * 4 chunks][Wh NB | Wl NB][16 B]
+  unsigned char* patch = bw + kTaps * 4 * bplane;               // [64 B] blocks
+  const uint32_t words = (8 * plane + kTaps * 4 * bplane + 4096) / 4;
+  for (uint32_t i = tid; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(a_hi)[i] = 0x3c003c00u + (i & 63u);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  if (warp < issuers) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t D = base_u + (uint32_t)warp * 64u, S = base_u + 256u + (uint32_t)warp * 32u;
+    const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo), b0 = smem_u32(bw), pt = smem_u32(patch);
+    const uint32_t idesc = instr_desc_f16(128, NB);
+    const bool do_patch = flags & 1, ash = flags & 2;
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+        tc_cp(S + 0, smem_desc(ahi, plane, 128), 0);
+        tc_cp(S + 8, smem_desc(ahi + 2 * plane, plane, 128), 0);
+        tc_cp(S + 16, smem_desc(alo, plane, 128), 0);
+        tc_cp(S + 24, smem_desc(alo + 2 * plane, plane, 128), 0);
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+          const bool sh = ash && k < kTaps - 1;
+          const uint64_t wh0 = smem_desc(b0 + (k * 4 + 0) * bplane, bplane, 128), wh1 = smem_desc(b0 + (k * 4 + 2) * bplane, bplane, 128);
+          const uint64_t wl0 = smem_desc(b0 + (k * 4 + 0) * bplane + NB * 16, bplane, 128),
+                         wl1 = smem_desc(b0 + (k * 4 + 2) * bplane + NB * 16, bplane, 128);
+          mma_f16_ta(D, S + 0, wl0, idesc, k ? 1u : 0u, sh);
+          mma_f16_ta(D, S + 8, wl1, idesc, 1u, sh);
+          mma_f16_ta(D, S + 16, wh0, idesc, 1u, sh);
+          mma_f16_ta(D, S + 24, wh1, idesc, 1u, sh);
+          if (do_patch && k < kTaps - 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tc_cp(S + 8 * q + (31u << 16), smem_desc(pt + (k * 4 + q) * 128, 64, 128), 1);
+          }
+        }
+        tc_cp(S + 0, smem_desc(ahi, plane, 128), 0);
+        tc_cp(S + 8, smem_desc(ahi + 2 * plane, plane, 128), 0);
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+          const bool sh = ash && k < kTaps - 1;
+          const uint64_t wh0 = smem_desc(b0 + (k * 4 + 0) * bplane, bplane, 128), wh1 = smem_desc(b0 + (k * 4 + 2) * bplane, bplane, 128);
+          mma_f16_ta(D, S + 0, wh0, idesc, 1u, sh);
+          mma_f16_ta(D, S + 8, wh1, idesc, 1u, sh);
+          if (do_patch && k < kTaps - 1) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) tc_cp(S + 8 * q + (31u << 16), smem_desc(pt + (16 + k * 2 + q) * 128, 64, 128), 1);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (elect_one()) mma_commit(&bars[warp]);
+    __syncwarp();
+    mbar_wait_guarded(&bars[warp], 0);
+    if ((tid & 31) == 0) cycles[blockIdx.x * 4 + warp] = clock64() - t0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------
 // MMA issue-rate microbenchmark (debug): one warp issues reps x 20 (tap, ci-block) steps on planes of
 // arbitrary data; the CTA measures the clocks until tcgen05.commit fires.  Per step up to two MMAs:
@@ -448,6 +730,59 @@ int ddd1d_debug_tc_overlap(int device, int mode, int reps, int iters, int blocks
   CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
   CUDA_TRY(nullptr, cudaFree(d));
   CUDA_TRY(nullptr, cudaFree(sink));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_shift_probe(int device, unsigned int* out_host) {
+  if (!out_host) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  unsigned int* d = nullptr;
+  const size_t n = (size_t)10 * 128 * 16;
+  CUDA_TRY(nullptr, cudaMalloc(&d, n * sizeof(unsigned int)));
+  CUDA_TRY(nullptr, cudaMemset(d, 0xee, n * sizeof(unsigned int)));
+  const int smem = 128 + 4 * 160 * 16 + 2 * 16 * 16 + 256;
+  tc::tc_shift_probe_kernel<<<1, 160, smem>>>(d);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaDeviceSynchronize());
+  CUDA_TRY(nullptr, cudaMemcpy(out_host, d, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_war_probe(int device, int chain, int rounds, unsigned int* out_host) {
+  if (!out_host || chain < 1 || rounds < 1) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  unsigned int* d = nullptr;
+  const size_t n = (size_t)2 * 128 * 16 + 1;
+  CUDA_TRY(nullptr, cudaMalloc(&d, n * sizeof(unsigned int)));
+  CUDA_TRY(nullptr, cudaMemset(d, 0, n * sizeof(unsigned int)));
+  const int smem = 128 + 4 * 128 * 16 + 2 * 256 * 16 + 256;
+  tc::tc_war_probe_kernel<<<1, 160, smem>>>(d, chain, rounds);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaDeviceSynchronize());
+  CUDA_TRY(nullptr, cudaMemcpy(out_host, d, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_ta_rate(int device, int nb, int reps, int issuers, int flags, int blocks, long long* cycles_host) {
+  if (reps < 1 || blocks < 1 || issuers < 1 || issuers > 4 || !cycles_host || (nb != 16 && nb != 32)) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  long long* d = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, (size_t)blocks * 4 * sizeof(long long)));
+  CUDA_TRY(nullptr, cudaMemset(d, 0, (size_t)blocks * 4 * sizeof(long long)));
+  const int smem = 128 + 8 * 260 * 16 + tc::kTaps * 4 * 2 * nb * 16 + 4096 + 256;
+  if (nb == 32) {
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_ta_rate_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::tc_ta_rate_kernel<32><<<blocks, 128, smem>>>(reps, issuers, flags, d);
+  } else {
+    CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_ta_rate_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc::tc_ta_rate_kernel<16><<<blocks, 128, smem>>>(reps, issuers, flags, d);
+  }
+  CUDA_TRY(nullptr, cudaGetLastError());
+  CUDA_TRY(nullptr, cudaDeviceSynchronize());
+  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
   return DDD1D_OK;
 }
 

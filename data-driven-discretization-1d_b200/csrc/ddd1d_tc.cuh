@@ -74,6 +74,10 @@ struct TcParams {
   alignas(16) float bl[kF];         //         folded last layer
 };
 
+#ifndef DDD1D_TC_SPLIT_REQ
+#define DDD1D_TC_SPLIT_REQ 0       // 1: request a layer per ci-block (measured: correct, 2.5 % slower at C2)
+#endif
+
 // SL_: rows ("slots") a team keeps in flight.  2: every slot owns a TMEM accumulator block.  3: the team's slots
 // share its TWO blocks as a pool (a block is only needed from a layer's request to the tcgen05.ld of its epilogue),
 // so a slot has two turns of the other slots between a request and the need for its result instead of one.
@@ -100,7 +104,16 @@ struct Geo {
   static constexpr uint32_t SLOT_BYTES = ((PLANES * PLANE + 127) / 128) * 128;
   static constexpr uint32_t BH_BYTES = kTaps * 4 * 64 * 16;                           // hidden B planes [20][Wh 32 | Wl 32][16 B]
   static constexpr uint32_t BL_BYTES = kTaps * 4 * 2 * NL * 16;
-  static constexpr uint32_t OFF_BAR = 0, OFF_TMEM = 192, OFF_BLOB = 256;
+  // Split requests: a layer's MMAs over the first ci-block (chunk planes 0, 1) are requested as soon as those
+  // planes are stored, half a phase before the rest, so only half a layer is still to run when the phase ends.
+  static constexpr bool SPLIT = DDD1D_TC_SPLIT_REQ != 0;
+  static constexpr int REQS = SPLIT ? 2 : 1;          // request barriers per slot (one per ci-block)
+  // mbarriers: [0] blob copy | [BAR_REQ + kb * TS + ts] "planes of ci-block kb stored" (one arrival per team warp)
+  // | [BAR_DONE + blk * TILES + m] "tile's MMAs done" | pool only: [BAR_READ + blk] "block read"
+  static constexpr int BAR_REQ = 1, BAR_DONE = BAR_REQ + REQS * TS, BAR_READ = BAR_DONE + BLOCKS * TILES;
+  static constexpr int NBARS = BAR_READ + (SL == 3 ? BLOCKS : 0);
+  static constexpr uint32_t OFF_BAR = 0, OFF_TMEM = 240, OFF_BLOB = 256;
+  static_assert(NBARS * 8 <= (int)OFF_TMEM, "mbarriers overlap the TMEM address slot");
   static constexpr uint32_t OFF_SLOTS = OFF_BLOB + BH_BYTES + BL_BYTES;
   static constexpr uint32_t SMEM = OFF_SLOTS + TS * SLOT_BYTES;
   static constexpr int COLS = PREC == 1 ? 32 : 64;    // TMEM columns of one tile's accumulator block
@@ -193,6 +206,33 @@ __device__ __forceinline__ void issue_tile(uint32_t a_hi, uint32_t a_lo, uint32_
           mma_f16_ab(d, ah0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_wide, acc);        // hi * [Wh | Wl] -> main | cross
           if (G::PREC == 3) mma_f16_ab(d + NB, al0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_narrow, 1u);   // lo * Wh -> cross
         }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// The same for one ci-block kb (run-time: one copy of the code serves both halves of a split request): the five
+// taps of K chunk pair kb; the very first MMA of the layer (kb = 0, tap 0) overwrites the accumulators.
+template <class G, int NB>
+__device__ __forceinline__ void issue_tile_half(uint32_t a_hi, uint32_t a_lo, uint32_t b, uint32_t d, uint32_t kb) {
+  constexpr uint32_t plane16 = G::PLANE >> 4, bplane16 = (2u * NB * 16u) >> 4;
+  const uint32_t desc_hi = (G::SBO >> 4) | (1u << 14);
+  const uint32_t bdesc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t ah0 = ((a_hi + 2u * kb * plane16) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t al0 = ((a_lo + 2u * kb * plane16) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t b0 = ((b + 2u * kb * bplane16) & 0x3FFFu) | (bplane16 << 16);
+  const uint32_t idesc_wide = instr_desc_f16(128, 2 * NB), idesc_narrow = instr_desc_f16(128, NB);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+      const uint32_t ao = (uint32_t)k, bo = (uint32_t)(k * 4) * bplane16;
+      const uint32_t acc = k == 0 ? kb : 1u;
+      if (G::PREC == 1) {
+        mma_f16_ab(d, ah0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_narrow, acc);
+      } else {
+        mma_f16_ab(d, ah0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_wide, acc);
+        if (G::PREC == 3) mma_f16_ab(d + NB, al0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_narrow, 1u);
       }
     }
   }
@@ -501,16 +541,17 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler (role branches, uniform registers)
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw + G::OFF_BAR);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + G::OFF_TMEM);
-  // bars[0] blob copy | [1 + ts] "planes stored" (one arrival per team warp) | [1 + TS + blk * TILES + m] "tile's
-  // MMAs done" (blk = ts with two slots per team) | pool only: [1 + TS + BLOCKS * TILES + blk] "block read"
-  // (one arrival per team warp: the epilogue has its accumulators in registers, the block may be overwritten)
+  // barrier map: Geo (blk = ts with two slots per team; "block read": one arrival per team warp once the epilogue
+  // has its accumulators in registers, the block may be overwritten)
+  constexpr bool SPLIT = G::SPLIT;
+  constexpr int BAR_REQ = G::BAR_REQ, BAR_DONE = G::BAR_DONE, BAR_READ = G::BAR_READ;
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
-    for (int t = 0; t < TS; ++t) mbar_init(&bars[1 + t], (uint32_t)G::TEAM_WARPS);
-    for (int t = 0; t < BLOCKS * TILES; ++t) mbar_init(&bars[1 + TS + t], 1);
+    for (int t = 0; t < G::REQS * TS; ++t) mbar_init(&bars[BAR_REQ + t], (uint32_t)G::TEAM_WARPS);
+    for (int t = 0; t < BLOCKS * TILES; ++t) mbar_init(&bars[BAR_DONE + t], 1);
     if (POOL)
-      for (int t = 0; t < BLOCKS; ++t) mbar_init(&bars[1 + TS + BLOCKS * TILES + t], (uint32_t)G::TEAM_WARPS);
+      for (int t = 0; t < BLOCKS; ++t) mbar_init(&bars[BAR_READ + t], (uint32_t)G::TEAM_WARPS);
     mbar_fence_init();
   }
   __syncthreads();
@@ -554,12 +595,33 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
               const int ts = team * SL + q;
               const int blk = team * 2 + (int)(rq & 1u);
               const uint32_t use = rq >> 1;
+              const uint32_t slot16 = (smem_s + G::OFF_SLOTS + (uint32_t)ts * G::SLOT_BYTES) >> 4;
+              if constexpr (SPLIT) {
+#pragma unroll 1
+                for (uint32_t kb = 0; kb < 2; ++kb) {
+                  if (!(P.debug & 64)) {
+                    mbar_wait_guarded(&bars[BAR_REQ + kb * TS + ts], parity);
+                    if (kb == 0 && use >= 1u) mbar_wait_guarded(&bars[BAR_READ + blk], (use - 1u) & 1u);
+                  }
+                  fence_after();
+#pragma unroll 1
+                  for (int m = 0; m < TILES; ++m) {
+                    const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
+                    const uint32_t d = tmem_u + (uint32_t)((blk * TILES + m) * G::COLS);
+                    if (!(P.debug & 1)) {
+                      if (layer < nhid) issue_tile_half<G, 32>(a_hi, a_lo, bh16, d, kb);
+                      else issue_tile_half<G, NL>(a_hi, a_lo, bl16, d, kb);
+                    }
+                    if (kb == 1 && elect_one()) mma_commit(&bars[BAR_DONE + blk * TILES + m]);
+                    __syncwarp();
+                  }
+                }
+              } else {
               if (!(P.debug & 64)) {
-                mbar_wait_guarded(&bars[1 + ts], parity);
-                if (use >= 1u) mbar_wait_guarded(&bars[1 + TS + BLOCKS * TILES + blk], (use - 1u) & 1u);
+                mbar_wait_guarded(&bars[BAR_REQ + ts], parity);
+                if (use >= 1u) mbar_wait_guarded(&bars[BAR_READ + blk], (use - 1u) & 1u);
               }
               fence_after();
-              const uint32_t slot16 = (smem_s + G::OFF_SLOTS + (uint32_t)ts * G::SLOT_BYTES) >> 4;
 #pragma unroll 1
               for (int m = 0; m < TILES; ++m) {
                 const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
@@ -568,8 +630,9 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
                   if (layer < nhid) issue_tile<G, 32>(a_hi, a_lo, bh16, d);
                   else issue_tile<G, NL>(a_hi, a_lo, bl16, d);
                 }
-                if (elect_one()) mma_commit(&bars[1 + TS + blk * TILES + m]);
+                if (elect_one()) mma_commit(&bars[BAR_DONE + blk * TILES + m]);
                 __syncwarp();
+              }
               }
               ++rq;
             }
@@ -590,9 +653,27 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           for (int q = 0; q < G::SPI; ++q) {              // rolled: one copy of the issue code per layer kind
             const int ts = ts0 + q;
             if ((ts & 1) >= nslots) continue;
-            if (!(P.debug & 64)) mbar_wait_guarded(&bars[1 + ts], parity);
-            fence_after();
             const uint32_t slot16 = (smem_s + G::OFF_SLOTS + (uint32_t)ts * G::SLOT_BYTES) >> 4;
+            if constexpr (SPLIT) {
+#pragma unroll 1
+              for (uint32_t kb = 0; kb < 2; ++kb) {           // first ci-block as soon as its planes are stored
+                if (!(P.debug & 64)) mbar_wait_guarded(&bars[BAR_REQ + kb * TS + ts], parity);
+                fence_after();
+#pragma unroll 1
+                for (int m = 0; m < TILES; ++m) {
+                  const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
+                  const uint32_t d = tmem_u + (uint32_t)((ts * TILES + m) * G::COLS);
+                  if (!(P.debug & 1)) {
+                    if (layer < nhid) issue_tile_half<G, 32>(a_hi, a_lo, bh16, d, kb);
+                    else issue_tile_half<G, NL>(a_hi, a_lo, bl16, d, kb);
+                  }
+                  if (kb == 1 && elect_one()) mma_commit(&bars[BAR_DONE + ts * TILES + m]);
+                  __syncwarp();
+                }
+              }
+            } else {
+            if (!(P.debug & 64)) mbar_wait_guarded(&bars[BAR_REQ + ts], parity);
+            fence_after();
 #pragma unroll 1
             for (int m = 0; m < TILES; ++m) {
               const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
@@ -601,8 +682,9 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
                 if (layer < nhid) issue_tile<G, 32>(a_hi, a_lo, bh16, d);
                 else issue_tile<G, NL>(a_hi, a_lo, bl16, d);
               }
-              if (elect_one()) mma_commit(&bars[1 + TS + ts * TILES + m]);
+              if (elect_one()) mma_commit(&bars[BAR_DONE + ts * TILES + m]);
               __syncwarp();
+            }
             }
           }
           parity ^= 1u;
@@ -635,10 +717,10 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     const int blk_a = team * 2;                         // ... and first accumulator block (= slot with two slots per team)
     unsigned char* const mine = smem_raw + G::OFF_SLOTS + (uint32_t)ts_a * G::SLOT_BYTES + plane_pos<G>(p);
     float* const sc0 = P.scratch + ((size_t)blockIdx.x * TS + ts_a) * G::SC_STRIDE;
-    uint64_t* const req0 = &bars[1 + ts_a];
-    uint64_t* const done0 = &bars[1 + TS + blk_a * TILES + tile];
-    uint64_t* const done_nb0 = &bars[1 + TS + blk_a * TILES + (nb_tile < 0 ? tile : nb_tile)];
-    uint64_t* const read0 = &bars[1 + TS + BLOCKS * TILES + blk_a];      // pool: "block read"
+    uint64_t* const req0 = &bars[BAR_REQ + ts_a];            // ci-block 1 of a split request: + TS
+    uint64_t* const done0 = &bars[BAR_DONE + blk_a * TILES + tile];
+    uint64_t* const done_nb0 = &bars[BAR_DONE + blk_a * TILES + (nb_tile < 0 ? tile : nb_tile)];
+    uint64_t* const read0 = &bars[BAR_READ + blk_a];         // pool: "block read"
     const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((blk_a * TILES + tile) * G::COLS);
     uint32_t cq = 0;      // pool: requests of this team consumed so far; request cq sits in block cq & 1, use cq >> 1
     const float* const fbasis_x = P.fbasis + x;         // this point's column of the forcing basis (L1 resident)
@@ -857,10 +939,15 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             for (int i = 0; i < 4; ++i) h[i] = ffma2(u2, pair_at(P.w1, k * kF + 8 * c8 + 2 * i), h[i]);
           }
           store_chunk8<G>(my, c8, copy_off, has_copy, h);        // (ReLU inside the conversion)
+          if (SPLIT && c8 == 1) {                                // the first ci-block's planes are complete
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(req0 + sl);
+          }
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(req0 + sl);
+        if (lane == 0) mbar_arrive(req0 + (SPLIT ? TS : 0) + sl);
         if (forced && s == 0 && W.op == OP_INTEGRATE && step + 1 < nsteps) {
           // Forcing amplitudes of the NEXT step, off the critical path (the MMAs just requested are running).
           // One warp per (row, stage): one forcing term per lane, mode amplitudes by warp sums.  Three sets
@@ -891,6 +978,35 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         if (!nowait) mbar_wait_spin(done0 + blk * TILES, dpar);
         fence_after();
         if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + blk * TILES, dpar);
+        if constexpr (SPLIT) {
+          // The last layer's first ci-block is requested after half of the planes: its MMAs overwrite this block,
+          // so all 32 (+ 32) accumulator columns are in registers before the first request.
+          float2 acc[2][8];
+          tmem_read_pairs<PREC>(taddr, taddr + 32, acc[0]);
+          tmem_read_pairs<PREC>(taddr + 16, taddr + 48, acc[1]);
+          fence_before();
+          if (POOL) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(read0 + blk);
+            ++cq;
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float2 h[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 v = ffma2(acc[half][4 * c + i], inv2, pair_at(P.bh, 16 * half + 8 * c + 2 * i));
+                h[i] = fmul2(v, s2);                    // relu(v) * s = relu(v * s); the conversion clamps
+              }
+              store_chunk8<G>(my, 2 * half + c, copy_off, has_copy, h);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(req0 + half * TS + sl);
+          }
+        } else {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {            // 16 channels at a time keeps the register peak low
           float2 acc[8];
@@ -916,6 +1032,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(req0 + sl);
+        }
       };
 
       for (int step = 0; step < nsteps; ++step) {

@@ -20,6 +20,15 @@ int ddd1d_debug_tc_rate(int device, int variant, int reps, int blocks, long long
  * 7 LDS.128, 8 STS.128).
  * cycles_host[2*b] = clocks of the MMA stream, cycles_host[2*b + 1] = clocks of the CUDA-core stream. */
 int ddd1d_debug_tc_overlap(int device, int mode, int reps, int iters, int blocks, long long* cycles_host);
+/* TMEM-resident A operand probe (tcgen05.cp 128x256b / 4x256b, tcgen05.shift.down, tcgen05.mma with A in TMEM,
+ * .ashift): raw TMEM dumps after every step, out_host uint32 [10][128][16] (scripts/tc_shift_probe.py). */
+int ddd1d_debug_tc_shift_probe(int device, unsigned int* out_host);
+/* Write-after-read stress of the TMEM A operand: `chain` MMAs read A, a tcgen05.cp overwrites it, one more MMA reads
+ * the new rows; out_host uint32 [2][128][16] + 1 (mismatch count over `rounds` repetitions). */
+int ddd1d_debug_tc_war_probe(int device, int chain, int rounds, unsigned int* out_host);
+/* Rate of the TMEM-resident-A tile-layer pattern (6 x cp.128x256b, 30 MMAs of N = nb with .ashift, 24 x cp.4x256b):
+ * cycles_host[4 * block + issuer] = clocks for `reps` tile-layers.  flags bit 0: patches, bit 1: .ashift. */
+int ddd1d_debug_tc_ta_rate(int device, int nb, int reps, int issuers, int flags, int blocks, long long* cycles_host);
 #ifdef __cplusplus
 }
 #endif
