@@ -51,7 +51,7 @@ namespace ddd1d {
 namespace tc {
 
 constexpr int kFsStride = 2 * kMaxModes;     // forcing mode amplitudes per RK stage: [sine 0..7 | cosine 0..7]
-constexpr int kFsBuffers = 3;                // amplitude sets in rotation: written one step ahead of their use
+constexpr int kFsBuffers = 4;                // amplitude sets in rotation (three are needed: written one step ahead of their use; four makes the index a mask)
 constexpr int kFsWords = kFsBuffers * kMaxStages * kFsStride;
 constexpr int kMaxRpt = 4;
 
@@ -511,20 +511,23 @@ __device__ __forceinline__ void slot_put(SlotSet<3>& s, int sl, float SlotState:
 #define DDD1D_SLOT_GET(SS, sl, f) slot_get(SS, sl, &SlotState::f)
 #define DDD1D_SLOT_PUT(SS, sl, f, v) slot_put(SS, sl, &SlotState::f, v)
 
-// OP_COEF export of the last epilogue (per-call parity hook, not on the integration path): sixteen window
-// columns starting at column q0 of one grid point
-static __device__ __noinline__ void export_coefficients(const TcParams& P, const Work& W, const float (&c16)[16], int q0,
-                                                        size_t point) {
-  for (int i = 0; i < 16; ++i) {
-    const int q = q0 + i, d = q / kWin, slot = q % kWin - P.wshift;
-    if (d < P.D && slot >= 0 && slot < P.S) W.out[(point * P.D + d) * P.S + slot] = c16[i];
-  }
+// OP_COEF export of the last epilogue (per-call parity hook, not on the integration path): window column q of one
+// grid point.  One value per call, so that the caller's sixteen columns stay in registers (an array argument put
+// them on the stack of every right-hand side, export or not).
+static __device__ __noinline__ void export_coefficient(const TcParams& P, const Work& W, float c, int q, size_t point) {
+  const int d = q / kWin, slot = q % kWin - P.wshift;
+  if (d < P.D && slot >= 0 && slot < P.S) W.out[(point * P.D + d) * P.S + slot] = c;
 }
 
-// OP_DERIV export (per-call parity hook): out of line, the integration loop has to stay small
-static __device__ __noinline__ void export_derivatives(const TcParams& P, const Work& W, const float (&dv)[kMaxD],
-                                                       size_t point) {
-  for (int d = 0; d < P.D; ++d) W.out[point * P.D + d] = dv[d];
+// OP_DERIV export (per-call parity hook): out of line, the integration loop has to stay small; by value, so that
+// the derivatives stay in registers
+static __device__ __noinline__ void export_derivatives(const TcParams& P, const Work& W, float d0, float d1, float d2,
+                                                       float d3, size_t point) {
+  static_assert(kMaxD == 4, "one argument per derivative");
+  W.out[point * P.D] = d0;
+  if (P.D > 1) W.out[point * P.D + 1] = d1;
+  if (P.D > 2) W.out[point * P.D + 2] = d2;
+  if (P.D > 3) W.out[point * P.D + 3] = d3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -821,7 +824,10 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             c16[i] = fmaf(i & 1 ? v[i >> 1].y : v[i >> 1].x, inv_last, P.bl[q]);
             if (q < kMaxD * kWin) dv[q / kWin] = fmaf(c16[i], u7[q % kWin], dv[q / kWin]);
           }
-          if (W.op == OP_COEF && live) export_coefficients(P, W, c16, 16 * half, (size_t)row * N + x);
+          if (W.op == OP_COEF && live) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) export_coefficient(P, W, c16[i], 16 * half + i, (size_t)row * N + x);
+          }
         }
         fence_before();
         if constexpr (POOL) {                     // the block may be overwritten: its next request can be served
@@ -830,7 +836,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           ++cq;
         }
         if (!fast_op) {
-          if (W.op == OP_DERIV && live) export_derivatives(P, W, dv, (size_t)row * N + x);
+          if (W.op == OP_DERIV && live) export_derivatives(P, W, dv[0], dv[1], dv[2], dv[3], (size_t)row * N + x);
           return;
         }
         float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
