@@ -294,6 +294,7 @@ int finalize_tc(ddd1d_handle* h) {
     }
   }
   T.eq = h->P.eq; T.D = D; T.S = c.stencil_size; T.wshift = 3 - (c.stencil_size / 2);
+  T.plain_burgers = T.eq == EQ_BURGERS; T.plain_kdv = T.eq == EQ_KDV; T.plain_ks = T.eq == EQ_KS;
   T.M = h->P.M; T.P = h->P.P; T.fcap = h->P.fcap;
   T.sigma = h->P.sigma; T.eta = h->P.eta; T.inv_dx = h->P.inv_dx;
   T.fparams = h->P.fparams; T.fbasis = h->P.fbasis;
@@ -640,6 +641,7 @@ int launch(ddd1d_handle* h, Work& W, void* stream) {
     }
   }
   if (use_tc(h) && W.op != OP_ADAPTIVE) {
+    W.integrating = W.op == OP_INTEGRATE;
     h->tc_entry.launch(h->Ptc, W, make_tableau(W.scheme), tc_grid(h, W.batch), st);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;

@@ -72,6 +72,8 @@ struct Params {
 
 struct Work {
   int op, batch, sample_offset;
+  int integrating;     // op == OP_INTEGRATE as its own field (tensor engine: a test of `op` in the step loop joins the
+                       // per-call ops' tests in one jump table; this one is a plain predicate)
   const float* u;      // [batch][N] (or null when u64 is given)
   const double* u64;
   float* out;          // rhs [batch][N] | coef [batch][N][D][S] | deriv [batch][N][D]

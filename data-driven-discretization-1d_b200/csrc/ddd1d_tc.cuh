@@ -58,6 +58,8 @@ constexpr int kMaxRpt = 4;
 // Everything the kernel reads that is not a tensor-pipe operand: kernel parameter = constant bank.
 struct TcParams {
   int eq, D, S, wshift, nhid;       // nhid: tensor layers between the first and the last conv (0 | 1)
+  int plain_burgers, plain_kdv, plain_ks;   // eq as three flags: the common forms are tested one by one, a switch over
+                                            // eq compiles to a jump table (two dependent constant loads) per right-hand side
   int M, P, fcap;                   // forcing: modes, terms per sample, samples set
   int debug;                        // TIMING EXPERIMENTS ONLY (DDD1D_TC_DEBUG): bit 0 no MMAs, bit 2 teams do not wait
                                     // for their MMAs (garbage results), bit 6 MMA stream alone
@@ -477,6 +479,8 @@ struct SlotState {
   // floats yh + yl with yh = float(yh + yl): ~48 significant bits and no float64 instruction in the loop
   // (conversions to / from float64 run at 16 lanes per clock per SM).
   float yh, yl;
+  // Stage derivatives of the step in progress, newest first: after stage s, k0 = k_s, k1 = k_{s-1}, ...  (they rotate
+  // on every stage, so nothing dispatches on the stage index; the tableau rows are fetched in the same order)
   float k0, k1, k2, k3;
   float umax;        // verified bound on the slot's max |u / sigma|; < 0: not calibrated yet
 };
@@ -706,6 +710,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     const bool cons = eq_conservative(P.eq);
     const bool forced = eq_forced(P.eq) && P.P > 0 && (W.op == OP_RHS || W.op == OP_INTEGRATE);
     const bool fast_op = W.op == OP_RHS || W.op == OP_INTEGRATE;
+    const bool integrating = W.integrating != 0;       // == (W.op == OP_INTEGRATE), see Work
     const bool nowait = (P.debug & 4) != 0;
     // halo duties: the stage row's 3-point halo (scratch) and the planes' halo copies
     const bool halo_warp = RPT > 1 || warp_in_team == 0 || warp_in_team == G::TEAM_WARPS - 1;
@@ -767,7 +772,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
       int prev_step = 0, prev_s = 0;
 
       // ---- phase 2 (+ the Runge-Kutta update after the last stage) of right-hand side (fstep, fs) ----
-      auto finish = [&](int sl, int fstep, int fs, uint32_t fpar) {
+      // snap: index of the snapshot this right-hand side completes (-1: none)
+      auto finish = [&](int sl, int fstep, int fs, uint32_t fpar, int snap) {
         float* const sc = sc0 + sl * G::SC_STRIDE;
         const float* const rowbuf = sc + G::SC_ROWS + (fpar * 2u * RPT + rr) * G::ROWBUF;
         const int row = (unit0 + sl * total_teams) * RPT + rr;
@@ -824,7 +830,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             c16[i] = fmaf(i & 1 ? v[i >> 1].y : v[i >> 1].x, inv_last, P.bl[q]);
             if (q < kMaxD * kWin) dv[q / kWin] = fmaf(c16[i], u7[q % kWin], dv[q / kWin]);
           }
-          if (W.op == OP_COEF && live) {
+          if (!integrating && W.op == OP_COEF && live) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) export_coefficient(P, W, c16[i], 16 * half + i, (size_t)row * N + x);
           }
@@ -835,11 +841,15 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           if (lane == 0) mbar_arrive(read0 + blk);
           ++cq;
         }
-        if (!fast_op) {
+        if (!integrating && !fast_op) {
           if (W.op == OP_DERIV && live) export_derivatives(P, W, dv[0], dv[1], dv[2], dv[3], (size_t)row * N + x);
           return;
         }
-        float r = equation_point(P.eq, u7[kHalo], dv, P.eta);
+        float r;                      // equations.py:269-587, op by op like the float32 graph (equation_point)
+        if (P.plain_burgers) r = __fsub_rn(__fmul_rn(P.eta, dv[1]), __fmul_rn(u7[kHalo], dv[0]));
+        else if (P.plain_kdv) r = __fsub_rn(__fmul_rn(__fmul_rn(-6.f, u7[kHalo]), dv[0]), dv[1]);
+        else if (P.plain_ks) r = __fsub_rn(__fsub_rn(__fmul_rn(-u7[kHalo], dv[0]), dv[2]), dv[1]);
+        else r = equation_point(P.eq, u7[kHalo], dv, P.eta);
         if (cons) {
           float* const flux = sc + G::SC_FLUX;
           flux[p] = r;
@@ -848,24 +858,30 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           r = -__fmul_rn(P.inv_dx, __fsub_rn(fwd, r));
         }
         if (forced) r = __fadd_rn(r, f);
-        if (W.op == OP_RHS) {
+        if (!integrating) {           // OP_RHS
           if (live) {
             if (W.out64) W.out64[(size_t)row * N + x] = (double)r;
             else W.out[(size_t)row * N + x] = r;
           }
           return;
         }
-        if (fs == 0) DDD1D_SLOT_PUT(SS, sl, k0, r);
-        else if (fs == 1) DDD1D_SLOT_PUT(SS, sl, k1, r);
-        else if (fs == 2) DDD1D_SLOT_PUT(SS, sl, k2, r);
-        else DDD1D_SLOT_PUT(SS, sl, k3, r);
+        // the stage derivatives rotate: newest first
+        const float kn1 = DDD1D_SLOT_GET(SS, sl, k0), kn2 = DDD1D_SLOT_GET(SS, sl, k1), kn3 = DDD1D_SLOT_GET(SS, sl, k2);
+        DDD1D_SLOT_PUT(SS, sl, k3, kn3);
+        DDD1D_SLOT_PUT(SS, sl, k2, kn2);
+        DDD1D_SLOT_PUT(SS, sl, k1, kn1);
+        DDD1D_SLOT_PUT(SS, sl, k0, r);
         if (fs != nstages - 1) return;
         // ---- the step is complete: y += dt * sum b k ----
         // increment dt * b_j * k_j as a float pair: exact products (FMA residual) of the float-float constants,
         // highs summed with TwoSum -- the float64 sum of the reference to ~2^-48
         float ih = 0.f, il = 0.f;
-        const float kk[kMaxStages] = {DDD1D_SLOT_GET(SS, sl, k0), DDD1D_SLOT_GET(SS, sl, k1), DDD1D_SLOT_GET(SS, sl, k2),
-                                      DDD1D_SLOT_GET(SS, sl, k3)};
+        // k_j in stage order: the newest is k_{nstages-1}
+        float kk[kMaxStages];
+        if (nstages == 3) { kk[0] = kn2; kk[1] = kn1; kk[2] = r; kk[3] = 0.f; }
+        else if (nstages == 2) { kk[0] = kn1; kk[1] = r; kk[2] = kk[3] = 0.f; }
+        else if (nstages == 4) { kk[0] = kn3; kk[1] = kn2; kk[2] = kn1; kk[3] = r; }
+        else { kk[0] = r; kk[1] = kk[2] = kk[3] = 0.f; }
 #pragma unroll
         for (int j = 0; j < kMaxStages; ++j) {
           if (j >= nstages) break;
@@ -884,17 +900,22 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         DDD1D_SLOT_PUT(SS, sl, yh, y);
         if (!isfinite(y))       // first step at which the row left the finite range (rare, so an atomic is fine)
           atomicMin(reinterpret_cast<unsigned int*>(sc + G::SC_BAD) + rr, (unsigned int)fstep);
-        if (((fstep + 1) % W.save_every) == 0 && live)
-          W.snaps[((size_t)((fstep + 1) / W.save_every - 1) * W.batch + row) * N + x] = y;
+        if (snap >= 0 && live) W.snaps[((size_t)snap * W.batch + row) * N + x] = y;
       };
 
       // ---- phase 0 of right-hand side (step, s): stage value, exchange, first layer, planes, request ----
-      auto start = [&](int sl, int step, int s, float a0, float a1, float a2) {
+      // aN, aP, aQ: dt * a[s][s-1], a[s][s-2], a[s][s-3] (0 beyond the stage): the tableau row, newest derivative first
+      auto start = [&](int sl, int step, int s, float aN, float aP, float aQ) {
         float* const sc = sc0 + sl * G::SC_STRIDE;
         float* const rowbuf = sc + G::SC_ROWS + (stage_par * 2u * RPT + rr) * G::ROWBUF;   // raw; normalised at + RPT * ROWBUF
         // stage value y + dt * sum a_j k_j rounded to float32 (integrate.py:57-60,71): the increment in float32
         // (its rounding is 1e-7 of an increment that is itself far below half an ulp of y), added low part first
-        const float inc = fmaf(a2, DDD1D_SLOT_GET(SS, sl, k2), fmaf(a1, DDD1D_SLOT_GET(SS, sl, k1), a0 * DDD1D_SLOT_GET(SS, sl, k0)));      // a_j = float(dt * a[s][j]), 0 beyond the stage
+        // sum in stage order (a[s][0] k_0 first), as before the derivatives rotated: at stage 1 the two inner terms are
+        // exact zeros, at stage 2 the innermost one
+        const float inc = s == 1 ? aN * DDD1D_SLOT_GET(SS, sl, k0)
+                        : s == 2 ? fmaf(aN, DDD1D_SLOT_GET(SS, sl, k0), aP * DDD1D_SLOT_GET(SS, sl, k1))
+                                 : fmaf(aN, DDD1D_SLOT_GET(SS, sl, k0),
+                                        fmaf(aP, DDD1D_SLOT_GET(SS, sl, k1), aQ * DDD1D_SLOT_GET(SS, sl, k2)));
         const float yh0 = DDD1D_SLOT_GET(SS, sl, yh);
         const float us = s == 0 ? yh0 : yh0 + (DDD1D_SLOT_GET(SS, sl, yl) + inc);
         const float usn = __fdiv_rn(us, P.sigma);            // model.py:450-451
@@ -908,7 +929,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           // the first step's amplitudes; later steps get theirs one step ahead, after the planes are stored
           const double t0 = W.t0;
           for (int task = warp_in_team; task < RPT * nstages; task += G::TEAM_WARPS) {
-            const int fr = task / nstages, sq = task - fr * nstages;
+            int fr = 0, sq = task;                     // task = fr * nstages + sq without a division
+            if (RPT > 1) while (sq >= nstages) { sq -= nstages; ++fr; }
             const int frow = (unit0 + sl * total_teams) * RPT + fr;
             const float tq = (float)(W.op == OP_INTEGRATE ? t0 + tab.c[sq] * W.dt : W.t0);
             if (frow < W.batch)
@@ -960,7 +982,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           // rotate: set (step + 1) % 3 was last read in step - 2, and every warp that gets here has passed a
           // barrier of step `step`, which no warp reaches before it has finished step - 1.
           for (int task = warp_in_team; task < RPT * nstages; task += G::TEAM_WARPS) {
-            const int fr = task / nstages, sq = task - fr * nstages;
+            int fr = 0, sq = task;
+            if (RPT > 1) while (sq >= nstages) { sq -= nstages; ++fr; }
             const int frow = (unit0 + sl * total_teams) * RPT + fr;
             const float tq = (float)(W.t0 + (double)(step + 1) * W.dt + tab.c[sq] * W.dt);
             if (frow < W.batch)
@@ -1041,14 +1064,21 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
       };
 
+      int save_ctr = 0, snap_idx = 0;      // snapshots: a counter instead of a division per step
       for (int step = 0; step < nsteps; ++step) {
         for (int s = 0; s < nstages; ++s) {
-          // this stage's row of the tableau, fetched once for both slots
-          const float a0 = s > 0 ? W.adt[s][0] : 0.f, a1 = s > 1 ? W.adt[s][1] : 0.f, a2 = s > 2 ? W.adt[s][2] : 0.f;
+          // this stage's row of the tableau, newest derivative first, fetched once for both slots
+          const float aN = s > 0 ? W.adt[s][s - 1] : 0.f, aP = s > 1 ? W.adt[s][s - 2] : 0.f,
+                      aQ = s > 2 ? W.adt[s][s - 3] : 0.f;
+          int snap = -1;
+          if (have_prev && s == 0 && ++save_ctr == W.save_every) {      // the previous right-hand side completed a step
+            save_ctr = 0;
+            snap = snap_idx++;
+          }
 #pragma unroll 1
           for (int sl = 0; sl < nslots; ++sl) {
-            if (have_prev) finish(sl, prev_step, prev_s, stage_par ^ 1u);
-            start(sl, step, s, a0, a1, a2);
+            if (have_prev) finish(sl, prev_step, prev_s, stage_par ^ 1u, snap);
+            start(sl, step, s, aN, aP, aQ);
           }
           if (have_prev) done_parity ^= 1u;
           for (int l = 0; l < nhid; ++l) {
@@ -1064,9 +1094,12 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           stage_par ^= 1u;
         }
       }
+      {
+        const int snap = (W.op == OP_INTEGRATE && ++save_ctr == W.save_every) ? snap_idx : -1;
 #pragma unroll 1
-      for (int sl = 0; sl < nslots; ++sl) {
-        finish(sl, prev_step, prev_s, stage_par ^ 1u);
+        for (int sl = 0; sl < nslots; ++sl) {
+          finish(sl, prev_step, prev_s, stage_par ^ 1u, snap);
+        }
       }
       if (W.op == OP_INTEGRATE && W.first_bad) {
         team_sync(team, TEAM);
