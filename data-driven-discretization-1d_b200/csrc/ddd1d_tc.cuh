@@ -80,6 +80,11 @@ struct TcParams {
 #define DDD1D_TC_SPLIT_REQ 0       // 1: request a layer per ci-block (measured: correct, 2.5 % slower at C2)
 #endif
 
+#ifndef DDD1D_TC_ISSUER_FORCING
+#define DDD1D_TC_ISSUER_FORCING 0  // 1: the issuer warps compute the next step's forcing amplitudes (measured: correct,
+                                   // C2 6.1e9 -> 4.8e9: anything an issuer does between two requests delays the MMA stream)
+#endif
+
 // SL_: rows ("slots") a team keeps in flight.  2: every slot owns a TMEM accumulator block.  3: the team's slots
 // share its TWO blocks as a pool (a block is only needed from a layer's request to the tcgen05.ld of its epilogue),
 // so a slot has two turns of the other slots between a request and the need for its result instead of one.
@@ -113,7 +118,11 @@ struct Geo {
   // mbarriers: [0] blob copy | [BAR_REQ + kb * TS + ts] "planes of ci-block kb stored" (one arrival per team warp)
   // | [BAR_DONE + blk * TILES + m] "tile's MMAs done" | pool only: [BAR_READ + blk] "block read"
   static constexpr int BAR_REQ = 1, BAR_DONE = BAR_REQ + REQS * TS, BAR_READ = BAR_DONE + BLOCKS * TILES;
-  static constexpr int NBARS = BAR_READ + (SL == 3 ? BLOCKS : 0);
+  // AMP (opt-in experiment, off): the forcing amplitudes of the NEXT step computed by the issuer warps instead of
+  // three warps of the team; [BAR_AMP + ts] "next step's amplitudes written" (one arrival per step, by the issuer)
+  static constexpr bool AMP = DDD1D_TC_ISSUER_FORCING != 0 && RPT == 1 && SL == 2;
+  static constexpr int BAR_AMP = BAR_READ + (SL == 3 ? BLOCKS : 0);
+  static constexpr int NBARS = BAR_AMP + (AMP ? TS : 0);
   static constexpr uint32_t OFF_BAR = 0, OFF_TMEM = 240, OFF_BLOB = 256;
   static_assert(NBARS * 8 <= (int)OFF_TMEM, "mbarriers overlap the TMEM address slot");
   static constexpr uint32_t OFF_SLOTS = OFF_BLOB + BH_BYTES + BL_BYTES;
@@ -304,8 +313,12 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
 __device__ __forceinline__ float2 pair_at(const float* table, int i) { return *reinterpret_cast<const float2*>(table + i); }
 
 // mbarrier wait for the hot path: plain try_wait loop; a protocol bug traps after ~2^27 timeouts instead of hanging
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+// (barriers are addressed by their 32-bit shared address, computed once per thread: converting the generic pointer at
+// every wait costs an S2UR and four more instructions in front of each try_wait)
+__device__ __forceinline__ void mbar_arrive_s(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t addr, uint32_t parity) {
   uint32_t spins = 0;
   while (true) {
     uint32_t done;
@@ -395,8 +408,12 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float2 v) {
 
 // relu of eight consecutive channels of one position (four pairs) -> one 16-byte chunk of the hi plane (and of the
 // lo plane)
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// `mine`: 32-bit shared address of the thread's position in the slot's first plane
 template <class G>
-__device__ __forceinline__ void store_chunk8(unsigned char* mine, int c8, int copy_off, bool has_copy,
+__device__ __forceinline__ void store_chunk8(uint32_t mine, int c8, int copy_off, bool has_copy,
                                              const float2 (&v)[4]) {
   uint4 h, l;
   if (G::PREC == 3) {
@@ -410,12 +427,12 @@ __device__ __forceinline__ void store_chunk8(unsigned char* mine, int c8, int co
     h.z = pack_half2_relu(v[2]);
     h.w = pack_half2_relu(v[3]);
   }
-  unsigned char* hp = mine + (uint32_t)c8 * G::PLANE;
-  *reinterpret_cast<uint4*>(hp) = h;
-  if (G::PREC == 3) *reinterpret_cast<uint4*>(hp + 4 * G::PLANE) = l;
+  const uint32_t hp = mine + (uint32_t)c8 * G::PLANE;
+  sts128(hp, h);
+  if (G::PREC == 3) sts128(hp + 4 * G::PLANE, l);
   if (has_copy) {
-    *reinterpret_cast<uint4*>(hp + copy_off) = h;
-    if (G::PREC == 3) *reinterpret_cast<uint4*>(hp + 4 * G::PLANE + copy_off) = l;
+    sts128(hp + copy_off, h);
+    if (G::PREC == 3) sts128(hp + 4 * G::PLANE + copy_off, l);
   }
 }
 
@@ -559,6 +576,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     for (int t = 0; t < BLOCKS * TILES; ++t) mbar_init(&bars[BAR_DONE + t], 1);
     if (POOL)
       for (int t = 0; t < BLOCKS; ++t) mbar_init(&bars[BAR_READ + t], (uint32_t)G::TEAM_WARPS);
+    if (G::AMP)
+      for (int t = 0; t < TS; ++t) mbar_init(&bars[G::BAR_AMP + t], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -650,11 +669,12 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
     } else {
     const int ts0 = issuer * G::SPI;
     const int team = ts0 >> 1;
+    const bool issuer_forcing = eq_forced(P.eq) && P.P > 0 && W.integrating && !(P.debug & 64);
     const int g = blockIdx.x * R + team;
     uint32_t parity = 0;                                       // all served slots flip together
     for (int unit0 = g; unit0 < units; unit0 += 2 * total_teams) {
       const int nslots = unit0 + total_teams < units ? 2 : 1;
-      for (int it = 0; it < nsteps * nstages; ++it) {
+      for (int it = 0, step_i = 0, s_i = 0; it < nsteps * nstages; ++it) {
         for (int layer = 0; layer <= nhid; ++layer) {
 #pragma unroll 1
           for (int q = 0; q < G::SPI; ++q) {              // rolled: one copy of the issue code per layer kind
@@ -693,9 +713,25 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
               __syncwarp();
             }
             }
+            if constexpr (G::AMP) {
+              // With this slot's first layer of (step, stage s) on the pipe: the slot's forcing amplitudes of stage s
+              // of the NEXT step, into the set the team reads a step from now (same expression, same warp-level sums
+              // as the team's own first-step code).  After the last stage the three sets are announced.
+              if (layer == 0 && issuer_forcing && step_i + 1 < nsteps) {
+                const int frow = unit0 + (ts & 1) * total_teams;
+                float* const sc = P.scratch + ((size_t)blockIdx.x * TS + ts) * G::SC_STRIDE;
+                const float tq = (float)(W.t0 + (double)(step_i + 1) * W.dt + tab.c[s_i] * W.dt);
+                forcing_amplitudes_t(P, sc + G::SC_FS + (((step_i + 1) % kFsBuffers) * kMaxStages + s_i) * kFsStride,
+                                     W.sample_offset + frow, tq, lane);
+                __threadfence_block();
+                __syncwarp();
+                if (s_i == nstages - 1 && lane == 0) mbar_arrive(&bars[G::BAR_AMP + ts]);
+              }
+            }
           }
           parity ^= 1u;
         }
+        if (++s_i == nstages) { s_i = 0; ++step_i; }
       }
     }
     }
@@ -723,12 +759,15 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
 
     const int ts_a = team * SL;                         // the team's first slot
     const int blk_a = team * 2;                         // ... and first accumulator block (= slot with two slots per team)
-    unsigned char* const mine = smem_raw + G::OFF_SLOTS + (uint32_t)ts_a * G::SLOT_BYTES + plane_pos<G>(p);
+    const uint32_t mine = smem_s + G::OFF_SLOTS + (uint32_t)ts_a * G::SLOT_BYTES + plane_pos<G>(p);   // shared address
     float* const sc0 = P.scratch + ((size_t)blockIdx.x * TS + ts_a) * G::SC_STRIDE;
-    uint64_t* const req0 = &bars[BAR_REQ + ts_a];            // ci-block 1 of a split request: + TS
-    uint64_t* const done0 = &bars[BAR_DONE + blk_a * TILES + tile];
-    uint64_t* const done_nb0 = &bars[BAR_DONE + blk_a * TILES + (nb_tile < 0 ? tile : nb_tile)];
-    uint64_t* const read0 = &bars[BAR_READ + blk_a];         // pool: "block read"
+    const uint32_t bars_s = smem_u32(bars);
+    const uint32_t req0 = bars_s + 8u * (uint32_t)(BAR_REQ + ts_a);            // ci-block 1 of a split request: + TS
+    const uint32_t done0 = bars_s + 8u * (uint32_t)(BAR_DONE + blk_a * TILES + tile);
+    const uint32_t done_nb0 = bars_s + 8u * (uint32_t)(BAR_DONE + blk_a * TILES + (nb_tile < 0 ? tile : nb_tile));
+    const uint32_t read0 = bars_s + 8u * (uint32_t)(BAR_READ + blk_a);         // pool: "block read"
+    const uint32_t amp0 = bars_s + 8u * (uint32_t)(G::BAR_AMP + ts_a);         // "next step's amplitudes written"
+    uint32_t amp_base = 0;              // arrivals on the slots' amplitude barriers before this unit (their parity)
     const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((blk_a * TILES + tile) * G::COLS);
     uint32_t cq = 0;      // pool: requests of this team consumed so far; request cq sits in block cq & 1, use cq >> 1
     const float* const fbasis_x = P.fbasis + x;         // this point's column of the forcing basis (L1 resident)
@@ -782,6 +821,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
 #pragma unroll
         for (int j = 0; j < kWin; ++j) u7[j] = rowbuf[x + j];
         float f = 0.f;
+        if (G::AMP && forced && integrating && fs == 0 && fstep > 0)      // written by the issuer during step fstep - 1
+          mbar_wait_spin(amp0 + 8u * (uint32_t)sl, (amp_base + (uint32_t)(fstep - 1)) & 1u);
         if (forced) {
           const float* amp = sc + G::SC_FS + rr * kFsWords + ((fstep % kFsBuffers) * kMaxStages + fs) * kFsStride;
           if (P.M <= 4) {
@@ -810,8 +851,8 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         // where the slot's accumulators are: its own block, or (pool) the block its request was dealt
         const int blk = POOL ? (int)(cq & 1u) : sl;
         const uint32_t dpar = POOL ? ((cq >> 1) & 1u) : done_parity;
-        if (!nowait) mbar_wait_spin(done0 + blk * TILES, dpar);
-        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + blk * TILES, dpar);     // before the next stage rewrites the planes
+        if (!nowait) mbar_wait_spin(done0 + 8u * (uint32_t)(blk * TILES), dpar);
+        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + 8u * (uint32_t)(blk * TILES), dpar);     // before the next stage rewrites the planes
         fence_after();
         // window coefficients = accumulators + folded bias, then the stencil dot products (model.py:536-548);
         // sixteen columns at a time keeps the register peak low
@@ -838,7 +879,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         fence_before();
         if constexpr (POOL) {                     // the block may be overwritten: its next request can be served
           __syncwarp();
-          if (lane == 0) mbar_arrive(read0 + blk);
+          if (lane == 0) mbar_arrive_s(read0 + 8u * (uint32_t)blk);
           ++cq;
         }
         if (!integrating && !fast_op) {
@@ -953,7 +994,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         float un[kTaps];
 #pragma unroll
         for (int k = 0; k < kTaps; ++k) un[k] = rowbuf[RPT * G::ROWBUF + x + k + 1] * s_act;
-        unsigned char* const my = mine + sl * G::SLOT_BYTES;
+        const uint32_t my = mine + (uint32_t)sl * G::SLOT_BYTES;
         const float2 s2 = make_float2(s_act, s_act);
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
@@ -970,13 +1011,13 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           if (SPLIT && c8 == 1) {                                // the first ci-block's planes are complete
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(req0 + sl);
+            if (lane == 0) mbar_arrive_s(req0 + 8u * (uint32_t)sl);
           }
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(req0 + (SPLIT ? TS : 0) + sl);
-        if (forced && s == 0 && W.op == OP_INTEGRATE && step + 1 < nsteps) {
+        if (lane == 0) mbar_arrive_s(req0 + 8u * (uint32_t)((SPLIT ? TS : 0) + sl));
+        if (!G::AMP && forced && s == 0 && W.op == OP_INTEGRATE && step + 1 < nsteps) {
           // Forcing amplitudes of the NEXT step, off the critical path (the MMAs just requested are running).
           // One warp per (row, stage): one forcing term per lane, mode amplitudes by warp sums.  Three sets
           // rotate: set (step + 1) % 3 was last read in step - 2, and every warp that gets here has passed a
@@ -1000,13 +1041,13 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         const float inv = pow2_inverse(scale_for(bound1)) * P.inv_sw_hid;
         const float s_act = scale_for(fmaf(P.whabs, bound1, P.bhabs));   // |h2| <= |b2| + sum|W2| max|h1|
         const float2 inv2 = make_float2(inv, inv), s2 = make_float2(s_act, s_act);
-        unsigned char* const my = mine + sl * G::SLOT_BYTES;
+        const uint32_t my = mine + (uint32_t)sl * G::SLOT_BYTES;
         const int blk = POOL ? (int)(cq & 1u) : sl;
         const uint32_t dpar = POOL ? ((cq >> 1) & 1u) : done_parity;
         const uint32_t taddr = taddr0 + (uint32_t)(blk * TILES * G::COLS);
-        if (!nowait) mbar_wait_spin(done0 + blk * TILES, dpar);
+        if (!nowait) mbar_wait_spin(done0 + 8u * (uint32_t)(blk * TILES), dpar);
         fence_after();
-        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + blk * TILES, dpar);
+        if (nb_tile >= 0 && !nowait) mbar_wait_spin(done_nb0 + 8u * (uint32_t)(blk * TILES), dpar);
         if constexpr (SPLIT) {
           // The last layer's first ci-block is requested after half of the planes: its MMAs overwrite this block,
           // so all 32 (+ 32) accumulator columns are in registers before the first request.
@@ -1016,7 +1057,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           fence_before();
           if (POOL) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(read0 + blk);
+            if (lane == 0) mbar_arrive_s(read0 + 8u * (uint32_t)blk);
             ++cq;
           }
 #pragma unroll
@@ -1033,7 +1074,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(req0 + half * TS + sl);
+            if (lane == 0) mbar_arrive_s(req0 + 8u * (uint32_t)(half * TS + sl));
           }
         } else {
 #pragma unroll
@@ -1043,7 +1084,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
           if (POOL && half == 1) {                        // all accumulators are in registers: release the block early
             fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(read0 + blk);
+            if (lane == 0) mbar_arrive_s(read0 + 8u * (uint32_t)blk);
             ++cq;
           }
 #pragma unroll
@@ -1060,20 +1101,20 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(req0 + sl);
+        if (lane == 0) mbar_arrive_s(req0 + 8u * (uint32_t)sl);
         }
       };
 
-      int save_ctr = 0, snap_idx = 0;      // snapshots: a counter instead of a division per step
+      int until_save = W.save_every;       // snapshots: a down-counter; the index is divided out only when one is due
       for (int step = 0; step < nsteps; ++step) {
         for (int s = 0; s < nstages; ++s) {
           // this stage's row of the tableau, newest derivative first, fetched once for both slots
           const float aN = s > 0 ? W.adt[s][s - 1] : 0.f, aP = s > 1 ? W.adt[s][s - 2] : 0.f,
                       aQ = s > 2 ? W.adt[s][s - 3] : 0.f;
           int snap = -1;
-          if (have_prev && s == 0 && ++save_ctr == W.save_every) {      // the previous right-hand side completed a step
-            save_ctr = 0;
-            snap = snap_idx++;
+          if (have_prev && s == 0 && --until_save == 0) {               // the previous right-hand side completed a step
+            until_save = W.save_every;
+            snap = step / W.save_every - 1;                             // `step` steps are complete
           }
 #pragma unroll 1
           for (int sl = 0; sl < nslots; ++sl) {
@@ -1095,7 +1136,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
       }
       {
-        const int snap = (W.op == OP_INTEGRATE && ++save_ctr == W.save_every) ? snap_idx : -1;
+        const int snap = (W.op == OP_INTEGRATE && --until_save == 0) ? nsteps / W.save_every - 1 : -1;
 #pragma unroll 1
         for (int sl = 0; sl < nslots; ++sl) {
           finish(sl, prev_step, prev_s, stage_par ^ 1u, snap);
@@ -1112,6 +1153,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
       }
       team_sync(team, TEAM);       // the next rows reuse the slot regions
+      if (G::AMP && forced && integrating) amp_base += (uint32_t)(nsteps - 1);
     }
   }
   fence_before();
