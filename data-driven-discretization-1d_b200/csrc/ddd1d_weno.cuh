@@ -85,8 +85,11 @@ struct WenoShared {
 
 // EQ: EQ_BURGERS_GOD for the instantiation specialised for BASELINE config 5 (folds equation_point's switch, an
 // indirect branch per point and stage), -1 = read P.eq
+#ifndef DDD1D_WENO_MIN_BLOCKS
+#define DDD1D_WENO_MIN_BLOCKS 2          // CTAs per SM the register budget is set for (A/B builds: 1 = 128 registers)
+#endif
 template <int EQ>
-__global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
+__global__ void __launch_bounds__(512, DDD1D_WENO_MIN_BLOCKS) weno_block_kernel(const __grid_constant__ Params P, const __grid_constant__ Work W,
                                                             const __grid_constant__ Tableau tab) {
   constexpr int PPT = kWenoPpt;
   __shared__ WenoShared sh;
@@ -98,9 +101,11 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
   const float4* const basis4 = reinterpret_cast<const float4*>(P.fbasis + p0);
 
   // window-form stencils of the non-WENO derivative channels (d >= 2), in registers
-  float cf[2][kWin];
+  // (Godunov Burgers has one: u_x.  Its instantiation drops the second row, 7 registers and 7 FFMAs per point.)
+  constexpr int NCF = EQ == EQ_BURGERS_GOD ? 1 : 2;
+  float cf[NCF][kWin];
 #pragma unroll
-  for (int d = 0; d < 2; ++d)
+  for (int d = 0; d < NCF; ++d)
 #pragma unroll
     for (int j = 0; j < kWin; ++j) cf[d][j] = d + 2 < P.D ? __ldg(P.blob + P.st_off + (d + 2) * kWinPad + j) : 0.f;
 
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
     for (int i = 0; i < PPT; ++i) k0[i] = k1[i] = k2[i] = k3[i] = 0.f;
     if (tid == 0) sh.first_bad = 0xffffffffu;
     int first_bad = -1;
-    int save_idx = 0;
+    int save_idx = 0, until_save = W.save_every;       // a down-counter: no division per step
 
     for (int step = 0; step < W.nsteps; ++step) {
       float sn0 = 0.f, cs0 = 0.f;
@@ -211,8 +216,9 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
           float dv[kMaxD];
           dv[0] = weno_left(bt[i], E[i], E[i + 1], E[i + 2], E[i + 3], E[i + 4]);
           dv[1] = weno_right(bt[i + 1], E[i + 1], E[i + 2], E[i + 3], E[i + 4], E[i + 5]);
+          dv[3] = 0.f;
 #pragma unroll
-          for (int d = 0; d < 2; ++d) {
+          for (int d = 0; d < NCF; ++d) {
             float acc = 0.f;                       // constant stencil rows (model.py:99-109, 536-548)
 #pragma unroll
             for (int j = 0; j < kWin; ++j) acc = fmaf(cf[d][j], E[i + j], acc);
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
         par ^= 1u;
       }
       // ---- end of the step: y += dt * sum b k in float-float (the float64 sum of the reference to ~2^-48) ----
-      const bool save = ((step + 1) % W.save_every) == 0;
+      const bool save = --until_save == 0;
       float out[PPT];
 #pragma unroll
       for (int i = 0; i < PPT; ++i) {
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(512, 2) weno_block_kernel(const __grid_constan
         *reinterpret_cast<float4*>(W.snaps + ((size_t)save_idx * W.batch + row) * N + p0) =
             make_float4(out[0], out[1], out[2], out[3]);
         ++save_idx;
+        until_save = W.save_every;
       }
     }
     if (W.first_bad) {
