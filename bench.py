@@ -485,6 +485,23 @@ def run_ours(args):
                         'peak = measured dense bf16/f16 cuBLAS rate (burst; the sustained figure beside it).  The '
                         'FP32-faithful fp16 hi/lo split executes 3x the conv FLOPs on the tensor pipe (hi*Wh, hi*Wl, lo*Wh) '
                         'and streams every operand from shared memory' % fl}
+    # What binds this kernel in practice: the tensor core's operand path.  A tcgen05.mma of M = 128, K = 16 fetches its
+    # 128 x 16 fp16 A tile in 32 clocks of shared-memory wavefronts whatever N is (+ N/4 for B), so the small-N
+    # MMAs of a 32-channel conv cost 32 + N/4 clocks for N/2 clocks of math.  Floor = the measured clocks of one
+    # tile's MMAs per right-hand side, streamed back to back from ONE issuer (profiles/r01/tc_mma_rate.txt; 148
+    # CTAs: same), x the tiles an SM processes per launch / the SM clock sampled during the run.
+    step_clk = {3: {64: 88.2, 32: 79.2}, 2: {64: 48.2, 32: 40.2}, 1: {64: 40.2, 32: 39.2}}      # [prec][2 * NB]: (tap, ci-block) step
+    prec = {'tensor': 3, 'tensor_f16x2': 2, 'tensor_f16': 1}.get(engine, 3)
+    nl = 32 if kind == 'ks' else 16
+    clk_tile_rhs = 10.0 * (step_clk[prec][64] + step_clk[prec][2 * nl])      # one hidden tensor layer + the last layer
+    tiles = batch * max(n, 128) / 128.0 if n >= 128 else batch * n / 128.0   # 128-position tiles in the batch
+    sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+    floor_ms = tiles * 3 * rk / 148.0 * clk_tile_rhs / (sm_mhz * 1e3)
+    roofline['operand_path'] = {
+        'bound': 'tcgen05 shared-memory operand fetch', 'floor_clk_per_tile_rhs': clk_tile_rhs,
+        'achieved_clk_per_tile_rhs': kernel_ms * sm_mhz * 1e3 / (tiles * 3 * rk / 148.0),
+        'floor_ms': floor_ms, 'frac': floor_ms / kernel_ms, 'sm_mhz': sm_mhz,
+        'ncu': 'sm__pipe_tc_cycles_active / l1tex__data_pipe_tc_wavefronts_mem_shared in profiles/r02/tc_*_ncu_full.json'}
   else:
     roofline = dict(hbm)
   roofline.update({'kernel': kernel_name, 'kernel_ms': kernel_ms})

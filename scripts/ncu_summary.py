@@ -10,6 +10,11 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
            'sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
            'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+           # the tensor core with its operand path (the unit the small-N MMAs of this engine keep busy: a 128 x 16
+           # fp16 A tile costs 32 clocks of shared-memory wavefronts whatever N is)
+           'sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed',
+           'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+           'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
            'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed',
            'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed',
            'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed',
