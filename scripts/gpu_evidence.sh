@@ -21,10 +21,12 @@ python bench.py --workload c2s --engine ffma --steps 4 --warmup 3 --rk-steps 50 
 # every launch of the bench command with its device time (cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/launches_c2.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --extra '' > $out/launches_c2.log 2>&1
-prof() {   # name, kernel regex, bench args...
+prof() {   # name, kernel regex, bench args...: capture, summarise on the box (gpurun_out is capped at 64 MiB)
   name=$1; regex=$2; shift 2
-  ncu --set full --clock-control none --import-source on -k regex:$regex -s 3 -c 1 -o $out/prof_$name \
+  ncu --set full --clock-control none --import-source on -k regex:$regex -s 3 -c 1 -o /tmp/prof_$name \
       python bench.py --steps 2 --warmup 3 --no-cpu --extra '' "$@" > $out/prof_$name.log 2>&1
+  python scripts/ncu_summary.py /tmp/prof_$name.ncu-rep $out/${name}_ncu_full.json >> $out/prof_$name.log 2>&1
+  if [ "$name" = tc_c2 ]; then cp /tmp/prof_$name.ncu-rep $out/; fi
 }
 prof tc_c2 tc_row_kernel --workload c2 --rk-steps 20
 prof tc_c3 tc_row_kernel --workload c3 --rk-steps 20
