@@ -83,6 +83,10 @@ _DEBUG_SIGNATURES = {
     'ddd1d_debug_tc_probe': (ctypes.c_int, [ctypes.c_int, _P, _P, _P, ctypes.c_int, _P]),
     'ddd1d_debug_tc_rate': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
     'ddd1d_debug_tc_overlap': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    'ddd1d_debug_tc_shift_probe': (ctypes.c_int, [ctypes.c_int, _P]),
+    'ddd1d_debug_tc_war_probe': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
+    'ddd1d_debug_tc_ta_rate': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, _P]),
 }
 
 
