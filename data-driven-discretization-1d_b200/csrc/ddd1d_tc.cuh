@@ -41,7 +41,14 @@
 //            equation of motion, flux difference, forcing, stage derivative; after the last stage the
 //            Runge-Kutta update and the snapshot.
 // Shared memory holds only what the tensor pipe reads (shared-memory LOADS stall while MMAs stream their
-// operands: profiles/r01/tc_overlap.txt); per-thread state lives in registers (slots are unrolled).
+// operands: profiles/r01/tc_overlap.txt); per-thread state lives in registers.
+//
+// What binds the kernel (profiles/r02/README.md): the tensor core's shared-memory operand fetch.  An MMA of M = 128,
+// K = 16 costs 32 + N/4 clocks of wavefronts for N/2 clocks of math, so the N = 64 + 32 MMAs of a 32-channel conv keep
+// the unit busy 85-93 % of the cycles at 38 % math.  The CUDA-core side has four team warps per scheduler and is
+// bound by dependent-latency chains, not by its instruction count: the step loop therefore has no jump table (the
+// plain equations and `integrating` are predicates of their own), no division, no stack array (per-call exports take
+// values), and the stage derivatives rotate instead of being dispatched on the stage index.
 #pragma once
 #include <type_traits>
 
