@@ -87,6 +87,7 @@ _DEBUG_SIGNATURES = {
     'ddd1d_debug_tc_war_probe': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
     'ddd1d_debug_tc_ta_rate': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_int, _P]),
+    'ddd1d_debug_tc_reuse_rate': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _P]),
 }
 
 

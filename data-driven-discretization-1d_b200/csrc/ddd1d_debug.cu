@@ -403,6 +403,66 @@ __global__ void __launch_bounds__(128, 1) tc_ta_rate_kernel(int reps, int issuer
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+
+// Collector-buffer reuse: clocks per MMA of pairs of fp16 MMAs (M = 128, K = 16, width N) that share an operand.
+//   mode 0: plain pair, different A tiles, same B           (the production order would re-fetch B)
+//   mode 1: tcgen05.mma.ws pair, B kept in collector b0     (fill, then use with the other A tile)
+//   mode 2: plain pair on the same A tile, .collector::a::fill then ::lastuse, different B
+//   mode 3: plain pair on the same A tile without the qualifiers
+template <int N>
+__global__ void __launch_bounds__(128, 1) tc_reuse_rate_kernel(int reps, int mode, long long* __restrict__ cycles) {
+  unsigned char* const smem_raw = dyn_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr uint32_t plane = 260u * 16u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 64);
+  unsigned char* a0 = smem_raw + 128;                  // two tiles: [2 chunks][260][16 B] each
+  unsigned char* a1 = a0 + 2 * plane;
+  unsigned char* bw = a1 + 2 * plane;                  // two B tiles [2 chunks][N rows][16 B]
+  for (uint32_t i = tid; i < (4 * plane + 4 * N * 16) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a0)[i] = 0x3c003c00u + (i & 63u);
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *slot;
+  if (warp == 0) {
+    const uint32_t base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t A0 = smem_desc(smem_u32(a0), plane, 128), A1 = smem_desc(smem_u32(a1), plane, 128);
+    const uint64_t B0 = smem_desc(smem_u32(bw), N * 16, 128), B1 = smem_desc(smem_u32(bw) + 2 * N * 16, N * 16, 128);
+    const uint32_t idesc = instr_desc_f16(128, N);
+    const uint32_t D0 = base_u, D1 = base_u + 256;
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+        if (mode == 0) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(D0), "l"(A0), "l"(B0), "r"(idesc), "r"(1u) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(D1), "l"(A1), "l"(B0), "r"(idesc), "r"(1u) : "memory");
+        } else if (mode == 1) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(D0), "l"(A0), "l"(B0), "r"(idesc), "r"(1u) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(D1), "l"(A1), "l"(B0), "r"(idesc), "r"(1u) : "memory");
+        } else if (mode == 2) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(D0), "l"(A0), "l"(B0), "r"(idesc), "r"(1u) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(D1), "l"(A0), "l"(B1), "r"(idesc), "r"(1u) : "memory");
+        } else {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(D0), "l"(A0), "l"(B0), "r"(idesc), "r"(1u) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(D1), "l"(A0), "l"(B1), "r"(idesc), "r"(1u) : "memory");
+        }
+      }
+    }
+    __syncwarp();
+    if (elect_one()) mma_commit(bar);
+    __syncwarp();
+    mbar_wait_guarded(bar, 0);
+    if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------
 // MMA issue-rate microbenchmark (debug): one warp issues reps x 20 (tap, ci-block) steps on planes of
 // arbitrary data; the CTA measures the clocks until tcgen05.commit fires.  Per step up to two MMAs:
@@ -676,6 +736,15 @@ int run_rate(int reps, int blocks, long long* d) {
   CUDA_TRY(nullptr, cudaGetLastError());
   return DDD1D_OK;
 }
+template <int N>
+int run_reuse_rate(int reps, int mode, long long* d) {
+  const int smem = 128 + 4 * 260 * 16 + 4 * N * 16 + 256;
+  CUDA_TRY(nullptr, cudaFuncSetAttribute(tc::tc_reuse_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc::tc_reuse_rate_kernel<N><<<1, 128, smem>>>(reps, mode, d);
+  CUDA_TRY(nullptr, cudaGetLastError());
+  return DDD1D_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -782,6 +851,24 @@ int ddd1d_debug_tc_ta_rate(int device, int nb, int reps, int issuers, int flags,
   CUDA_TRY(nullptr, cudaGetLastError());
   CUDA_TRY(nullptr, cudaDeviceSynchronize());
   CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, (size_t)blocks * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(nullptr, cudaFree(d));
+  return DDD1D_OK;
+}
+
+int ddd1d_debug_tc_reuse_rate(int device, int n, int mode, int reps, long long* cycles_host) {
+  if (reps < 1 || mode < 0 || mode > 3 || !cycles_host) return fail("bad argument");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  long long* d = nullptr;
+  CUDA_TRY(nullptr, cudaMalloc(&d, sizeof(long long)));
+  int rc = DDD1D_EINVAL;
+  if (n == 32) rc = run_reuse_rate<32>(reps, mode, d);
+  else if (n == 64) rc = run_reuse_rate<64>(reps, mode, d);
+  else if (n == 128) rc = run_reuse_rate<128>(reps, mode, d);
+  else return fail("n must be 32, 64 or 128");
+  if (rc) return rc;
+  const cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e));
+  CUDA_TRY(nullptr, cudaMemcpy(cycles_host, d, sizeof(long long), cudaMemcpyDeviceToHost));
   CUDA_TRY(nullptr, cudaFree(d));
   return DDD1D_OK;
 }

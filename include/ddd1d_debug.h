@@ -29,6 +29,10 @@ int ddd1d_debug_tc_war_probe(int device, int chain, int rounds, unsigned int* ou
 /* Rate of the TMEM-resident-A tile-layer pattern (6 x cp.128x256b, 30 MMAs of N = nb with .ashift, 24 x cp.4x256b):
  * cycles_host[4 * block + issuer] = clocks for `reps` tile-layers.  flags bit 0: patches, bit 1: .ashift. */
 int ddd1d_debug_tc_ta_rate(int device, int nb, int reps, int issuers, int flags, int blocks, long long* cycles_host);
+/* Collector-buffer reuse: clocks for `reps` pairs of fp16 MMAs of width n sharing an operand (mode 0 plain pair with
+ * the same B, 1 tcgen05.mma.ws with B kept in collector b0, 2 same A with .collector::a::fill / ::lastuse, 3 same A
+ * without qualifiers). */
+int ddd1d_debug_tc_reuse_rate(int device, int n, int mode, int reps, long long* cycles_host);
 #ifdef __cplusplus
 }
 #endif
