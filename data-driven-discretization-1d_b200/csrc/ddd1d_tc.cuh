@@ -87,6 +87,12 @@ struct TcParams {
 #define DDD1D_TC_SPLIT_REQ 0       // 1: request a layer per ci-block (measured: correct, 2.5 % slower at C2)
 #endif
 
+#ifndef DDD1D_TC_WS
+#define DDD1D_TC_WS 0              // 1: the wide MMAs of rows of several tiles as tcgen05.mma.ws, B kept in a collector buffer
+                                   // (measured: bit-identical results, C2 -0.9 %, C4 -7 %: tiles finish together instead of
+                                   // one after the other, which costs more than the saved B fetches)
+#endif
+
 #ifndef DDD1D_TC_ISSUER_FORCING
 #define DDD1D_TC_ISSUER_FORCING 0  // 1: the issuer warps compute the next step's forcing amplitudes (measured: correct,
                                    // C2 6.1e9 -> 4.8e9: anything an issuer does between two requests delays the MMA stream)
@@ -251,6 +257,68 @@ __device__ __forceinline__ void issue_tile_half(uint32_t a_hi, uint32_t a_lo, ui
       } else {
         mma_f16_ab(d, ah0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_wide, acc);
         if (G::PREC == 3) mma_f16_ab(d + NB, al0 + ao, desc_hi, b0 + bo, bdesc_hi, idesc_narrow, 1u);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Weight-stationary form of the wide MMA (tcgen05.mma.ws, N = 64): B stays in collector buffer b<BUF> from the tile
+// that fills it to the tile that uses it last, so only the first tile of a row fetches the filter planes (measured:
+// 46.4 instead of 53.0 clk per MMA of a pair, scripts/tc_reuse_rate.py).  One buffer per issuer warp.
+//   OP: 0 fill, 1 use, 2 lastuse
+template <int BUF, int OP>
+__device__ __forceinline__ void mma_f16_ws(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+#define DDD1D_WS_ASM(BN, ON)                                                                                        \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"      \
+               "setp.ne.b32 p, %6, 0;\n\t"                                                                          \
+               "tcgen05.mma.ws.cta_group::1.kind::f16.collector::" BN "::" ON " [%0], da, db, %5, p;\n\t}" ::"r"(    \
+                   tmem_d),                                                                                         \
+               "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)                              \
+               : "memory")
+  if (BUF == 0) {
+    if (OP == 0) DDD1D_WS_ASM("b0", "fill"); else if (OP == 1) DDD1D_WS_ASM("b0", "use"); else DDD1D_WS_ASM("b0", "lastuse");
+  } else {
+    if (OP == 0) DDD1D_WS_ASM("b1", "fill"); else if (OP == 1) DDD1D_WS_ASM("b1", "use"); else DDD1D_WS_ASM("b1", "lastuse");
+  }
+#undef DDD1D_WS_ASM
+}
+
+// Every MMA of one layer for ALL tiles of a slot, tiles innermost: per (tap, ci-block) the wide MMAs of the tiles share
+// their B planes through the collector, then the narrow ones follow.  slot16: shared address (>> 4) of the slot's
+// first plane; d0: TMEM address of the slot's first tile block.
+template <class G, int NB, int BUF>
+__device__ __forceinline__ void issue_slot_ws(uint32_t slot16, uint32_t b, uint32_t d0) {
+  static_assert(G::TILES >= 2 && NB == 32 && G::PREC >= 2, "wide MMAs of width 64 over several tiles");
+  constexpr uint32_t plane16 = G::PLANE >> 4, bplane16 = (2u * NB * 16u) >> 4;
+  const uint32_t desc_hi = (G::SBO >> 4) | (1u << 14);
+  const uint32_t bdesc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t ah0 = (slot16 & 0x3FFFu) | (plane16 << 16);
+  const uint32_t al0 = ((slot16 + ((4u * G::PLANE) >> 4)) & 0x3FFFu) | (plane16 << 16);
+  const uint32_t b0 = (b & 0x3FFFu) | (bplane16 << 16);
+  const uint32_t idesc_wide = instr_desc_f16(128, 2 * NB), idesc_narrow = instr_desc_f16(128, NB);
+  if (elect_one()) {
+#pragma unroll
+    for (int k = 0; k < kTaps; ++k) {
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint32_t ao = (uint32_t)(2 * kb) * plane16 + (uint32_t)k;
+        const uint32_t bo = (uint32_t)(k * 4 + 2 * kb) * bplane16;
+        const uint32_t acc = (k == 0 && kb == 0) ? 0u : 1u;
+#pragma unroll
+        for (int m = 0; m < G::TILES; ++m) {
+          const uint32_t d = d0 + (uint32_t)(m * G::COLS), am = ah0 + ao + (uint32_t)m * 128u;
+          if (m == 0) mma_f16_ws<BUF, 0>(d, am, desc_hi, b0 + bo, bdesc_hi, idesc_wide, acc);
+          else if (m == G::TILES - 1) mma_f16_ws<BUF, 2>(d, am, desc_hi, b0 + bo, bdesc_hi, idesc_wide, acc);
+          else mma_f16_ws<BUF, 1>(d, am, desc_hi, b0 + bo, bdesc_hi, idesc_wide, acc);
+        }
+        if (G::PREC == 3) {
+#pragma unroll
+          for (int m = 0; m < G::TILES; ++m)
+            mma_f16_ab(d0 + (uint32_t)(m * G::COLS) + NB, al0 + ao + (uint32_t)m * 128u, desc_hi, b0 + bo, bdesc_hi,
+                       idesc_narrow, 1u);
+        }
       }
     }
   }
@@ -708,6 +776,25 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             } else {
             if (!(P.debug & 64)) mbar_wait_guarded(&bars[BAR_REQ + ts], parity);
             fence_after();
+            constexpr bool WS = DDD1D_TC_WS != 0 && TILES >= 2 && PREC >= 2;
+            bool ws_done = false;
+            if constexpr (WS) {
+              // all tiles of the slot in one pass, the filter planes fetched once per (tap, ci-block); one collector
+              // buffer per issuer warp
+              if (layer < nhid || NL == 32) {
+                const uint32_t d0 = tmem_u + (uint32_t)(ts * TILES * G::COLS);
+                if (!(P.debug & 1)) {
+                  const uint32_t bb = layer < nhid ? bh16 : bl16;
+                  if (issuer == 0) issue_slot_ws<G, 32, 0>(slot16, bb, d0);
+                  else issue_slot_ws<G, 32, 1>(slot16, bb, d0);
+                }
+                if (elect_one())
+                  for (int m = 0; m < TILES; ++m) mma_commit(&bars[BAR_DONE + ts * TILES + m]);
+                __syncwarp();
+                ws_done = true;
+              }
+            }
+            if (!ws_done) {
 #pragma unroll 1
             for (int m = 0; m < TILES; ++m) {
               const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
@@ -718,6 +805,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
               }
               if (elect_one()) mma_commit(&bars[BAR_DONE + ts * TILES + m]);
               __syncwarp();
+            }
             }
             }
             if constexpr (G::AMP) {
