@@ -87,6 +87,11 @@ struct TcParams {
 #define DDD1D_TC_SPLIT_REQ 0       // 1: request a layer per ci-block (measured: correct, 2.5 % slower at C2)
 #endif
 
+#ifndef DDD1D_TC_TILE_REQ
+#define DDD1D_TC_TILE_REQ 0        // 1: rows of several tiles request their layers per tile (measured: bit-identical,
+                                   // C2 -2.3 %, C4 -5 %: finer requests cost the issuers more waits than they start MMAs early)
+#endif
+
 #ifndef DDD1D_TC_WS
 #define DDD1D_TC_WS 0              // 1: the wide MMAs of rows of several tiles as tcgen05.mma.ws, B kept in a collector buffer
                                    // (measured: bit-identical results, C2 -0.9 %, C4 -7 %: tiles finish together instead of
@@ -127,7 +132,10 @@ struct Geo {
   // Split requests: a layer's MMAs over the first ci-block (chunk planes 0, 1) are requested as soon as those
   // planes are stored, half a phase before the rest, so only half a layer is still to run when the phase ends.
   static constexpr bool SPLIT = DDD1D_TC_SPLIT_REQ != 0;
-  static constexpr int REQS = SPLIT ? 2 : 1;          // request barriers per slot (one per ci-block)
+  // TREQ: a row of several tiles requests a layer PER TILE: tile m's MMAs start when its own four warps and the two
+  // neighbouring edge warps (whose positions are its halo) have stored their planes, not when the whole row has
+  static constexpr bool TREQ = DDD1D_TC_TILE_REQ != 0 && TILES >= 2 && SL == 2 && !SPLIT;
+  static constexpr int REQS = SPLIT ? 2 : TREQ ? TILES : 1;   // request barriers per slot (per ci-block | per tile)
   // mbarriers: [0] blob copy | [BAR_REQ + kb * TS + ts] "planes of ci-block kb stored" (one arrival per team warp)
   // | [BAR_DONE + blk * TILES + m] "tile's MMAs done" | pool only: [BAR_READ + blk] "block read"
   static constexpr int BAR_REQ = 1, BAR_DONE = BAR_REQ + REQS * TS, BAR_READ = BAR_DONE + BLOCKS * TILES;
@@ -647,7 +655,7 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
-    for (int t = 0; t < G::REQS * TS; ++t) mbar_init(&bars[BAR_REQ + t], (uint32_t)G::TEAM_WARPS);
+    for (int t = 0; t < G::REQS * TS; ++t) mbar_init(&bars[BAR_REQ + t], G::TREQ ? 6u : (uint32_t)G::TEAM_WARPS);
     for (int t = 0; t < BLOCKS * TILES; ++t) mbar_init(&bars[BAR_DONE + t], 1);
     if (POOL)
       for (int t = 0; t < BLOCKS; ++t) mbar_init(&bars[BAR_READ + t], (uint32_t)G::TEAM_WARPS);
@@ -774,9 +782,9 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
                 }
               }
             } else {
-            if (!(P.debug & 64)) mbar_wait_guarded(&bars[BAR_REQ + ts], parity);
+            if (!G::TREQ && !(P.debug & 64)) mbar_wait_guarded(&bars[BAR_REQ + ts], parity);
             fence_after();
-            constexpr bool WS = DDD1D_TC_WS != 0 && TILES >= 2 && PREC >= 2;
+            constexpr bool WS = DDD1D_TC_WS != 0 && TILES >= 2 && PREC >= 2 && !G::TREQ;
             bool ws_done = false;
             if constexpr (WS) {
               // all tiles of the slot in one pass, the filter planes fetched once per (tap, ci-block); one collector
@@ -797,6 +805,10 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
             if (!ws_done) {
 #pragma unroll 1
             for (int m = 0; m < TILES; ++m) {
+              if (G::TREQ) {
+                if (!(P.debug & 64)) mbar_wait_guarded(&bars[BAR_REQ + m * TS + ts], parity);
+                fence_after();
+              }
               const uint32_t a_hi = slot16 + (uint32_t)m * 128u, a_lo = a_hi + ((4u * G::PLANE) >> 4);
               const uint32_t d = tmem_u + (uint32_t)((ts * TILES + m) * G::COLS);
               if (!(P.debug & 1)) {
@@ -1111,7 +1123,14 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_s(req0 + 8u * (uint32_t)((SPLIT ? TS : 0) + sl));
+        if (G::TREQ) {
+          if (lane == 0) {
+            mbar_arrive_s(req0 + 8u * (uint32_t)(tile * TS + sl));
+            if (nb_tile >= 0) mbar_arrive_s(req0 + 8u * (uint32_t)(nb_tile * TS + sl));
+          }
+        } else if (lane == 0) {
+          mbar_arrive_s(req0 + 8u * (uint32_t)((SPLIT ? TS : 0) + sl));
+        }
         if (!G::AMP && forced && s == 0 && W.op == OP_INTEGRATE && step + 1 < nsteps) {
           // Forcing amplitudes of the NEXT step, off the critical path (the MMAs just requested are running).
           // One warp per (row, stage): one forcing term per lane, mode amplitudes by warp sums.  Three sets
@@ -1196,7 +1215,14 @@ tc_row_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Work W
         fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_s(req0 + 8u * (uint32_t)sl);
+        if (G::TREQ) {
+          if (lane == 0) {
+            mbar_arrive_s(req0 + 8u * (uint32_t)(tile * TS + sl));
+            if (nb_tile >= 0) mbar_arrive_s(req0 + 8u * (uint32_t)(nb_tile * TS + sl));
+          }
+        } else if (lane == 0) {
+          mbar_arrive_s(req0 + 8u * (uint32_t)sl);
+        }
         }
       };
 
