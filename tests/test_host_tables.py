@@ -115,6 +115,19 @@ def test_abi_exports_every_declared_symbol():
   assert ctypes.sizeof(_lib.Config) == 88
 
 
+def test_debug_library_exports_every_declared_symbol():
+  """The test-only library (include/ddd1d_debug.h): laboratory kernels, never loaded by the product path; no symbol
+  of it lives in the product library."""
+  header = open(os.path.join(ROOT, 'include', 'ddd1d_debug.h')).read()
+  declared = sorted(set(re.findall(r'\b(ddd1d_debug_[a-z0-9_]+)\s*\(', header)))
+  assert declared == sorted(_lib._DEBUG_SIGNATURES)
+  debug = _lib.load_debug()
+  product = _lib.load()
+  for name in declared:
+    assert getattr(debug, name) is not None
+    assert not hasattr(product, name)
+
+
 def test_create_rejects_bad_configs_without_gpu():
   """Argument validation happens before any CUDA call (the reference's ValueErrors)."""
   lib = _lib.load()
